@@ -1,0 +1,216 @@
+// TEST INFRASTRUCTURE — NOT PRODUCT CODE.
+//
+// C-ABI harness around the UNMODIFIED reference scan decoder.  oracle/Makefile compiles
+// /root/reference/source/{ImgDecode,WindowBuf,General}.cpp in place (never copied) against
+// oracle/compat/ and links them with this file into
+//     oracle/_ref/liboracle_ref_fixed.so   (-DIDCT_FIXEDPT: the integer IDCT north_star names)
+//     oracle/_ref/liboracle_ref_float.so   (shipping default: float IDCT)
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+// may load these libraries, and only as the checker / the reported CPU baseline.
+//
+// The harness owns one {CDocLog, CwindowBuf, CimgDecode} triple per context, exactly the
+// wiring of CJPEGsnoopCore (source/JPEGsnoopCore.cpp:38,46,53), and forwards the setter
+// sequence CjfifDecode issues (source/JfifDecode.cpp:3577-3600, 4648, 5008-5025, 5161,
+// 5291-5299).  ref_decode_jpeg() is a convenience that performs that marker walk itself.
+
+#include "stdafx.h"
+#define private public          // the harness reads m_pMcuFileMap, m_pBlkDcVal*, m_anDhtHisto ...
+#include "ImgDecode.h"
+#undef private
+#include "JPEGsnoop.h"
+
+#include <thread>
+#include <atomic>
+#include <memory>
+
+static CSnoopConfig   g_cfg;
+static CJPEGsnoopApp  g_app;
+CWinApp* AfxGetApp() { g_app.m_pAppConfig = &g_cfg; return &g_app; }
+
+struct RefCtx {
+	CDocLog      log;
+	CwindowBuf   wbuf;
+	CFile        file;
+	CimgDecode*  dec;
+	RefCtx() : dec(nullptr) { AfxGetApp(); dec = new CimgDecode(&log,&wbuf); }
+	~RefCtx() { delete dec; }
+};
+
+extern "C" {
+
+int ref_is_fixedpt(void) {
+#ifdef IDCT_FIXEDPT
+	return 1;
+#else
+	return 0;
+#endif
+}
+
+RefCtx* ref_create(void) { return new RefCtx(); }
+void    ref_destroy(RefCtx* c) { delete c; }
+
+// Global (process-wide) config, as in the reference (one CSnoopConfig per app).
+void ref_config(int decode_ac,int histo_en,unsigned err_max) {
+	g_cfg.bDecodeScanImgAc = decode_ac!=0;
+	g_cfg.bHistoEn = histo_en!=0;
+	g_cfg.nErrMaxDecodeScan = err_max;
+}
+
+void ref_set_file(RefCtx* c,const uint8_t* data,uint64_t n) {
+	c->file = CFile(data,n);
+	c->wbuf.BufFileSet(&c->file);
+	c->wbuf.BufLoadWindow(0);
+}
+
+void ref_Reset(RefCtx* c)      { c->dec->Reset(); }
+void ref_ResetState(RefCtx* c) { c->dec->ResetState(); }
+int  ref_SetDqtEntry(RefCtx* c,unsigned t,unsigned i,unsigned izz,unsigned v) { return c->dec->SetDqtEntry(t,i,izz,(unsigned short)v); }
+int  ref_SetDqtTables(RefCtx* c,unsigned comp,unsigned t) { return c->dec->SetDqtTables(comp,t); }
+int  ref_SetDhtTables(RefCtx* c,unsigned comp,unsigned dc,unsigned ac) { return c->dec->SetDhtTables(comp,dc,ac); }
+int  ref_SetDhtEntry(RefCtx* c,unsigned id,unsigned cls,unsigned ind,unsigned len,unsigned bits,unsigned mask,unsigned code) {
+	return c->dec->SetDhtEntry(id,cls,ind,len,bits,mask,code); }
+int  ref_SetDhtSize(RefCtx* c,unsigned id,unsigned cls,unsigned n) { return c->dec->SetDhtSize(id,cls,n); }
+void ref_SetPrecision(RefCtx* c,unsigned p) { c->dec->SetPrecision(p); }
+void ref_SetSofSampFactors(RefCtx* c,unsigned comp,unsigned h,unsigned v) { c->dec->SetSofSampFactors(comp,h,v); }
+void ref_SetImageDetails(RefCtx* c,unsigned x,unsigned y,unsigned nf,unsigned ns,int rst,unsigned ri) { c->dec->SetImageDetails(x,y,nf,ns,rst!=0,ri); }
+void ref_DecodeScanImg(RefCtx* c,unsigned start,int display,int quiet) { c->dec->DecodeScanImg(start,display!=0,quiet!=0); }
+
+void ref_GetImageSize(RefCtx* c,unsigned* x,unsigned* y) { c->dec->GetImageSize(*x,*y); }
+int  ref_IsPreviewReady(RefCtx* c) { return c->dec->IsPreviewReady(); }
+const int16_t* ref_pix_y(RefCtx* c)  { return c->dec->m_pPixValY; }
+const int16_t* ref_pix_cb(RefCtx* c) { return c->dec->m_pPixValCb; }
+const int16_t* ref_pix_cr(RefCtx* c) { return c->dec->m_pPixValCr; }
+const uint8_t* ref_dib(RefCtx* c)    { unsigned char* p=nullptr; c->dec->GetBitmapPtr(p); return p; }
+const uint32_t* ref_mcu_file_map(RefCtx* c) { return c->dec->m_pMcuFileMap; }
+const int16_t* ref_blk_dc_y(RefCtx* c)  { return c->dec->m_pBlkDcValY; }
+const int16_t* ref_blk_dc_cb(RefCtx* c) { return c->dec->m_pBlkDcValCb; }
+const int16_t* ref_blk_dc_cr(RefCtx* c) { return c->dec->m_pBlkDcValCr; }
+void ref_geometry(RefCtx* c,unsigned* out /*[8]*/) {
+	out[0]=c->dec->m_nMcuWidth; out[1]=c->dec->m_nMcuHeight; out[2]=c->dec->m_nMcuXMax; out[3]=c->dec->m_nMcuYMax;
+	out[4]=c->dec->m_nBlkXMax; out[5]=c->dec->m_nBlkYMax; out[6]=c->dec->m_nImgSizeX; out[7]=c->dec->m_nImgSizeY;
+}
+void ref_dht_histo(RefCtx* c,uint32_t* out /*[2][4][17]*/) { memcpy(out,c->dec->m_anDhtHisto,sizeof(c->dec->m_anDhtHisto)); }
+void ref_stats(RefCtx* c,int32_t* out /*[12]*/) {
+	out[0]=(int32_t)c->dec->m_nAvgY; out[1]=c->dec->m_bAvgYValid;
+	out[2]=c->dec->m_nBrightY; out[3]=c->dec->m_nBrightCb; out[4]=c->dec->m_nBrightCr;
+	out[5]=(int32_t)c->dec->m_nBrightR; out[6]=(int32_t)c->dec->m_nBrightG; out[7]=(int32_t)c->dec->m_nBrightB;
+	out[8]=c->dec->m_ptBrightMcu.x; out[9]=c->dec->m_ptBrightMcu.y;
+	out[10]=(int32_t)c->dec->m_nRestartRead; out[11]=c->dec->m_bScanBad;
+}
+void ref_idct_tables(RefCtx* c,float* lf /*[64][64]*/,int32_t* li /*[64][64]*/) {
+	memcpy(lf,c->dec->m_afIdctLookup,sizeof(c->dec->m_afIdctLookup));
+	memcpy(li,c->dec->m_anIdctLookup,sizeof(c->dec->m_anIdctLookup));
+}
+void ref_LookupFilePosMcu(RefCtx* c,unsigned mx,unsigned my,unsigned* byte,unsigned* bit) { c->dec->LookupFilePosMcu(mx,my,*byte,*bit); }
+void ref_LookupBlkYCC(RefCtx* c,unsigned bx,unsigned by,int* y,int* cb,int* cr) { c->dec->LookupBlkYCC(bx,by,*y,*cb,*cr); }
+
+int ref_num_err_lines(RefCtx* c)  { return (int)c->log.errs.size(); }
+int ref_num_warn_lines(RefCtx* c) { return (int)c->log.warns.size(); }
+int ref_num_lines(RefCtx* c)      { return (int)c->log.lines.size(); }
+const char* ref_err_line(RefCtx* c,int i) { return c->log.errs[(size_t)i].c_str(); }
+const char* ref_line(RefCtx* c,int i)     { return c->log.lines[(size_t)i].c_str(); }
+void ref_log_clear(RefCtx* c) { c->log.Clear(); }
+
+// ---------------------------------------------------------------------------------------
+// Convenience marker walk: SOI/DQT/SOF0-1/DHT/DRI/SOS -> the setter calls of
+// CjfifDecode::DecodeMarker (source/JfifDecode.cpp:3759...) -> DecodeScanImg(start,true,quiet).
+// Returns the scan start offset (>0) or a negative code; does not decode when do_decode==0.
+static int walk_and_decode(RefCtx* c,const uint8_t* d,uint64_t n,int do_decode,int quiet)
+{
+	extern const unsigned glb_anZigZag[64];
+	extern const unsigned glb_anUnZigZag[64];
+	ref_set_file(c,d,n);
+	c->dec->ResetState();
+	uint64_t p=0;
+	if (n<4 || d[0]!=0xFF || d[1]!=0xD8) return -1;
+	p=2;
+	unsigned X=0,Y=0,Nf=0,P=8; bool rstEn=false; unsigned ri=0;
+	while (p+4<=n) {
+		if (d[p]!=0xFF) return -2;
+		unsigned m=d[p+1]; p+=2;
+		if (m==0xFF) { p-=1; continue; }
+		if (m==0xD8 || (m>=0xD0 && m<=0xD7) || m==0x01) continue;
+		if (m==0xD9) return -3;
+		unsigned L=(d[p]<<8)|d[p+1];
+		uint64_t q=p+2, e=p+L;
+		if (e>n) return -4;
+		if (m==0xDB) {
+			while (q<e) {
+				unsigned pq=d[q]>>4, tq=d[q]&15; q++;
+				unsigned tbl[64];
+				for (unsigned i=0;i<64;i++) { unsigned v=d[q++]; if (pq) { v=(v<<8)|d[q++]; } tbl[glb_anZigZag[i]]=v; }
+				for (unsigned i=0;i<64;i++) c->dec->SetDqtEntry(tq,i,glb_anUnZigZag[i],(unsigned short)tbl[i]);
+			}
+		} else if (m==0xC0 || m==0xC1) {
+			P=d[q]; Y=(d[q+1]<<8)|d[q+2]; X=(d[q+3]<<8)|d[q+4]; Nf=d[q+5]; q+=6;
+			unsigned H[256],V[256],T[256];
+			for (unsigned i=1;i<=Nf;i++) { q++; H[i]=d[q]>>4; V[i]=d[q]&15; q++; T[i]=d[q++]; }
+			for (unsigned i=1;i<=Nf;i++) { c->dec->SetDqtTables(i,T[i]); c->dec->SetPrecision(P); }
+			for (unsigned i=1;i<=Nf;i++) c->dec->SetSofSampFactors(i,H[i],V[i]);
+		} else if (m==0xC4) {
+			while (q<e) {
+				unsigned tc=d[q]>>4, th=d[q]&15; q++;
+				unsigned li[17]; unsigned tot=0;
+				for (unsigned i=1;i<=16;i++) { li[i]=d[q++]; tot+=li[i]; }
+				const uint8_t* vals=d+q; q+=tot;
+				unsigned code=0, k=0, ind=0;
+				for (unsigned len=1;len<=16;len++) {
+					for (unsigned j=0;j<li[len];j++) {
+						unsigned mask=(unsigned)(((uint64_t)1<<len)-1)<<(32-len);
+						c->dec->SetDhtEntry(th,tc,ind,len,code<<(32-len),mask,vals[k]);
+						ind++; code++; k++;
+					}
+					code<<=1;
+				}
+				c->dec->SetDhtSize(th,tc,ind);
+			}
+		} else if (m==0xDD) {
+			ri=(d[q]<<8)|d[q+1]; rstEn=(ri!=0);
+		} else if (m==0xDA) {
+			unsigned Ns=d[q++];
+			for (unsigned i=1;i<=Ns;i++) { q++; unsigned t=d[q++]; c->dec->SetDhtTables(i,t>>4,t&15); }
+			unsigned start=(unsigned)e;
+			c->dec->SetImageDetails(X,Y,Nf,Ns,rstEn,ri);
+			if (do_decode) c->dec->DecodeScanImg(start,true,quiet!=0);
+			return (int)start;
+		}
+		p=e;
+	}
+	return -5;
+}
+
+int ref_decode_jpeg(RefCtx* c,const uint8_t* d,uint64_t n,int quiet) { return walk_and_decode(c,d,n,1,quiet); }
+int ref_setup_jpeg(RefCtx* c,const uint8_t* d,uint64_t n)  { return walk_and_decode(c,d,n,0,1); }
+
+// CPU baseline: `threads` workers, one {CDocLog,CwindowBuf,CimgDecode} each (the reference is
+// single-threaded; instances share only read-only globals), pulling images from a shared
+// counter.  Timed region = DecodeScanImg() only (tables already set) summed per image is not
+// what a batch user sees, so we time the wall clock of the whole pool and report that.
+// Returns seconds; *err_lines receives the number of error log lines seen.
+double ref_bench(const uint8_t* const* datas,const uint64_t* lens,int n,int threads,int reps,int* err_lines)
+{
+	if (threads<1) threads=1;
+	std::vector<std::unique_ptr<RefCtx>> ctx;
+	for (int t=0;t<threads;t++) ctx.emplace_back(new RefCtx());
+	std::atomic<int> next(0); std::atomic<int> errs(0);
+	int total=n*reps;
+	auto t0=std::chrono::steady_clock::now();
+	std::vector<std::thread> th;
+	for (int t=0;t<threads;t++) th.emplace_back([&,t]{
+		RefCtx* c=ctx[(size_t)t].get();
+		for (;;) {
+			int i=next.fetch_add(1); if (i>=total) break;
+			int k=i%n;
+			c->log.Clear();
+			int r=walk_and_decode(c,datas[k],lens[k],1,1);
+			if (r<0) errs.fetch_add(1);
+			errs.fetch_add((int)c->log.errs.size());
+		}
+	});
+	for (auto& x:th) x.join();
+	auto t1=std::chrono::steady_clock::now();
+	if (err_lines) *err_lines=errs.load();
+	return std::chrono::duration<double>(t1-t0).count();
+}
+
+} // extern "C"

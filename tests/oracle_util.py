@@ -1,0 +1,140 @@
+"""TEST INFRASTRUCTURE: ctypes front-end to the CPU oracles.
+
+Two oracles share one API shape:
+  * "port"          -> oracle/liboracle_port.so      (our plain-C restatement, oracle/port/)
+  * "ref_fixed/float" -> oracle/_ref/liboracle_ref_*.so (the UNMODIFIED reference compiled in place)
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+
+def build_oracles(quiet=True):
+    """Build the port always; the reference oracle only where /root/reference exists."""
+    out = subprocess.run(["make", "-C", ORACLE_DIR, "port", "ref"], capture_output=True, text=True)
+    if out.returncode != 0:
+        raise RuntimeError("oracle build failed:\n" + out.stdout[-2000:] + out.stderr[-2000:])
+    return out.stdout if not quiet else ""
+
+
+def ref_available(mode="fixed"):
+    return os.path.exists(os.path.join(ORACLE_DIR, "_ref", f"liboracle_ref_{mode}.so"))
+
+
+class Decoded:
+    """Plain container of one decode's outputs (numpy copies)."""
+    def __init__(self):
+        self.geom = None       # mcu_w, mcu_h, mcu_xmax, mcu_ymax, blk_xmax, blk_ymax, img_x, img_y
+        self.pix_y = self.pix_cb = self.pix_cr = None   # int16 [Hp, Wp]
+        self.dib = None        # uint8 [Hp, Wp, 4] BGRA bottom-up (row 0 = bottom image row)
+        self.mcu_map = None    # uint32 [mcu_ymax*mcu_xmax]
+        self.blk_dc = None     # tuple of int16 [blk_ymax*blk_xmax]
+        self.dht_histo = None  # uint32 [2,4,17]
+        self.stats = None      # int32[12]: avgY, avgValid, brightY,Cb,Cr,R,G,B, mcuX, mcuY, nRst, scanBad
+        self.nerr = 0
+        self.scan_start = 0
+
+
+class Oracle:
+    """One decoder instance of either oracle.  kind: 'port' | 'ref_fixed' | 'ref_float'.
+    For 'port', idct_fixed selects the arithmetic (True = -DIDCT_FIXEDPT semantics)."""
+
+    def __init__(self, kind="port", idct_fixed=True, decode_ac=True):
+        self.kind = kind
+        if kind == "port":
+            path = os.path.join(ORACLE_DIR, "liboracle_port.so")
+            self.p = "op_"
+        else:
+            path = os.path.join(ORACLE_DIR, "_ref", f"liboracle_{kind}.so")
+            self.p = "ref_"
+            idct_fixed = (kind == "ref_fixed")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.idct_fixed = idct_fixed
+        self.lib = L = C.CDLL(path)
+        f = self._f
+        f("create").restype = C.c_void_p
+        for n in ("pix_y", "pix_cb", "pix_cr", "blk_dc_y", "blk_dc_cb", "blk_dc_cr"):
+            f(n).restype = C.POINTER(C.c_int16)
+            f(n).argtypes = [C.c_void_p]
+        f("dib").restype = C.POINTER(C.c_uint8); f("dib").argtypes = [C.c_void_p]
+        f("mcu_file_map").restype = C.POINTER(C.c_uint32); f("mcu_file_map").argtypes = [C.c_void_p]
+        f("decode_jpeg").argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
+        f("setup_jpeg").argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        for n in ("geometry", "dht_histo", "stats"):
+            f(n).argtypes = [C.c_void_p, C.c_void_p]
+        f("idct_tables").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        f("num_err_lines").argtypes = [C.c_void_p]
+        f("destroy").argtypes = [C.c_void_p]
+        f("bench").restype = C.c_double
+        self.ctx = C.c_void_p(f("create")())
+        if kind == "port":
+            L.op_config.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint]
+            L.op_config(self.ctx, int(idct_fixed), int(decode_ac), 20)
+        else:
+            assert bool(L.ref_is_fixedpt()) == idct_fixed
+            L.ref_config(int(decode_ac), 0, 20)
+        self._keep = None
+
+    def _f(self, name):
+        return getattr(self.lib, self.p + name)
+
+    def close(self):
+        if self.ctx:
+            self._f("destroy")(self.ctx)
+            self.ctx = None
+
+    def idct_tables(self):
+        lf = np.zeros((64, 64), np.float32); li = np.zeros((64, 64), np.int32)
+        self._f("idct_tables")(self.ctx, lf.ctypes.data, li.ctypes.data)
+        return lf, li
+
+    def decode(self, jpeg_bytes):
+        """Marker walk + DecodeScanImg(start, bDisplay=true, bQuiet=true); returns Decoded."""
+        buf = np.frombuffer(jpeg_bytes, np.uint8).copy()
+        self._keep = buf
+        r = self._f("decode_jpeg")(self.ctx, buf.ctypes.data, buf.size, 1)
+        if r < 0:
+            raise ValueError(f"marker walk failed ({r})")
+        d = Decoded(); d.scan_start = r
+        g = np.zeros(8, np.uint32); self._f("geometry")(self.ctx, g.ctypes.data); d.geom = g
+        Wp, Hp = int(g[6]), int(g[7])
+        nblk = int(g[4]) * int(g[5]); nmcu = int(g[2]) * int(g[3])
+
+        def arr(ptr, shape):
+            if not ptr:
+                return None
+            return np.ctypeslib.as_array(ptr, shape=shape).copy()
+        d.pix_y = arr(self._f("pix_y")(self.ctx), (Hp, Wp))
+        d.pix_cb = arr(self._f("pix_cb")(self.ctx), (Hp, Wp))
+        d.pix_cr = arr(self._f("pix_cr")(self.ctx), (Hp, Wp))
+        d.dib = arr(self._f("dib")(self.ctx), (Hp, Wp, 4))
+        d.mcu_map = arr(self._f("mcu_file_map")(self.ctx), (nmcu,))
+        d.blk_dc = tuple(arr(self._f(n)(self.ctx), (nblk,)) for n in ("blk_dc_y", "blk_dc_cb", "blk_dc_cr"))
+        h = np.zeros((2, 4, 17), np.uint32); self._f("dht_histo")(self.ctx, h.ctypes.data); d.dht_histo = h
+        s = np.zeros(12, np.int32); self._f("stats")(self.ctx, s.ctypes.data); d.stats = s
+        d.nerr = self._f("num_err_lines")(self.ctx)
+        return d
+
+    def bench(self, jpegs, threads=1, reps=1):
+        """Wall seconds to decode every JPEG in `jpegs` `reps` times on `threads` host threads."""
+        bufs = [np.frombuffer(j, np.uint8).copy() for j in jpegs]
+        n = len(bufs)
+        ptrs = (C.c_void_p * n)(*[b.ctypes.data for b in bufs])
+        lens = (C.c_uint64 * n)(*[b.size for b in bufs])
+        errs = C.c_int(0)
+        if self.kind == "port":
+            t = self.lib.op_bench(ptrs, lens, n, threads, reps, int(self.idct_fixed), C.byref(errs))
+        else:
+            t = self.lib.ref_bench(ptrs, lens, n, threads, reps, C.byref(errs))
+        return float(t), int(errs.value)
+
+
+def dib_to_rgb(dib):
+    """BGRA bottom-up DIB [Hp,Wp,4] -> top-down RGB [Hp,Wp,3]."""
+    return dib[::-1, :, 2::-1]
