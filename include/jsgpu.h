@@ -1,0 +1,210 @@
+/* jsgpu.h — C-ABI of the B200 scan decoder (libjsgpu.so).
+ *
+ * This is the drop-in boundary for JPEGsnoop's per-MCU scan-decode path.  Everything above
+ * it (the CimgDecode class with the reference's public surface, see
+ * jpegsnoop_b200/csrc/host/ImgDecode.h) is host C++; everything below it is hand-written
+ * CUDA for sm_100a.  Signatures use plain pointers and sizes only.  Every entry point names
+ * the reference interface it replaces (paths relative to /root/reference/source).
+ *
+ * Conventions: every function returns JSGPU_OK (0) or a negative JSGPU_E* code and never
+ * throws; jsgpu_last_error() gives text for the last failure on that context.  A context is
+ * bound to one CUDA device and must be driven from one host thread at a time (the reference
+ * decoder is single-threaded and non-re-entrant too: ImgDecode.cpp:142-234).  The context
+ * owns all device memory; pointers it hands out stay valid until the next
+ * jsgpu_batch_begin() / jsgpu_free() on that context.  There is NO CPU fallback: without a
+ * CUDA device jsgpu_init() fails with JSGPU_ENODEV.
+ */
+#ifndef JSGPU_H
+#define JSGPU_H
+#include <stdint.h>
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JSGPU_OK          0
+#define JSGPU_ENODEV     -1   /* no usable CUDA device / driver                      */
+#define JSGPU_EINVAL     -2   /* bad argument or descriptor                          */
+#define JSGPU_ENOMEM     -3   /* device or pinned-host allocation failed             */
+#define JSGPU_ECUDA      -4   /* a CUDA call or kernel failed                        */
+#define JSGPU_ESTATE     -5   /* call out of order (e.g. decode before batch_begin)  */
+#define JSGPU_EUNSUP     -6   /* image not decodable by this path (as the reference: */
+                              /* Ns not in {1,3}, sampling factor > 4, ...)          */
+
+#define JSGPU_MAX_DHT_CODES 260     /* MAX_DHT_CODES, ImgDecode.h:68 */
+
+typedef struct jsgpu_ctx jsgpu_ctx;
+
+/* One set of decode tables = the state CimgDecode holds after CjfifDecode's DQT/DHT setter
+ * calls: m_anDqtCoeffZz (ImgDecode.h:570, filled by SetDqtEntry ImgDecode.cpp:424-453) and
+ * m_anDhtLookup_{bitlen,bits,code} + m_anDhtLookupSize (ImgDecode.h:609-613, filled by
+ * SetDhtEntry/SetDhtSize ImgDecode.cpp:748-847).  Entry order is the order of SetDhtEntry
+ * calls (canonical: length ascending, code ascending — JfifDecode.cpp:3535-3595); the
+ * decoder honours "first matching entry wins" (ImgDecode.cpp:1145-1164).  POD on purpose:
+ * this is the blob that is broadcast rank0 -> all ranks over NCCL before a multi-GPU batch. */
+typedef struct {
+    uint16_t dqt_zz[4][64];                          /* quantiser of zig-zag position k   */
+    uint32_t dht_size[2][4];                         /* [class DC=0/AC=1][Th]             */
+    uint32_t dht_bits[2][4][JSGPU_MAX_DHT_CODES];    /* code << (32-len), left-justified  */
+    uint8_t  dht_len [2][4][JSGPU_MAX_DHT_CODES];    /* code length 1..16                 */
+    uint8_t  dht_code[2][4][JSGPU_MAX_DHT_CODES];    /* symbol byte (run<<4 | size)       */
+} jsgpu_tables;
+
+/* One image of a batch = the arguments of SetImageDetails / SetSofSampFactors /
+ * SetDqtTables / SetDhtTables / SetPrecision (ImgDecode.cpp:505-624) plus where its
+ * entropy-coded segment lives inside the batch bitstream buffer (the nStart argument of
+ * DecodeScanImg, ImgDecode.cpp:2723).  Component arrays are indexed by component INDEX-1
+ * (index 1=Y,2=Cb,3=Cr as the reference addresses them: ImgDecode.cpp:3059-3061,3113-3118). */
+typedef struct {
+    uint32_t dim_x, dim_y;                /* SOF X,Y                                        */
+    uint32_t num_sof_comps, num_sos_comps;
+    uint32_t precision;                   /* SOF P (8 or 12)                                */
+    uint32_t restart_en, restart_interval;/* DRI                                            */
+    uint32_t samp_h[4], samp_v[4];
+    uint32_t dqt_sel[4];
+    uint32_t dht_dc_sel[4], dht_ac_sel[4];
+    uint32_t table_set;                   /* index into the sets given to upload_tables     */
+    uint32_t file_pos;                    /* file offset of scan_offset (for the MCU map)   */
+    uint64_t scan_offset;                 /* first ECS byte, offset into the batch bitstream */
+    uint64_t scan_length;                 /* bytes readable from scan_offset (to file end)   */
+} jsgpu_image_desc;
+
+/* Where image i's outputs live (element offsets into the pools below) and its geometry as
+ * derived by ImgDecode.cpp:2773-2872. */
+typedef struct {
+    uint32_t mcu_w, mcu_h, mcu_xmax, mcu_ymax, blk_xmax, blk_ymax;
+    uint32_t img_x, img_y;                /* padded size = GetImageSize()                   */
+    uint32_t num_segments;                /* restart intervals expected                     */
+    uint32_t status;                      /* after decode: 0 ok, else JSGPU_ST_* bits       */
+    uint64_t pix_off;                     /* int16 elements into pix_y/pix_cb/pix_cr pools   */
+    uint64_t dib_off;                     /* bytes into the DIB pool                         */
+    uint64_t blk_off;                     /* int16 elements into the block-DC pools          */
+    uint64_t mcu_off;                     /* uint32 elements into the MCU file-map pool      */
+} jsgpu_image_layout;
+
+#define JSGPU_ST_BADCODE   1u   /* no Huffman code matched (ImgDecode.cpp:1257-1282)        */
+#define JSGPU_ST_OVERRUN   2u   /* read past the end of a restart interval (:1096-1115)     */
+#define JSGPU_ST_COEFOVF   4u   /* nNumCoeffs > 64 (:1776-1797)                             */
+#define JSGPU_ST_MISSING   8u   /* fewer RSTn markers than the DRI interval implies (:3180) */
+#define JSGPU_ST_LEFTOVER 16u   /* data left in an interval after its last MCU              */
+
+typedef struct {
+    int32_t idct_mode;      /* 0 = integer IDCT (the -DIDCT_FIXEDPT build, ImgDecode.cpp:2402-2423,
+                               2512-2515; default), 1 = float IDCT (:2372-2392, 2517-2519)       */
+    int32_t decode_ac;      /* m_bDecodeScanAc (ImgDecode.cpp:1723-1725,1818); default 1          */
+    int32_t huff_kernel;    /* 0 = auto, 1 = one warp per restart interval, 2 = one lane per
+                               restart interval                                                   */
+    int32_t idct_kernel;    /* 0 = auto, 1 = simple reference kernels, 2 = fused tiled kernel    */
+    int32_t want_histo;     /* accumulate m_anDhtHisto (ImgDecode.cpp:1190-1191); default 1      */
+    int32_t want_mcu_map;   /* build m_pMcuFileMap (ImgDecode.cpp:3229); default 1               */
+    int32_t device_markers; /* 1 = find RSTn/end-of-scan on the GPU (default), 0 = host walk      */
+    int32_t reserved;
+} jsgpu_options;
+
+/* Device pointers of the output pools of the current batch (owned by the context). */
+typedef struct {
+    int16_t*  pix_y;  int16_t* pix_cb; int16_t* pix_cr;  /* m_pPixValY/Cb/Cr  (ImgDecode.h:454-456) */
+    uint8_t*  dib;                                       /* m_pDibTemp bits, BGRA bottom-up (:4786)  */
+    int16_t*  blk_y;  int16_t* blk_cb; int16_t* blk_cr;  /* m_pBlkDcValY/Cb/Cr (ImgDecode.h:459-461) */
+    uint32_t* mcu_map;                                   /* m_pMcuFileMap      (ImgDecode.h:444)     */
+    uint32_t* dht_histo;                                 /* [n][2][4][17]      (ImgDecode.h:615)     */
+    int32_t*  stats;                                     /* [n][16], see JSGPU_STAT_*               */
+    int16_t*  coef;                                      /* intermediate coefficient rows            */
+    uint8_t*  bitstream;                                 /* device copy of the batch bitstream       */
+} jsgpu_pools;
+
+/* stats[n][16] = the scalar results of CalcChannelPreviewFull (ImgDecode.cpp:4722-4730,4805-4819) */
+#define JSGPU_STAT_SUMY_LO   0   /* low/high 32 bits of the 64-bit sum of nFinalY              */
+#define JSGPU_STAT_SUMY_HI   1
+#define JSGPU_STAT_AVGY      2   /* m_nAvgY                                                     */
+#define JSGPU_STAT_BRIGHT_Y  3   /* m_nBrightY, Cb, Cr                                          */
+#define JSGPU_STAT_BRIGHT_CB 4
+#define JSGPU_STAT_BRIGHT_CR 5
+#define JSGPU_STAT_BRIGHT_R  6   /* m_nBrightR, G, B                                            */
+#define JSGPU_STAT_BRIGHT_G  7
+#define JSGPU_STAT_BRIGHT_B  8
+#define JSGPU_STAT_BRIGHT_MX 9   /* m_ptBrightMcu                                               */
+#define JSGPU_STAT_BRIGHT_MY 10
+#define JSGPU_STAT_NRST      11  /* m_nRestartRead                                              */
+#define JSGPU_STAT_WORDS     16
+
+/* Output selectors for jsgpu_batch_download */
+#define JSGPU_OUT_PIX_Y   0
+#define JSGPU_OUT_PIX_CB  1
+#define JSGPU_OUT_PIX_CR  2
+#define JSGPU_OUT_DIB     3
+#define JSGPU_OUT_BLK_Y   4
+#define JSGPU_OUT_BLK_CB  5
+#define JSGPU_OUT_BLK_CR  6
+#define JSGPU_OUT_MCU_MAP 7
+#define JSGPU_OUT_HISTO   8
+#define JSGPU_OUT_STATS   9
+
+/* --- lifetime -------------------------------------------------------------------------- */
+/* Replaces the CimgDecode constructor's device-independent setup (ImgDecode.cpp:142-234). */
+int  jsgpu_init(int device, jsgpu_ctx** out);
+void jsgpu_free(jsgpu_ctx* ctx);
+const char* jsgpu_last_error(const jsgpu_ctx* ctx);
+const char* jsgpu_strerror(int code);
+int  jsgpu_version(void);
+/* CUDA stream all work of this context is enqueued on (a cudaStream_t). */
+void* jsgpu_stream(jsgpu_ctx* ctx);
+int  jsgpu_sync(jsgpu_ctx* ctx);
+
+/* --- tables ---------------------------------------------------------------------------- */
+/* The IDCT look-up tables of PrecalcIdct (ImgDecode.cpp:2313-2351): li[yx*64+vu] =
+ * m_anIdctLookup, lf[yx*64+vu] = m_afIdctLookup.  They depend on the HOST libm's cosf, so the
+ * host computes them with the reference's expression and hands them over; the device never
+ * recomputes them. */
+int jsgpu_set_idct_tables(jsgpu_ctx* ctx, const int32_t* li, const float* lf);
+int jsgpu_set_options(jsgpu_ctx* ctx, const jsgpu_options* opt);
+int jsgpu_get_options(jsgpu_ctx* ctx, jsgpu_options* opt);
+/* Replaces SetDqtEntry / SetDhtEntry / SetDhtSize state (ImgDecode.cpp:424-453,748-847):
+ * builds the device look-up tables for `nsets` table sets. */
+int jsgpu_upload_tables(jsgpu_ctx* ctx, const jsgpu_tables* sets, uint32_t nsets);
+
+/* --- batch decode (replaces the body of CimgDecode::DecodeScanImg, ImgDecode.cpp:2723-3745,
+ *     i.e. HOT LOOPS 1-4 of SURVEY.md §3.3, for n images at once) ------------------------- */
+/* Geometry (ImgDecode.cpp:2773-2872), validation (:2755-2770,2821-2825,3047-3123) and device
+ * allocation (:2892-2987) for n images whose scan bytes occupy `bitstream_bytes` bytes.
+ * Images the reference would refuse get layout.status != 0 / JSGPU_EUNSUP semantics: they are
+ * skipped, exactly as DecodeScanImg returns early. */
+int jsgpu_batch_begin(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, uint64_t bitstream_bytes);
+int jsgpu_batch_layout(jsgpu_ctx* ctx, jsgpu_image_layout* out, uint32_t n);
+int jsgpu_batch_pools(jsgpu_ctx* ctx, jsgpu_pools* out);
+/* Copy the batch bitstream (host memory, pinned or pageable) to the device, asynchronously
+ * on the context stream.  Replaces the per-byte CwindowBuf::Buf() fetch
+ * (ImgDecode.cpp:1398-1399, WindowBuf.cpp:639-713). */
+int jsgpu_batch_upload(jsgpu_ctx* ctx, const uint8_t* host_bitstream, uint64_t bytes);
+/* Enqueue marker scan + Huffman + dequant/IDCT/upsample + colour conversion + statistics
+ * for the whole batch on the context stream (asynchronous). */
+int jsgpu_batch_decode(jsgpu_ctx* ctx);
+/* After jsgpu_sync(): per-image status words and scalar results are in the layout/stats. */
+int jsgpu_batch_download(jsgpu_ctx* ctx, int which, uint32_t image, void* host_dst, uint64_t bytes);
+/* Device-side times (ms) of the last jsgpu_batch_decode, measured with CUDA events on the
+ * context stream: [0] marker scan, [1] Huffman, [2] IDCT+colour, [3] stats/map finalise,
+ * [4] total.  Forces a sync. */
+int jsgpu_batch_stage_ms(jsgpu_ctx* ctx, float* ms5);
+/* Number of kernels launched by the last jsgpu_batch_decode. */
+int jsgpu_batch_launches(jsgpu_ctx* ctx);
+
+/* One-call end-to-end form: host bitstream in, host outputs out (any pointer may be NULL to
+ * skip that output).  Output buffers hold the images back to back in batch order using the
+ * element offsets of jsgpu_batch_layout.  H2D, decode and D2H run on the context stream. */
+typedef struct {
+    int16_t* pix_y; int16_t* pix_cb; int16_t* pix_cr; uint8_t* dib;
+    int16_t* blk_y; int16_t* blk_cb; int16_t* blk_cr; uint32_t* mcu_map;
+    uint32_t* dht_histo; int32_t* stats;
+} jsgpu_host_outputs;
+int jsgpu_decode_batch_host(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n,
+                            const uint8_t* host_bitstream, uint64_t bitstream_bytes,
+                            const jsgpu_host_outputs* out);
+
+/* Pinned host memory helpers (for callers that want true async copies). */
+void* jsgpu_host_alloc(uint64_t bytes);
+void  jsgpu_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JSGPU_H */

@@ -1,0 +1,506 @@
+// jsgpu_api.cu — the C-ABI of include/jsgpu.h: context, table upload, batch planning
+// (geometry / validation / allocation of ImgDecode.cpp:2755-3123 for n images), and the
+// enqueue of the kernels in jsgpu_kernels.cu.  No CPU decode path exists here: every
+// decode goes to the device or fails.
+#include "../../include/jsgpu.h"
+#include "jsgpu_internal.h"
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cstdarg>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#define JSGPU_VERSION 100
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct jsgpu_ctx {
+    int device = 0, sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {};
+    std::string err;
+    jsgpu_options opt;
+    bool have_idct = false;
+    // device state
+    DevBuf d_li, d_lf, d_tables, d_img, d_items, d_tiles;
+    DevBuf d_bits, d_seg, d_coef, d_mcubits, d_pix, d_dib, d_blk, d_mcumap, d_histo, d_stats, d_misc;
+    uint32_t nsets = 0;
+    // batch state
+    bool planned = false, decoded = false;
+    std::vector<DevImage> himg;
+    std::vector<jsgpu_image_layout> layout;
+    DevBatch batch;
+    uint64_t bits_len = 0, pix_total = 0, dib_total = 0, blk_total = 0, mcu_total = 0, coef_rows = 0;
+    uint64_t max_scan_len = 0;
+    int launches = 0;
+    float ms[5] = {0, 0, 0, 0, 0};
+};
+
+static int fail(jsgpu_ctx* c, int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, (e_ == cudaErrorMemoryAllocation) ? JSGPU_ENOMEM : JSGPU_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); } while (0)
+
+extern "C" {
+
+int jsgpu_version(void) { return JSGPU_VERSION; }
+
+const char* jsgpu_strerror(int code)
+{
+    switch (code) {
+    case JSGPU_OK: return "ok";
+    case JSGPU_ENODEV: return "no usable CUDA device";
+    case JSGPU_EINVAL: return "invalid argument";
+    case JSGPU_ENOMEM: return "out of memory";
+    case JSGPU_ECUDA: return "CUDA error";
+    case JSGPU_ESTATE: return "call out of order";
+    case JSGPU_EUNSUP: return "image not supported by the scan decoder";
+    default: return "unknown error";
+    }
+}
+const char* jsgpu_last_error(const jsgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int jsgpu_init(int device, jsgpu_ctx** out)
+{
+    if (!out) return JSGPU_EINVAL;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return JSGPU_ENODEV;       // no CPU fallback by design
+    if (device < 0 || device >= ndev) return JSGPU_EINVAL;
+    if (cudaSetDevice(device) != cudaSuccess) return JSGPU_ENODEV;
+    jsgpu_ctx* ctx = new jsgpu_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return JSGPU_ENODEV; }
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return JSGPU_ECUDA; }
+    for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+    memset(&ctx->opt, 0, sizeof ctx->opt);
+    ctx->opt.decode_ac = 1; ctx->opt.want_histo = 1; ctx->opt.want_mcu_map = 1; ctx->opt.device_markers = 1;
+    memset(&ctx->batch, 0, sizeof ctx->batch);
+    *out = ctx;
+    return JSGPU_OK;
+}
+
+void jsgpu_free(jsgpu_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf* bufs[] = { &ctx->d_li, &ctx->d_lf, &ctx->d_tables, &ctx->d_img, &ctx->d_items, &ctx->d_tiles, &ctx->d_bits, &ctx->d_seg,
+                       &ctx->d_coef, &ctx->d_mcubits, &ctx->d_pix, &ctx->d_dib, &ctx->d_blk, &ctx->d_mcumap, &ctx->d_histo, &ctx->d_stats, &ctx->d_misc };
+    for (auto* b : bufs) b->release();
+    for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+void* jsgpu_stream(jsgpu_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int jsgpu_sync(jsgpu_ctx* ctx)
+{
+    if (!ctx) return JSGPU_EINVAL;
+    cudaSetDevice(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    return JSGPU_OK;
+}
+
+int jsgpu_set_idct_tables(jsgpu_ctx* ctx, const int32_t* li, const float* lf)
+{
+    if (!ctx || !li || !lf) return JSGPU_EINVAL;
+    cudaSetDevice(ctx->device);
+    CK(ctx->d_li.reserve(64 * 64 * 4)); CK(ctx->d_lf.reserve(64 * 64 * 4));
+    CK(cudaMemcpyAsync(ctx->d_li.p, li, 64 * 64 * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_lf.p, lf, 64 * 64 * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->have_idct = true;
+    return JSGPU_OK;
+}
+
+int jsgpu_set_options(jsgpu_ctx* ctx, const jsgpu_options* opt)
+{
+    if (!ctx || !opt) return JSGPU_EINVAL;
+    if (opt->idct_mode < 0 || opt->idct_mode > 1) return fail(ctx, JSGPU_EINVAL, "idct_mode must be 0 (integer) or 1 (float)");
+    ctx->opt = *opt;
+    return JSGPU_OK;
+}
+int jsgpu_get_options(jsgpu_ctx* ctx, jsgpu_options* opt) { if (!ctx || !opt) return JSGPU_EINVAL; *opt = ctx->opt; return JSGPU_OK; }
+
+// zig-zag position -> natural index (T.81 Figure A.6; same permutation as glb_anZigZag, General.cpp:257-267)
+static const uint8_t kZigZagNat[64] = {
+     0, 1, 8,16, 9, 2, 3,10, 17,24,32,25,18,11, 4, 5, 12,19,26,33,40,48,41,34, 27,20,13, 6, 7,14,21,28,
+    35,42,49,56,57,50,43,36, 29,22,15,23,30,37,44,51, 58,59,52,45,38,31,39,46, 53,60,61,54,47,55,62,63 };
+
+// Build the device decode tables of one set.  The direct LUT must give exactly what
+// ReadScanVal's "first matching entry in SetDhtEntry order" search gives (ImgDecode.cpp:1145-1164):
+// for each JS_LUT_BITS-bit prefix we walk the entries in order; a short entry that matches decides
+// the prefix, a longer entry that COULD match sends the prefix to the slow in-order search.
+static void build_table_set(const jsgpu_tables& t, DevTableSet& d)
+{
+    memset(&d, 0, sizeof d);
+    for (int cls = 0; cls < 2; cls++) for (int id = 0; id < 4; id++) {
+        int slot = cls * 4 + id;
+        uint32_t n = std::min<uint32_t>(t.dht_size[cls][id], JS_MAX_CODES);
+        d.ent_n[slot] = n;
+        for (uint32_t i = 0; i < n; i++) {
+            uint32_t len = t.dht_len[cls][id][i];
+            d.ent_len[slot][i] = (uint8_t)len;
+            uint32_t mask = (len >= 1 && len <= 32) ? (0xffffffffu << (32 - len)) : 0;
+            d.ent_bits[slot][i] = t.dht_bits[cls][id][i] & mask;
+            d.ent_sym[slot][i] = t.dht_code[cls][id][i];
+        }
+        for (uint32_t p = 0; p < JS_LUT_SIZE; p++) {
+            uint32_t top = p << (32 - JS_LUT_BITS);
+            uint16_t e = 0;
+            for (uint32_t i = 0; i < n; i++) {
+                uint32_t len = d.ent_len[slot][i];
+                if (len == 0 || len > 16) continue;
+                if (len <= JS_LUT_BITS) {
+                    uint32_t mask = 0xffffffffu << (32 - len);
+                    if ((top & mask) == d.ent_bits[slot][i]) { e = (uint16_t)((len << 8) | d.ent_sym[slot][i]); break; }
+                } else {
+                    uint32_t mask = 0xffffffffu << (32 - JS_LUT_BITS);
+                    if ((d.ent_bits[slot][i] & mask) == top) { e = 0; break; }    // undecidable from the prefix alone
+                }
+            }
+            d.lut[slot][p] = e;
+        }
+    }
+    for (int q = 0; q < 4; q++) for (int k = 0; k < 64; k++) d.qz[q][k] = (uint32_t)t.dqt_zz[q][k] | ((uint32_t)kZigZagNat[k] << 16);
+}
+
+int jsgpu_upload_tables(jsgpu_ctx* ctx, const jsgpu_tables* sets, uint32_t nsets)
+{
+    if (!ctx || !sets || nsets == 0) return JSGPU_EINVAL;
+    cudaSetDevice(ctx->device);
+    std::vector<DevTableSet> h(nsets);
+    for (uint32_t i = 0; i < nsets; i++) build_table_set(sets[i], h[i]);
+    CK(ctx->d_tables.reserve(sizeof(DevTableSet) * (size_t)nsets));
+    CK(cudaMemcpyAsync(ctx->d_tables.p, h.data(), sizeof(DevTableSet) * (size_t)nsets, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->nsets = nsets;
+    return JSGPU_OK;
+}
+
+static inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+// Geometry + validation for one image: ImgDecode.cpp:2755-2872, 3029-3123.  Returns false when the
+// reference's DecodeScanImg would return before decoding.
+static bool plan_image(const jsgpu_image_desc& d, uint32_t nsets, DevImage& im)
+{
+    memset(&im, 0, sizeof im);
+    uint32_t ns = d.num_sos_comps;
+    if (ns != 1 && ns != 3) return false;                                  // :2764-2770
+    if (d.num_sof_comps != 1 && d.num_sof_comps != 3) return false;        // :3029-3035
+    if (d.table_set >= nsets) return false;
+    uint32_t H[3], V[3];
+    for (uint32_t c = 0; c < ns; c++) { H[c] = d.samp_h[c]; V[c] = d.samp_v[c]; }
+    uint32_t hmax = 0, vmax = 0;
+    for (uint32_t c = 0; c < ns; c++) { hmax = std::max(hmax, H[c]); vmax = std::max(vmax, V[c]); }
+    if (ns == 1) { H[0] = V[0] = 1; hmax = vmax = 1; }                     // :2805-2817
+    if (hmax == 0 || vmax == 0 || hmax > 4 || vmax > 4) return false;      // :2821-2825
+    for (uint32_t c = 0; c < ns; c++) if (H[c] == 0 || V[c] == 0) return false;
+    for (uint32_t c = 0; c < ns; c++) if (d.dqt_sel[c] > 3 || d.dht_dc_sel[c] > 3 || d.dht_ac_sel[c] > 3) return false;
+    im.dim_x = d.dim_x; im.dim_y = d.dim_y; im.ns = ns; im.precision = d.precision;
+    im.mcu_w = hmax * 8; im.mcu_h = vmax * 8;
+    im.mcu_xmax = d.dim_x / im.mcu_w + ((d.dim_x % im.mcu_w) ? 1 : 0);
+    im.mcu_ymax = d.dim_y / im.mcu_h + ((d.dim_y % im.mcu_h) ? 1 : 0);
+    im.blk_xmax = im.mcu_xmax * hmax; im.blk_ymax = im.mcu_ymax * vmax;
+    if (im.blk_xmax == 0 || im.blk_ymax == 0) return false;                // :2866-2868
+    im.wp = im.mcu_xmax * im.mcu_w; im.hp = im.mcu_ymax * im.mcu_h;
+    im.nmcu = im.mcu_xmax * im.mcu_ymax;
+    im.bpm = 0;
+    for (uint32_t c = 0; c < ns; c++) {
+        im.H[c] = H[c]; im.V[c] = V[c];
+        im.eh[c] = hmax / H[c]; im.ev[c] = vmax / V[c];                    // :2836-2839
+        if (im.eh[c] == 0 || im.ev[c] == 0) return false;
+        im.cw[c] = im.mcu_xmax * H[c]; im.ch[c] = im.mcu_ymax * V[c];
+        im.bpm += H[c] * V[c];
+        im.slot_dc[c] = d.dht_dc_sel[c]; im.slot_ac[c] = 4 + d.dht_ac_sel[c];
+        im.dqt[c] = d.dqt_sel[c];
+    }
+    im.restart_en = (d.restart_en && d.restart_interval) ? 1 : 0;
+    im.ri = im.restart_en ? d.restart_interval : im.nmcu;
+    im.nseg = (im.nmcu + im.ri - 1) / im.ri;
+    im.table_set = d.table_set; im.file_pos = d.file_pos;
+    im.scan_off = d.scan_offset; im.scan_len = d.scan_length;
+    im.valid = 1;
+    return true;
+}
+
+int jsgpu_batch_begin(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, uint64_t bitstream_bytes)
+{
+    if (!ctx || !imgs || n == 0) return JSGPU_EINVAL;
+    if (!ctx->have_idct) return fail(ctx, JSGPU_ESTATE, "jsgpu_set_idct_tables() has not been called");
+    if (ctx->nsets == 0) return fail(ctx, JSGPU_ESTATE, "jsgpu_upload_tables() has not been called");
+    cudaSetDevice(ctx->device);
+    ctx->planned = false; ctx->decoded = false;
+    ctx->himg.assign(n, DevImage());
+    ctx->layout.assign(n, jsgpu_image_layout());
+    uint64_t pix = 0, dib = 0, blk = 0, mcu = 0, rows = 0, max_scan = 0;
+    uint32_t seg = 0;
+    std::vector<uint2> items;
+    for (uint32_t i = 0; i < n; i++) {
+        DevImage& im = ctx->himg[i];
+        jsgpu_image_layout& lo = ctx->layout[i];
+        memset(&lo, 0, sizeof lo);
+        bool ok = plan_image(imgs[i], ctx->nsets, im);
+        if (ok && (imgs[i].scan_offset > bitstream_bytes || imgs[i].scan_length > bitstream_bytes - imgs[i].scan_offset))
+            return fail(ctx, JSGPU_EINVAL, "image %u: scan [%llu,+%llu) outside the %llu-byte bitstream", i,
+                        (unsigned long long)imgs[i].scan_offset, (unsigned long long)imgs[i].scan_length, (unsigned long long)bitstream_bytes);
+        if (ok && imgs[i].scan_length >= 0xfffffff0ull) return fail(ctx, JSGPU_EINVAL, "image %u: scan longer than 4 GiB", i);
+        if (!ok) { im.valid = 0; lo.status = 0x80000000u; continue; }
+        im.pix_off = pix; im.dib_off = dib; im.blk_off = blk; im.mcu_off = mcu; im.seg_first = seg;
+        for (uint32_t c = 0; c < im.ns; c++) { im.coef_row[c] = rows; rows += (uint64_t)im.cw[c] * im.ch[c]; }
+        uint64_t npx = (uint64_t)im.wp * im.hp;
+        pix += align_up(npx, 64); dib += align_up(npx * 4, 256); blk += align_up((uint64_t)im.blk_xmax * im.blk_ymax, 64);
+        mcu += align_up(im.nmcu, 32); seg += im.nseg;
+        max_scan = std::max(max_scan, im.scan_len);
+        im.item_first = (uint32_t)items.size();
+        for (uint32_t k = 0; k < im.nseg; k += JS_HUFF_WARPS) items.push_back(make_uint2(i, k));
+        im.nitems = (uint32_t)items.size() - im.item_first;
+        lo.mcu_w = im.mcu_w; lo.mcu_h = im.mcu_h; lo.mcu_xmax = im.mcu_xmax; lo.mcu_ymax = im.mcu_ymax;
+        lo.blk_xmax = im.blk_xmax; lo.blk_ymax = im.blk_ymax; lo.img_x = im.wp; lo.img_y = im.hp;
+        lo.num_segments = im.nseg; lo.pix_off = im.pix_off; lo.dib_off = im.dib_off; lo.blk_off = im.blk_off; lo.mcu_off = im.mcu_off;
+    }
+    ctx->bits_len = bitstream_bytes; ctx->pix_total = pix; ctx->dib_total = dib; ctx->blk_total = blk; ctx->mcu_total = mcu;
+    ctx->coef_rows = rows; ctx->max_scan_len = max_scan;
+    // allocate
+    CK(ctx->d_img.reserve(sizeof(DevImage) * (size_t)n));
+    CK(ctx->d_items.reserve(sizeof(uint2) * std::max<size_t>(items.size(), 1)));
+    CK(ctx->d_bits.reserve(bitstream_bytes + 64));
+    CK(ctx->d_seg.reserve(sizeof(uint32_t) * (4 * (size_t)seg + 2 * (size_t)n + 16)));
+    CK(ctx->d_coef.reserve(rows * 128 + 128));
+    CK(ctx->d_mcubits.reserve(mcu * 4 + 16));
+    CK(ctx->d_pix.reserve(pix * 2 * 3 + 64));
+    CK(ctx->d_dib.reserve(dib + 64));
+    CK(ctx->d_blk.reserve(blk * 2 * 3 + 64));
+    CK(ctx->d_mcumap.reserve(mcu * 4 + 16));
+    CK(ctx->d_histo.reserve((size_t)n * 2 * 4 * 17 * 4));
+    CK(ctx->d_stats.reserve((size_t)n * 16 * 4));
+    CK(ctx->d_misc.reserve((size_t)n * (8 + 8 + 4) + 64));
+    CK(cudaMemcpyAsync(ctx->d_img.p, ctx->himg.data(), sizeof(DevImage) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    if (!items.empty()) CK(cudaMemcpyAsync(ctx->d_items.p, items.data(), sizeof(uint2) * items.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));      // `items` is a local
+    DevBatch& b = ctx->batch;
+    memset(&b, 0, sizeof b);
+    b.img = (const DevImage*)ctx->d_img.p; b.tables = (const DevTableSet*)ctx->d_tables.p; b.nimg = n;
+    b.bits = (const uint8_t*)ctx->d_bits.p; b.bits_len = bitstream_bytes;
+    uint32_t* sp = (uint32_t*)ctx->d_seg.p;
+    b.seg_start = sp; b.seg_end = sp + seg; b.seg_endbits = sp + 2 * (size_t)seg; b.seg_status = sp + 3 * (size_t)seg;
+    b.scan_end = sp + 4 * (size_t)seg; b.nseg_found = b.scan_end + n; b.nseg_total = seg;
+    b.items = (const uint2*)ctx->d_items.p; b.nitems = (uint32_t)items.size();
+    b.coef = (int16_t*)ctx->d_coef.p; b.mcu_bitpos = (uint32_t*)ctx->d_mcubits.p;
+    b.pix_y = (int16_t*)ctx->d_pix.p; b.pix_cb = b.pix_y + pix; b.pix_cr = b.pix_cb + pix;
+    b.dib = (uint8_t*)ctx->d_dib.p;
+    b.blk_y = (int16_t*)ctx->d_blk.p; b.blk_cb = b.blk_y + blk; b.blk_cr = b.blk_cb + blk;
+    b.mcu_map = (uint32_t*)ctx->d_mcumap.p;
+    b.histo = (uint32_t*)ctx->d_histo.p; b.stats = (int32_t*)ctx->d_stats.p;
+    b.bright_key = (unsigned long long*)ctx->d_misc.p; b.sum_y = b.bright_key + n; b.img_status = (uint32_t*)(b.sum_y + n);
+    ctx->planned = true;
+    return JSGPU_OK;
+}
+
+int jsgpu_batch_layout(jsgpu_ctx* ctx, jsgpu_image_layout* out, uint32_t n)
+{
+    if (!ctx || !out) return JSGPU_EINVAL;
+    if (!ctx->planned) return fail(ctx, JSGPU_ESTATE, "no batch planned");
+    if (n > ctx->layout.size()) n = (uint32_t)ctx->layout.size();
+    if (ctx->decoded) {
+        cudaSetDevice(ctx->device);
+        std::vector<uint32_t> st(ctx->layout.size());
+        CK(cudaMemcpyAsync(st.data(), ctx->batch.img_status, st.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (size_t i = 0; i < st.size(); i++) if (ctx->himg[i].valid) ctx->layout[i].status = st[i];
+    }
+    memcpy(out, ctx->layout.data(), sizeof(jsgpu_image_layout) * n);
+    return JSGPU_OK;
+}
+
+int jsgpu_batch_pools(jsgpu_ctx* ctx, jsgpu_pools* out)
+{
+    if (!ctx || !out) return JSGPU_EINVAL;
+    if (!ctx->planned) return fail(ctx, JSGPU_ESTATE, "no batch planned");
+    const DevBatch& b = ctx->batch;
+    out->pix_y = b.pix_y; out->pix_cb = b.pix_cb; out->pix_cr = b.pix_cr; out->dib = b.dib;
+    out->blk_y = b.blk_y; out->blk_cb = b.blk_cb; out->blk_cr = b.blk_cr; out->mcu_map = b.mcu_map;
+    out->dht_histo = b.histo; out->stats = b.stats; out->coef = b.coef; out->bitstream = (uint8_t*)ctx->d_bits.p;
+    return JSGPU_OK;
+}
+
+int jsgpu_batch_upload(jsgpu_ctx* ctx, const uint8_t* host, uint64_t bytes)
+{
+    if (!ctx || !host) return JSGPU_EINVAL;
+    if (!ctx->planned) return fail(ctx, JSGPU_ESTATE, "no batch planned");
+    if (bytes > ctx->bits_len) return fail(ctx, JSGPU_EINVAL, "upload larger than the planned bitstream");
+    cudaSetDevice(ctx->device);
+    CK(cudaMemcpyAsync(ctx->d_bits.p, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return JSGPU_OK;
+}
+
+// Host form of the marker walk (used when opt.device_markers == 0): the PASS-1 byte walk of
+// CjfifDecode (JfifDecode.cpp:5207-5265) extended to record every RSTn position.
+static int host_marker_walk(jsgpu_ctx* ctx, const uint8_t* bits_host)
+{
+    const DevBatch& b = ctx->batch;
+    std::vector<uint32_t> seg(4 * (size_t)b.nseg_total + 2 * (size_t)b.nimg, 0);
+    uint32_t* s_start = seg.data(); uint32_t* s_end = s_start + b.nseg_total;
+    uint32_t* scan_end = seg.data() + 4 * (size_t)b.nseg_total; uint32_t* nfound = scan_end + b.nimg;
+    std::vector<int32_t> nrst(b.nimg, 0);
+    for (uint32_t i = 0; i < b.nimg; i++) {
+        const DevImage& im = ctx->himg[i];
+        if (!im.valid) continue;
+        const uint8_t* p = bits_host + im.scan_off; uint64_t n = im.scan_len;
+        uint32_t k = 0, endpos = (uint32_t)n;
+        s_start[im.seg_first] = 0;
+        for (uint64_t q = 0; q + 1 < n; q++) {
+            if (p[q] != 0xFF) continue;
+            uint8_t m = p[q + 1];
+            if (m >= 0xD0 && m <= 0xD7) {
+                if (k < im.nseg) s_end[im.seg_first + k] = (uint32_t)q;
+                if (k + 1 < im.nseg) s_start[im.seg_first + k + 1] = (uint32_t)q + 2;
+                k++; q++;
+            } else if (m != 0x00 && m != 0xFF) { endpos = (uint32_t)q; break; }
+        }
+        uint32_t nf = k + 1;
+        if (nf <= im.nseg) s_end[im.seg_first + nf - 1] = endpos;
+        for (uint32_t j = nf; j < im.nseg; j++) { s_start[im.seg_first + j] = endpos; s_end[im.seg_first + j] = endpos; }
+        scan_end[i] = endpos; nfound[i] = nf; nrst[i] = (int32_t)k;
+    }
+    cudaMemcpyAsync(b.seg_start, s_start, 2 * (size_t)b.nseg_total * 4, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(b.scan_end, scan_end, 2 * (size_t)b.nimg * 4, cudaMemcpyHostToDevice, ctx->stream);
+    for (uint32_t i = 0; i < b.nimg; i++)
+        cudaMemcpyAsync(b.stats + (size_t)i * 16 + 11, &nrst[i], 4, cudaMemcpyHostToDevice, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    return 0;
+}
+
+int jsgpu_batch_decode(jsgpu_ctx* ctx)
+{
+    if (!ctx) return JSGPU_EINVAL;
+    if (!ctx->planned) return fail(ctx, JSGPU_ESTATE, "no batch planned");
+    cudaSetDevice(ctx->device);
+    DevBatch& b = ctx->batch;
+    b.decode_ac = ctx->opt.decode_ac; b.want_histo = ctx->opt.want_histo; b.idct_mode = ctx->opt.idct_mode;
+    cudaStream_t s = ctx->stream;
+    int launches = 0;
+    CK(cudaEventRecord(ctx->ev[0], s));
+    // clear accumulators (the reference memsets its maps: ImgDecode.cpp:2900,2924-2928,2965)
+    CK(cudaMemsetAsync(b.histo, 0, (size_t)b.nimg * 2 * 4 * 17 * 4, s));
+    CK(cudaMemsetAsync(b.stats, 0, (size_t)b.nimg * 16 * 4, s));
+    CK(cudaMemsetAsync(b.bright_key, 0, (size_t)b.nimg * (8 + 8 + 4), s));
+    CK(cudaMemsetAsync(b.mcu_map, 0, ctx->mcu_total * 4, s));
+    if (ctx->opt.device_markers) launches += js_launch_marker_scan(b, ctx->max_scan_len, s);
+    else {
+        std::vector<uint8_t> hb(ctx->bits_len);
+        CK(cudaMemcpyAsync(hb.data(), ctx->d_bits.p, ctx->bits_len, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        host_marker_walk(ctx, hb.data());
+    }
+    CK(cudaEventRecord(ctx->ev[1], s));
+    if (ctx->opt.huff_kernel == 2) launches += js_launch_huffman_lane(b, ctx->sm_count, s);
+    else launches += js_launch_huffman_warp(b, ctx->sm_count, s);
+    CK(cudaEventRecord(ctx->ev[2], s));
+    if (ctx->opt.idct_kernel == 1) launches += js_launch_idct_simple(b, (const int32_t*)ctx->d_li.p, (const float*)ctx->d_lf.p, 0, 0, s);
+    else launches += js_launch_idct_fused(b, (const int32_t*)ctx->d_li.p, (const float*)ctx->d_lf.p, ctx->sm_count, s);
+    CK(cudaEventRecord(ctx->ev[3], s));
+    {
+        DevBatch bf = b;
+        if (!ctx->opt.want_mcu_map) bf.mcu_map = nullptr;
+        launches += js_launch_finalize(bf, s);
+    }
+    CK(cudaEventRecord(ctx->ev[4], s));
+    CK(cudaGetLastError());
+    ctx->launches = launches;
+    ctx->decoded = true;
+    return JSGPU_OK;
+}
+
+int jsgpu_batch_launches(jsgpu_ctx* ctx) { return ctx ? ctx->launches : JSGPU_EINVAL; }
+
+int jsgpu_batch_stage_ms(jsgpu_ctx* ctx, float* ms5)
+{
+    if (!ctx || !ms5) return JSGPU_EINVAL;
+    if (!ctx->decoded) return fail(ctx, JSGPU_ESTATE, "nothing decoded yet");
+    cudaSetDevice(ctx->device);
+    CK(cudaEventSynchronize(ctx->ev[4]));
+    for (int i = 0; i < 4; i++) CK(cudaEventElapsedTime(&ms5[i], ctx->ev[i], ctx->ev[i + 1]));
+    CK(cudaEventElapsedTime(&ms5[4], ctx->ev[0], ctx->ev[4]));
+    return JSGPU_OK;
+}
+
+int jsgpu_batch_download(jsgpu_ctx* ctx, int which, uint32_t image, void* dst, uint64_t bytes)
+{
+    if (!ctx || !dst) return JSGPU_EINVAL;
+    if (!ctx->decoded) return fail(ctx, JSGPU_ESTATE, "nothing decoded yet");
+    if (image >= ctx->himg.size()) return fail(ctx, JSGPU_EINVAL, "image index out of range");
+    cudaSetDevice(ctx->device);
+    const DevImage& im = ctx->himg[image]; const DevBatch& b = ctx->batch;
+    if (!im.valid) return fail(ctx, JSGPU_EUNSUP, "image %u was not decoded", image);
+    const void* src = nullptr; uint64_t avail = 0;
+    uint64_t npx = (uint64_t)im.wp * im.hp, nblk = (uint64_t)im.blk_xmax * im.blk_ymax;
+    switch (which) {
+    case JSGPU_OUT_PIX_Y:  src = b.pix_y + im.pix_off; avail = npx * 2; break;
+    case JSGPU_OUT_PIX_CB: src = b.pix_cb + im.pix_off; avail = (im.ns == 3) ? npx * 2 : 0; break;
+    case JSGPU_OUT_PIX_CR: src = b.pix_cr + im.pix_off; avail = (im.ns == 3) ? npx * 2 : 0; break;
+    case JSGPU_OUT_DIB:    src = b.dib + im.dib_off; avail = npx * 4; break;
+    case JSGPU_OUT_BLK_Y:  src = b.blk_y + im.blk_off; avail = nblk * 2; break;
+    case JSGPU_OUT_BLK_CB: src = b.blk_cb + im.blk_off; avail = (im.ns == 3) ? nblk * 2 : 0; break;
+    case JSGPU_OUT_BLK_CR: src = b.blk_cr + im.blk_off; avail = (im.ns == 3) ? nblk * 2 : 0; break;
+    case JSGPU_OUT_MCU_MAP: src = b.mcu_map + im.mcu_off; avail = (uint64_t)im.nmcu * 4; break;
+    case JSGPU_OUT_HISTO:  src = b.histo + (size_t)image * 2 * 4 * 17; avail = 2 * 4 * 17 * 4; break;
+    case JSGPU_OUT_STATS:  src = b.stats + (size_t)image * 16; avail = 16 * 4; break;
+    default: return fail(ctx, JSGPU_EINVAL, "unknown output selector %d", which);
+    }
+    if (bytes > avail) return fail(ctx, JSGPU_EINVAL, "output %d of image %u has %llu bytes, %llu requested", which, image,
+                                   (unsigned long long)avail, (unsigned long long)bytes);
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return JSGPU_OK;
+}
+
+int jsgpu_decode_batch_host(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, const uint8_t* bits, uint64_t bytes,
+                            const jsgpu_host_outputs* out)
+{
+    if (!ctx || !imgs || !bits || !out) return JSGPU_EINVAL;
+    int r = jsgpu_batch_begin(ctx, imgs, n, bytes); if (r) return r;
+    r = jsgpu_batch_upload(ctx, bits, bytes); if (r) return r;
+    r = jsgpu_batch_decode(ctx); if (r) return r;
+    const DevBatch& b = ctx->batch; cudaStream_t s = ctx->stream;
+    // pooled D2H: each pool is one contiguous copy in batch order
+    if (out->pix_y)  CK(cudaMemcpyAsync(out->pix_y,  b.pix_y,  ctx->pix_total * 2, cudaMemcpyDeviceToHost, s));
+    if (out->pix_cb) CK(cudaMemcpyAsync(out->pix_cb, b.pix_cb, ctx->pix_total * 2, cudaMemcpyDeviceToHost, s));
+    if (out->pix_cr) CK(cudaMemcpyAsync(out->pix_cr, b.pix_cr, ctx->pix_total * 2, cudaMemcpyDeviceToHost, s));
+    if (out->dib)    CK(cudaMemcpyAsync(out->dib,    b.dib,    ctx->dib_total,     cudaMemcpyDeviceToHost, s));
+    if (out->blk_y)  CK(cudaMemcpyAsync(out->blk_y,  b.blk_y,  ctx->blk_total * 2, cudaMemcpyDeviceToHost, s));
+    if (out->blk_cb) CK(cudaMemcpyAsync(out->blk_cb, b.blk_cb, ctx->blk_total * 2, cudaMemcpyDeviceToHost, s));
+    if (out->blk_cr) CK(cudaMemcpyAsync(out->blk_cr, b.blk_cr, ctx->blk_total * 2, cudaMemcpyDeviceToHost, s));
+    if (out->mcu_map) CK(cudaMemcpyAsync(out->mcu_map, b.mcu_map, ctx->mcu_total * 4, cudaMemcpyDeviceToHost, s));
+    if (out->dht_histo) CK(cudaMemcpyAsync(out->dht_histo, b.histo, (size_t)n * 2 * 4 * 17 * 4, cudaMemcpyDeviceToHost, s));
+    if (out->stats)  CK(cudaMemcpyAsync(out->stats, b.stats, (size_t)n * 16 * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return JSGPU_OK;
+}
+
+void* jsgpu_host_alloc(uint64_t bytes) { void* p = nullptr; if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr; return p; }
+void  jsgpu_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+} // extern "C"

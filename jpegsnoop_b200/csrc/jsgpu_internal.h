@@ -1,0 +1,91 @@
+// jsgpu_internal.h — device-side data layout shared by the kernels (jsgpu_kernels.cu) and the
+// C-ABI / host orchestration (jsgpu_api.cu).  See DESIGN.md §3 "Data layout in HBM".
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+#define JS_LUT_BITS   10                 // direct Huffman look-up width (reference uses 9: ImgDecode.h:96)
+#define JS_LUT_SIZE   (1 << JS_LUT_BITS)
+#define JS_MAX_CODES  260
+#define JS_NSLOT      8                  // (class,Th) pairs: slot = class*4 + Th
+
+// Device form of one jsgpu_tables set.
+struct DevTableSet {
+    uint16_t lut[JS_NSLOT][JS_LUT_SIZE];     // (len<<8)|symbol for codes <= JS_LUT_BITS bits, 0 = take slow path
+    uint32_t ent_bits[JS_NSLOT][JS_MAX_CODES];   // left-justified code bits, in SetDhtEntry order
+    uint8_t  ent_len [JS_NSLOT][JS_MAX_CODES];
+    uint8_t  ent_sym [JS_NSLOT][JS_MAX_CODES];
+    uint32_t ent_n[JS_NSLOT];
+    uint32_t qz[4][64];                      // per DQT id, zig-zag position k: quantiser | natural_index<<16
+};
+
+// Device descriptor of one image of the batch.
+struct DevImage {
+    uint32_t valid;                 // 0 = skipped (the reference would return early)
+    uint32_t dim_x, dim_y, ns, precision;
+    uint32_t mcu_w, mcu_h, mcu_xmax, mcu_ymax, blk_xmax, blk_ymax, wp, hp;
+    uint32_t nmcu;
+    uint32_t ri;                    // MCUs per restart interval (= nmcu when DRI is off)
+    uint32_t restart_en;
+    uint32_t nseg, seg_first;       // expected segments; index of the first one in the segment arrays
+    uint32_t bpm;                   // blocks per MCU
+    uint32_t H[3], V[3], eh[3], ev[3];
+    uint32_t slot_dc[3], slot_ac[3];// LUT slot per component
+    uint32_t dqt[3];
+    uint32_t table_set;
+    uint32_t file_pos;              // file offset of scan_off
+    uint32_t cw[3], ch[3];          // coefficient plane size in blocks
+    uint64_t scan_off, scan_len;    // into the batch bitstream
+    uint64_t coef_row[3];           // first 128-byte row of each component plane in the coef pool
+    uint64_t pix_off, dib_off, blk_off, mcu_off;
+    uint32_t item_first, nitems;    // Huffman work items (groups of HUFF_WARPS segments)
+    uint32_t tile_first, ntiles;    // IDCT tiles
+};
+
+// Everything a kernel needs about the current batch (passed by value).
+struct DevBatch {
+    const DevImage*    img;
+    const DevTableSet* tables;
+    uint32_t           nimg;
+    const uint8_t*     bits;        // batch bitstream
+    uint64_t           bits_len;
+    // segments (expected count per image; seg_end == seg_start for missing ones)
+    uint32_t*          seg_start;   // relative to img.scan_off
+    uint32_t*          seg_end;
+    uint32_t*          seg_endbits; // unstuffed bit position where decoding of the segment stopped
+    uint32_t*          seg_status;
+    uint32_t           nseg_total;
+    uint32_t*          scan_end;    // [nimg] relative offset of the terminating marker
+    uint32_t*          nseg_found;  // [nimg]
+    // work lists
+    const uint2*       items;       // Huffman: (image, first segment)   [nitems]
+    uint32_t           nitems;
+    const uint4*       tiles;       // IDCT: (image, mcu_row, mcu_col0, nmcu) [ntiles]
+    uint32_t           ntiles;
+    // pools
+    int16_t*           coef;        // 64 int16 per block, natural order, slot 0 = cumulative DC
+    uint32_t*          mcu_bitpos;  // unstuffed bit offset of each MCU start within its segment
+    int16_t*           pix_y; int16_t* pix_cb; int16_t* pix_cr;
+    uint8_t*           dib;
+    int16_t*           blk_y; int16_t* blk_cb; int16_t* blk_cr;
+    uint32_t*          mcu_map;
+    uint32_t*          histo;       // [nimg][2][4][17]
+    int32_t*           stats;       // [nimg][16]
+    unsigned long long* bright_key; // [nimg] packed (Y+32768)<<32 | ~pixel_index
+    unsigned long long* sum_y;      // [nimg]
+    uint32_t*          img_status;  // [nimg]
+    // options
+    int                decode_ac, want_histo, idct_mode;
+};
+
+#define JS_HUFF_WARPS 4              // warps (= restart intervals in flight) per Huffman CTA
+
+// launchers (jsgpu_kernels.cu) — each returns the number of kernels it enqueued
+int js_launch_marker_scan(const DevBatch& b, uint64_t max_scan_len, cudaStream_t s);
+int js_launch_huffman_warp(const DevBatch& b, int sm_count, cudaStream_t s);
+int js_launch_huffman_lane(const DevBatch& b, int sm_count, cudaStream_t s);
+int js_launch_idct_simple(const DevBatch& b, const int32_t* li, const float* lf, uint64_t total_blocks,
+                          uint64_t total_pix, cudaStream_t s);
+int js_launch_idct_fused(const DevBatch& b, const int32_t* li, const float* lf, int sm_count, cudaStream_t s);
+int js_launch_finalize(const DevBatch& b, cudaStream_t s);
+int js_upload_idct_const(const int32_t* li, const float* lf, cudaStream_t s);

@@ -1,0 +1,59 @@
+"""TEST INFRASTRUCTURE: seeded test JPEGs made with Pillow/libjpeg-turbo (an encoder independent of
+both the reference and this repo), covering the layouts BASELINE.json's configs name."""
+import io
+import numpy as np
+from PIL import Image
+
+
+def synth_rgb(W, H, seed):
+    """Smooth sinusoid field + N(0,12) noise per channel (SURVEY.md §8d content)."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:H, 0:W]
+    img = np.stack([128 + 80 * np.sin(xx / 37.0) * np.cos(yy / 23.0),
+                    128 + 60 * np.sin(xx / 11.0 + yy / 50.0),
+                    128 + 70 * np.cos(yy / 17.0)], -1) + rng.normal(0, 12, (H, W, 3))
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+def enc(img, **kw):
+    b = io.BytesIO()
+    Image.fromarray(img).save(b, "JPEG", **kw)
+    return b.getvalue()
+
+
+def small_cases():
+    """(name, jpeg bytes) — small enough that the CPU oracle finishes each in well under a second."""
+    return [
+        ("444_rst_row_640x480", enc(synth_rgb(640, 480, 1), quality=85, subsampling=0, restart_marker_rows=1)),   # BASELINE config 1
+        ("422_opt_dri5", enc(synth_rgb(640, 480, 2), quality=75, subsampling=1, optimize=True, restart_marker_blocks=5)),
+        ("420_dri4_1080p", enc(synth_rgb(1920, 1080, 3), quality=85, subsampling=2, restart_marker_blocks=4)),     # one image of config 2
+        ("420_norst_odd", enc(synth_rgb(333, 211, 4), quality=92, subsampling=2)),                                # no DRI, ragged size
+        ("gray_dri3", enc(synth_rgb(200, 100, 5)[:, :, 0], quality=80, restart_marker_blocks=3)),
+        ("444_q100_tiny", enc(synth_rgb(64, 48, 6), quality=100, subsampling=0)),
+        ("420_q30_opt_rst2rows", enc(synth_rgb(800, 600, 7), quality=30, subsampling=2, optimize=True, restart_marker_rows=2)),
+        ("444_1x1_8px", enc(synth_rgb(8, 8, 8), quality=90, subsampling=0)),
+        ("420_dri1", enc(synth_rgb(160, 96, 9), quality=70, subsampling=2, restart_marker_blocks=1)),
+        ("420_dri8_4k_strip", enc(synth_rgb(3840, 64, 10), quality=85, subsampling=2, restart_marker_blocks=8)),  # config 3 geometry, 4 MCU rows
+    ]
+
+
+def compare(a, b, what=("geom", "pix_y", "pix_cb", "pix_cr", "dib", "mcu_map", "blk_dc", "dht_histo", "stats")):
+    """Bit-exact comparison of two Decoded-like objects; returns list of mismatching field names."""
+    bad = []
+
+    def eq(x, y):
+        if x is None and y is None:
+            return True
+        if x is None or y is None:
+            return False
+        return np.array_equal(np.asarray(x), np.asarray(y))
+    for f in what:
+        if f == "blk_dc":
+            if not all(eq(p, q) for p, q in zip(a.blk_dc, b.blk_dc)):
+                bad.append(f)
+        elif f == "stats":
+            if not eq(np.asarray(a.stats)[:11], np.asarray(b.stats)[:11]):
+                bad.append(f)
+        elif not eq(getattr(a, f), getattr(b, f)):
+            bad.append(f)
+    return bad

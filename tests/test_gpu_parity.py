@@ -1,0 +1,63 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C-ABI
+(jsimg_* = CimgDecode drop-in, jsgpu_* = batch), against the CPU oracle — bit-exact on every
+output buffer: int16 Y/Cb/Cr maps, BGRA DIB, block-DC maps, MCU file map, code-length histogram,
+brightest-pixel / average-luma scalars."""
+import numpy as np
+import pytest
+
+import jpeg_cases as JC
+from oracle_util import Oracle, ref_available
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle(fixed):
+    if ref_available("fixed" if fixed else "float"):
+        return Oracle("ref_fixed" if fixed else "ref_float")      # the compiled reference itself
+    return Oracle("port", idct_fixed=fixed)
+
+
+@pytest.fixture(scope="module")
+def cases():
+    return JC.small_cases()
+
+
+@pytest.mark.parametrize("fixed", [True, False], ids=["idct_fixed", "idct_float"])
+def test_single_image_dropin_matches_oracle(built, cases, fixed):
+    from jpegsnoop_b200 import CimgDecode
+    orc = _oracle(fixed)
+    dec = CimgDecode(idct_fixedpt=fixed, idct_kernel=1)
+    for name, j in cases:
+        want = orc.decode(j)
+        got = dec.decode(j)
+        assert got.nerr == 0 and want.nerr == 0, (name, dec.log_lines(3))
+        bad = JC.compare(want, got)
+        assert not bad, f"{name}: mismatch in {bad}"
+        want_stats = np.asarray(want.stats); got_stats = np.asarray(got.stats)
+        assert np.array_equal(want_stats, got_stats), (name, want_stats, got_stats)
+
+
+def test_batch_matches_oracle(built, cases):
+    from jpegsnoop_b200 import BatchDecoder
+    orc = _oracle(True)
+    bd = BatchDecoder(idct_kernel=1)
+    jpegs = [j for _, j in cases]
+    bd.set_batch(jpegs)
+    bd.decode(); bd.sync()
+    for i, (name, j) in enumerate(cases):
+        want = orc.decode(j); got = bd.fetch(i)
+        assert got.status == 0, (name, got.status)
+        bad = JC.compare(want, got, what=("geom", "pix_y", "pix_cb", "pix_cr", "dib", "mcu_map", "blk_dc", "dht_histo"))
+        assert not bad, f"{name}: mismatch in {bad}"
+
+
+def test_host_marker_walk_equals_device_marker_scan(built, cases):
+    from jpegsnoop_b200 import BatchDecoder
+    jpegs = [j for _, j in cases]
+    outs = []
+    for dm in (True, False):
+        bd = BatchDecoder(idct_kernel=1, device_markers=dm)
+        bd.set_batch(jpegs); bd.decode(); bd.sync()
+        outs.append([bd.fetch(i) for i in range(len(jpegs))])
+    for a, b, (name, _) in zip(outs[0], outs[1], cases):
+        assert not JC.compare(a, b, what=("pix_y", "dib", "mcu_map", "dht_histo")), name
