@@ -36,7 +36,8 @@ struct jsgpu_ctx {
     jsgpu_options opt;
     bool have_idct = false;
     // device state
-    DevBuf d_li, d_lf, d_tables, d_img, d_items, d_tiles;
+    DevBuf d_li, d_lf, d_sym, d_tables, d_img, d_items, d_litems, d_tiles, d_ubits, d_seg64;
+    bool sym_ok = false;
     DevBuf d_bits, d_seg, d_coef, d_mcubits, d_pix, d_dib, d_blk, d_mcumap, d_histo, d_stats, d_misc;
     uint32_t nsets = 0;
     // batch state
@@ -45,7 +46,8 @@ struct jsgpu_ctx {
     std::vector<jsgpu_image_layout> layout;
     DevBatch batch;
     uint64_t bits_len = 0, pix_total = 0, dib_total = 0, blk_total = 0, mcu_total = 0, coef_rows = 0;
-    uint64_t max_scan_len = 0;
+    uint64_t max_scan_len = 0, ubits_total = 0;
+    uint32_t n_nonstd = 0, n_std = 0;
     int launches = 0;
     float ms[5] = {0, 0, 0, 0, 0};
 };
@@ -106,7 +108,7 @@ void jsgpu_free(jsgpu_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = { &ctx->d_li, &ctx->d_lf, &ctx->d_tables, &ctx->d_img, &ctx->d_items, &ctx->d_tiles, &ctx->d_bits, &ctx->d_seg,
+    DevBuf* bufs[] = { &ctx->d_li, &ctx->d_lf, &ctx->d_sym, &ctx->d_tables, &ctx->d_img, &ctx->d_items, &ctx->d_litems, &ctx->d_tiles, &ctx->d_ubits, &ctx->d_seg64, &ctx->d_bits, &ctx->d_seg,
                        &ctx->d_coef, &ctx->d_mcubits, &ctx->d_pix, &ctx->d_dib, &ctx->d_blk, &ctx->d_mcumap, &ctx->d_histo, &ctx->d_stats, &ctx->d_misc };
     for (auto* b : bufs) b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -123,14 +125,53 @@ int jsgpu_sync(jsgpu_ctx* ctx)
     return JSGPU_OK;
 }
 
+// Split the integer IDCT table into its mirror-symmetric part (quadrant y,x < 4) and a sparse
+// correction: Li[y][x][vu] = sy*sx*S[min(y,7-y)][min(x,7-x)][vu] + D[yx][vu], sx = (x>=4 && u odd) ? -1 : 1,
+// sy = (y>=4 && v odd) ? -1 : 1.  Usable by the fused kernel when D is non-zero for <= 4 values of vu.
+static bool build_idct_sym(const int32_t* li, IdctSym& sym)
+{
+    memset(&sym, 0, sizeof sym);
+    std::vector<int> pos;
+    for (int vu = 0; vu < 64; vu++) {
+        const int u = vu & 7, v = vu >> 3;
+        bool any = false;
+        for (int y = 0; y < 8; y++) for (int x = 0; x < 8; x++) {
+            const int yy = y < 4 ? y : 7 - y, xx = x < 4 ? x : 7 - x;
+            int sg = 1; if (x >= 4 && (u & 1)) sg = -sg; if (y >= 4 && (v & 1)) sg = -sg;
+            const int d = li[(y * 8 + x) * 64 + vu] - sg * li[(yy * 8 + xx) * 64 + vu];
+            if (d != 0 && vu >= 1) any = true;
+        }
+        for (int q = 0; q < 16; q++) sym.s4[vu][q >> 2][q & 3] = li[((q >> 2) * 8 + (q & 3)) * 64 + vu];
+        if (any) pos.push_back(vu);
+    }
+    if (pos.size() > 4) { sym.ncorr = -1; return false; }
+    sym.ncorr = (int32_t)pos.size();
+    for (size_t j = 0; j < pos.size(); j++) {
+        const int vu = pos[j], u = vu & 7, v = vu >> 3;
+        sym.corr_pos[j] = vu;
+        for (int y = 0; y < 8; y++) for (int x = 0; x < 8; x++) {
+            const int yy = y < 4 ? y : 7 - y, xx = x < 4 ? x : 7 - x;
+            int sg = 1; if (x >= 4 && (u & 1)) sg = -sg; if (y >= 4 && (v & 1)) sg = -sg;
+            sym.corr[j][y * 8 + x] = li[(y * 8 + x) * 64 + vu] - sg * li[(yy * 8 + xx) * 64 + vu];
+        }
+    }
+    return true;
+}
+
 int jsgpu_set_idct_tables(jsgpu_ctx* ctx, const int32_t* li, const float* lf)
 {
     if (!ctx || !li || !lf) return JSGPU_EINVAL;
     cudaSetDevice(ctx->device);
-    CK(ctx->d_li.reserve(64 * 64 * 4)); CK(ctx->d_lf.reserve(64 * 64 * 4));
-    CK(cudaMemcpyAsync(ctx->d_li.p, li, 64 * 64 * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_lf.p, lf, 64 * 64 * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    IdctSym* sym = new IdctSym;
+    ctx->sym_ok = build_idct_sym(li, *sym);
+    cudaError_t e1 = ctx->d_li.reserve(64 * 64 * 4), e2 = ctx->d_lf.reserve(64 * 64 * 4), e3 = ctx->d_sym.reserve(sizeof(IdctSym));
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { delete sym; return fail(ctx, JSGPU_ENOMEM, "idct table allocation failed"); }
+    cudaMemcpyAsync(ctx->d_li.p, li, 64 * 64 * 4, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(ctx->d_lf.p, lf, 64 * 64 * 4, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(ctx->d_sym.p, sym, sizeof(IdctSym), cudaMemcpyHostToDevice, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    delete sym;
+    if (e != cudaSuccess) return fail(ctx, JSGPU_ECUDA, "idct table upload failed: %s", cudaGetErrorString(e));
     ctx->have_idct = true;
     return JSGPU_OK;
 }
@@ -167,21 +208,45 @@ static void build_table_set(const jsgpu_tables& t, DevTableSet& d)
             d.ent_bits[slot][i] = t.dht_bits[cls][id][i] & mask;
             d.ent_sym[slot][i] = t.dht_code[cls][id][i];
         }
-        for (uint32_t p = 0; p < JS_LUT_SIZE; p++) {
-            uint32_t top = p << (32 - JS_LUT_BITS);
-            uint16_t e = 0;
-            for (uint32_t i = 0; i < n; i++) {
-                uint32_t len = d.ent_len[slot][i];
-                if (len == 0 || len > 16) continue;
+        // Fill both levels in entry order; an entry never overwrites what an earlier entry claimed.
+        uint32_t nsub = 0; bool overflow = false;
+        for (uint32_t i = 0; i < n && !overflow; i++) {
+            const uint32_t len = d.ent_len[slot][i];
+            if (len == 0 || len > 16) continue;
+            const uint32_t bits = d.ent_bits[slot][i];
+            const uint16_t val = (uint16_t)((len << 8) | d.ent_sym[slot][i]);
+            const uint32_t p0 = bits >> (32 - JS_LUT_BITS);
+            const uint32_t np = (len <= JS_LUT_BITS) ? (1u << (JS_LUT_BITS - len)) : 1u;
+            for (uint32_t p = p0; p < p0 + np && p < JS_LUT_SIZE; p++) {
+                uint16_t& e = d.lut[slot][p];
                 if (len <= JS_LUT_BITS) {
-                    uint32_t mask = 0xffffffffu << (32 - len);
-                    if ((top & mask) == d.ent_bits[slot][i]) { e = (uint16_t)((len << 8) | d.ent_sym[slot][i]); break; }
+                    if (e == 0) e = val;
+                    else if (e & 0x8000) { uint16_t* sub = &d.lut2[slot][e & 0x7FFF]; for (uint32_t k = 0; k < (1u << JS_LUT2_BITS); k++) if (sub[k] == 0) sub[k] = val; }
                 } else {
-                    uint32_t mask = 0xffffffffu << (32 - JS_LUT_BITS);
-                    if ((d.ent_bits[slot][i] & mask) == top) { e = 0; break; }    // undecidable from the prefix alone
+                    if (e != 0 && !(e & 0x8000)) continue;           // an earlier short code owns this prefix
+                    if (e == 0) {
+                        if ((nsub + 1) * (1u << JS_LUT2_BITS) > JS_LUT2_SIZE) { overflow = true; break; }
+                        e = (uint16_t)(0x8000 | (nsub << JS_LUT2_BITS)); nsub++;
+                    }
+                    uint16_t* sub = &d.lut2[slot][e & 0x7FFF];
+                    const uint32_t k0 = (bits >> (32 - 16)) & ((1u << JS_LUT2_BITS) - 1);
+                    const uint32_t nk = 1u << (16 - len);
+                    for (uint32_t k = k0; k < k0 + nk && k < (1u << JS_LUT2_BITS); k++) if (sub[k] == 0) sub[k] = val;
                 }
             }
-            d.lut[slot][p] = e;
+        }
+        d.lut2_overflow[slot] = overflow ? 1 : 0;
+        if (overflow) {       // pathological table: every long prefix goes to the in-order search
+            memset(d.lut[slot], 0, sizeof d.lut[slot]);
+            for (uint32_t p = 0; p < JS_LUT_SIZE; p++) {
+                const uint32_t top = p << (32 - JS_LUT_BITS);
+                for (uint32_t i = 0; i < n; i++) {
+                    const uint32_t len = d.ent_len[slot][i];
+                    if (len == 0 || len > 16) continue;
+                    if (len <= JS_LUT_BITS) { if ((top & (0xffffffffu << (32 - len))) == d.ent_bits[slot][i]) { d.lut[slot][p] = (uint16_t)((len << 8) | d.ent_sym[slot][i]); break; } }
+                    else if ((d.ent_bits[slot][i] & (0xffffffffu << (32 - JS_LUT_BITS))) == top) { d.lut[slot][p] = 0x8000; break; }
+                }
+            }
         }
     }
     for (int q = 0; q < 4; q++) for (int k = 0; k < 64; k++) d.qz[q][k] = (uint32_t)t.dqt_zz[q][k] | ((uint32_t)kZigZagNat[k] << 16);
@@ -242,6 +307,13 @@ static bool plan_image(const jsgpu_image_desc& d, uint32_t nsets, DevImage& im)
     im.nseg = (im.nmcu + im.ri - 1) / im.ri;
     im.table_set = d.table_set; im.file_pos = d.file_pos;
     im.scan_off = d.scan_offset; im.scan_len = d.scan_length;
+    // fused IDCT kernel preconditions: component 1 carries the maximum sampling, chroma components
+    // are identical and either fully sampled or 1 in each direction, Hmax is a power of two
+    bool stdl = (H[0] == hmax && V[0] == vmax) && (hmax == 1 || hmax == 2 || hmax == 4);
+    if (ns == 3) stdl = stdl && H[1] == H[2] && V[1] == V[2] && (H[1] == 1 || H[1] == hmax) && (V[1] == 1 || V[1] == vmax);
+    im.std_layout = stdl ? 1 : 0;
+    im.tile_mcus = 32 / hmax;
+    im.tiles_per_row = (im.mcu_xmax + im.tile_mcus - 1) / im.tile_mcus;
     im.valid = 1;
     return true;
 }
@@ -255,9 +327,10 @@ int jsgpu_batch_begin(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, 
     ctx->planned = false; ctx->decoded = false;
     ctx->himg.assign(n, DevImage());
     ctx->layout.assign(n, jsgpu_image_layout());
-    uint64_t pix = 0, dib = 0, blk = 0, mcu = 0, rows = 0, max_scan = 0;
-    uint32_t seg = 0;
-    std::vector<uint2> items;
+    uint64_t pix = 0, dib = 0, blk = 0, mcu = 0, rows = 0, max_scan = 0, ub = 0;
+    uint32_t seg = 0, n_std = 0, n_nonstd = 0, plane_bytes = 0;
+    std::vector<uint2> items, litems;
+    std::vector<uint4> tiles;
     for (uint32_t i = 0; i < n; i++) {
         DevImage& im = ctx->himg[i];
         jsgpu_image_layout& lo = ctx->layout[i];
@@ -277,17 +350,34 @@ int jsgpu_batch_begin(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, 
         im.item_first = (uint32_t)items.size();
         for (uint32_t k = 0; k < im.nseg; k += JS_HUFF_WARPS) items.push_back(make_uint2(i, k));
         im.nitems = (uint32_t)items.size() - im.item_first;
+        for (uint32_t k = 0; k < im.nseg; k += JS_LANE_SEGS) litems.push_back(make_uint2(i, k));
+        im.ubits_off = ub; ub += align_up(im.scan_len + 32ull * im.nseg + 64, 256);
+        if (im.std_layout) {
+            n_std++;
+            im.tile_first = (uint32_t)tiles.size();
+            for (uint32_t r = 0; r < im.mcu_ymax; r++) for (uint32_t t = 0; t < im.tiles_per_row; t++) {
+                uint32_t c0 = t * im.tile_mcus;
+                tiles.push_back(make_uint4(i, r, c0, std::min(im.tile_mcus, im.mcu_xmax - c0)));
+            }
+            im.ntiles = (uint32_t)tiles.size() - im.tile_first;
+            uint32_t bpt = 0; for (uint32_t c = 0; c < im.ns; c++) bpt += im.H[c] * im.V[c] * im.tile_mcus;
+            plane_bytes = std::max(plane_bytes, bpt * 128);
+        } else n_nonstd++;
         lo.mcu_w = im.mcu_w; lo.mcu_h = im.mcu_h; lo.mcu_xmax = im.mcu_xmax; lo.mcu_ymax = im.mcu_ymax;
         lo.blk_xmax = im.blk_xmax; lo.blk_ymax = im.blk_ymax; lo.img_x = im.wp; lo.img_y = im.hp;
         lo.num_segments = im.nseg; lo.pix_off = im.pix_off; lo.dib_off = im.dib_off; lo.blk_off = im.blk_off; lo.mcu_off = im.mcu_off;
     }
     ctx->bits_len = bitstream_bytes; ctx->pix_total = pix; ctx->dib_total = dib; ctx->blk_total = blk; ctx->mcu_total = mcu;
-    ctx->coef_rows = rows; ctx->max_scan_len = max_scan;
+    ctx->coef_rows = rows; ctx->max_scan_len = max_scan; ctx->ubits_total = ub; ctx->n_std = n_std; ctx->n_nonstd = n_nonstd;
     // allocate
     CK(ctx->d_img.reserve(sizeof(DevImage) * (size_t)n));
     CK(ctx->d_items.reserve(sizeof(uint2) * std::max<size_t>(items.size(), 1)));
     CK(ctx->d_bits.reserve(bitstream_bytes + 64));
-    CK(ctx->d_seg.reserve(sizeof(uint32_t) * (4 * (size_t)seg + 2 * (size_t)n + 16)));
+    CK(ctx->d_ubits.reserve(ub + 256));
+    CK(ctx->d_litems.reserve(sizeof(uint2) * std::max<size_t>(litems.size(), 1)));
+    CK(ctx->d_tiles.reserve(sizeof(uint4) * std::max<size_t>(tiles.size(), 1)));
+    CK(ctx->d_seg64.reserve(8 * (size_t)seg + 16));
+    CK(ctx->d_seg.reserve(sizeof(uint32_t) * (5 * (size_t)seg + 2 * (size_t)n + 16)));
     CK(ctx->d_coef.reserve(rows * 128 + 128));
     CK(ctx->d_mcubits.reserve(mcu * 4 + 16));
     CK(ctx->d_pix.reserve(pix * 2 * 3 + 64));
@@ -299,14 +389,20 @@ int jsgpu_batch_begin(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, 
     CK(ctx->d_misc.reserve((size_t)n * (8 + 8 + 4) + 64));
     CK(cudaMemcpyAsync(ctx->d_img.p, ctx->himg.data(), sizeof(DevImage) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     if (!items.empty()) CK(cudaMemcpyAsync(ctx->d_items.p, items.data(), sizeof(uint2) * items.size(), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));      // `items` is a local
+    if (!litems.empty()) CK(cudaMemcpyAsync(ctx->d_litems.p, litems.data(), sizeof(uint2) * litems.size(), cudaMemcpyHostToDevice, ctx->stream));
+    if (!tiles.empty()) CK(cudaMemcpyAsync(ctx->d_tiles.p, tiles.data(), sizeof(uint4) * tiles.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));      // the work lists are locals
     DevBatch& b = ctx->batch;
     memset(&b, 0, sizeof b);
     b.img = (const DevImage*)ctx->d_img.p; b.tables = (const DevTableSet*)ctx->d_tables.p; b.nimg = n;
     b.bits = (const uint8_t*)ctx->d_bits.p; b.bits_len = bitstream_bytes;
     uint32_t* sp = (uint32_t*)ctx->d_seg.p;
     b.seg_start = sp; b.seg_end = sp + seg; b.seg_endbits = sp + 2 * (size_t)seg; b.seg_status = sp + 3 * (size_t)seg;
-    b.scan_end = sp + 4 * (size_t)seg; b.nseg_found = b.scan_end + n; b.nseg_total = seg;
+    b.seg_ulen = sp + 4 * (size_t)seg;
+    b.scan_end = sp + 5 * (size_t)seg; b.nseg_found = b.scan_end + n; b.nseg_total = seg;
+    b.seg_uoff = (unsigned long long*)ctx->d_seg64.p; b.ubits = (uint8_t*)ctx->d_ubits.p;
+    b.litems = (const uint2*)ctx->d_litems.p; b.nlitems = (uint32_t)litems.size();
+    b.tiles = (const uint4*)ctx->d_tiles.p; b.ntiles = (uint32_t)tiles.size(); b.tile_plane_bytes = plane_bytes;
     b.items = (const uint2*)ctx->d_items.p; b.nitems = (uint32_t)items.size();
     b.coef = (int16_t*)ctx->d_coef.p; b.mcu_bitpos = (uint32_t*)ctx->d_mcubits.p;
     b.pix_y = (int16_t*)ctx->d_pix.p; b.pix_cb = b.pix_y + pix; b.pix_cr = b.pix_cb + pix;
@@ -361,9 +457,9 @@ int jsgpu_batch_upload(jsgpu_ctx* ctx, const uint8_t* host, uint64_t bytes)
 static int host_marker_walk(jsgpu_ctx* ctx, const uint8_t* bits_host)
 {
     const DevBatch& b = ctx->batch;
-    std::vector<uint32_t> seg(4 * (size_t)b.nseg_total + 2 * (size_t)b.nimg, 0);
+    std::vector<uint32_t> seg(5 * (size_t)b.nseg_total + 2 * (size_t)b.nimg, 0);
     uint32_t* s_start = seg.data(); uint32_t* s_end = s_start + b.nseg_total;
-    uint32_t* scan_end = seg.data() + 4 * (size_t)b.nseg_total; uint32_t* nfound = scan_end + b.nimg;
+    uint32_t* scan_end = seg.data() + 5 * (size_t)b.nseg_total; uint32_t* nfound = scan_end + b.nimg;
     std::vector<int32_t> nrst(b.nimg, 0);
     for (uint32_t i = 0; i < b.nimg; i++) {
         const DevImage& im = ctx->himg[i];
@@ -415,12 +511,25 @@ int jsgpu_batch_decode(jsgpu_ctx* ctx)
         CK(cudaStreamSynchronize(s));
         host_marker_walk(ctx, hb.data());
     }
+    launches += js_launch_unstuff(b, s);
     CK(cudaEventRecord(ctx->ev[1], s));
-    if (ctx->opt.huff_kernel == 2) launches += js_launch_huffman_lane(b, ctx->sm_count, s);
-    else launches += js_launch_huffman_warp(b, ctx->sm_count, s);
+    {
+        int hk = ctx->opt.huff_kernel;
+        if (hk == 0) hk = (b.nseg_total >= 4096) ? 2 : 1;       // many short intervals -> lane kernel
+        if (hk == 2) launches += js_launch_huffman_lane(b, ctx->sm_count, s);
+        else launches += js_launch_huffman_warp(b, ctx->sm_count, s);
+    }
     CK(cudaEventRecord(ctx->ev[2], s));
-    if (ctx->opt.idct_kernel == 1) launches += js_launch_idct_simple(b, (const int32_t*)ctx->d_li.p, (const float*)ctx->d_lf.p, 0, 0, s);
-    else launches += js_launch_idct_fused(b, (const int32_t*)ctx->d_li.p, (const float*)ctx->d_lf.p, ctx->sm_count, s);
+    {
+        // fused tile kernel: integer IDCT, standard sampling layouts, decomposable table; everything
+        // else (float IDCT, exotic sampling, a libm whose table does not decompose) takes the simple kernels
+        const bool fused = (ctx->opt.idct_kernel != 1) && ctx->opt.idct_mode == 0 && ctx->sym_ok && b.ntiles > 0;
+        if (fused) launches += js_launch_idct_fused(b, (const IdctSym*)ctx->d_sym.p, (const int32_t*)ctx->d_li.p, (const float*)ctx->d_lf.p, ctx->sm_count, s);
+        if (!fused || ctx->n_nonstd > 0) {
+            DevBatch bs = b; bs.simple_only_nonstd = fused ? 1 : 0;
+            launches += js_launch_idct_simple(bs, (const int32_t*)ctx->d_li.p, (const float*)ctx->d_lf.p, 0, 0, s);
+        }
+    }
     CK(cudaEventRecord(ctx->ev[3], s));
     {
         DevBatch bf = b;

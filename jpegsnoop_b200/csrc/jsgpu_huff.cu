@@ -1,0 +1,441 @@
+// jsgpu_huff.cu — entropy decode (stage A): FF00 unstuffing pre-pass + two Huffman kernels.
+//
+//   k_unstuff      one warp per restart interval: 128 raw bytes per step, stuffed zeros found with
+//                  one shuffle, kept-byte ranks from three __ballot_sync (the per-lane count is
+//                  0..4, so three ballots give its exclusive prefix), compaction straight into an
+//                  aligned, 0xFF-padded copy of the interval.  (BuffAddByte, ImgDecode.cpp:1386-1573.)
+//   k_huff_warp    ONE WARP PER RESTART INTERVAL, warp-uniform symbol loop; lane i owns coefficients
+//                  2i,2i+1 so a block leaves as one coalesced 128-byte row.  Right when there are few,
+//                  long intervals (BASELINE config 5: no DRI) — a serial chain per interval.
+//   k_huff_lane    one LANE per restart interval, 32 intervals per warp; blocks are assembled in
+//                  per-lane shared-memory rows and written out cooperatively (coalesced).  Right when
+//                  there are many short intervals (configs 1-4): 32x fewer issue slots per symbol.
+// Both kernels share the look-up tables staged in shared memory and produce identical output:
+// dequantised int16 coefficient rows in natural order (DecodeIdctSet, :2270-2303) whose slot 0
+// holds the running DC predictor sum (m_nDcLum += m_anDctBlock[0], :3280).
+#include "jsgpu_internal.h"
+
+#define FULL 0xffffffffu
+
+// ------------------------------------------------------------------------------------------------
+// unstuff
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_unstuff(DevBatch b)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (gw >= b.nseg_total) return;
+    uint32_t lo = 0, hi = b.nimg - 1;
+    while (lo < hi) { uint32_t mid = (lo + hi + 1) >> 1; if (b.img[mid].seg_first <= gw) lo = mid; else hi = mid - 1; }
+    const DevImage& im = b.img[lo];
+    if (!im.valid) return;
+    const uint32_t k = gw - im.seg_first;
+    if (k >= im.nseg) return;
+    const uint32_t s0 = b.seg_start[gw], len = b.seg_end[gw] - s0;
+    const uint8_t* seg = b.bits + im.scan_off + s0;
+    // destination: 16-byte aligned, never overlapping the neighbours
+    const uint64_t dst0 = im.ubits_off + (uint64_t)(s0 & ~15u) + 32ull * k;
+    uint8_t* dst = b.ubits + dst0;
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(seg) & 3);
+    const uint8_t* abase = seg - mis;
+    uint32_t wr = 0, prev_ff = 0;
+    for (uint32_t rpos = 0; rpos < len + mis; rpos += 128) {
+        long long rel0 = (long long)rpos + 4 * lane - mis;
+        uint32_t word = 0;
+        if (rel0 + 3 >= 0 && rel0 < (long long)len) word = __ldg(reinterpret_cast<const uint32_t*>(abase + rpos + 4 * lane));
+        uint32_t up = __shfl_up_sync(FULL, word, 1);
+        uint32_t prevb = (lane == 0) ? (prev_ff ? 0xFFu : 0u) : (up >> 24);
+        uint32_t keep = 0, cnt = 0;
+        #pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint32_t bj = (word >> (8 * j)) & 0xFF;
+            long long rel = rel0 + j;
+            bool valid = rel >= 0 && rel < (long long)len;
+            bool drop = (bj == 0) && (prevb == 0xFF) && (rel > 0);
+            if (valid && !drop) { keep |= 1u << j; cnt++; }
+            prevb = valid ? bj : 0;
+        }
+        uint32_t lt = (1u << lane) - 1;
+        uint32_t b0 = __ballot_sync(FULL, cnt & 1), b1 = __ballot_sync(FULL, cnt & 2), b2 = __ballot_sync(FULL, cnt & 4);
+        uint32_t pre = __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
+        uint32_t tot = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+        uint32_t o = wr + pre;
+        #pragma unroll
+        for (int j = 0; j < 4; j++) if (keep >> j & 1) { dst[o] = (uint8_t)(word >> (8 * j)); o++; }
+        wr += tot;
+        uint32_t last = __shfl_sync(FULL, word, 31);
+        prev_ff = ((last >> 24) == 0xFF) ? 1u : 0u;
+    }
+    // pad with 1-bits (the JPEG pad value; no valid code is all ones) so readers can over-fetch
+    if (lane < 16) dst[wr + lane] = 0xFF;      // 16 bytes: the most a reader can over-fetch, and what the 32-byte slack allows
+    if (lane == 0) { b.seg_ulen[gw] = wr; b.seg_uoff[gw] = dst0; }
+}
+
+int js_launch_unstuff(const DevBatch& b, cudaStream_t s)
+{
+    if (b.nseg_total == 0) return 0;
+    k_unstuff<<<(b.nseg_total + 3) / 4, 128, 0, s>>>(b);
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared pieces
+// ------------------------------------------------------------------------------------------------
+struct HuffTabs {                       // shared-memory staged tables of ONE image
+    uint16_t lut[6][JS_LUT_SIZE];       // [comp*2 + class]  (len<<8)|symbol, 0 = not decidable from the prefix
+    uint32_t qz[3][80];                 // quantiser | natural index<<16 ; entries 64..79 = no-op (nat 127)
+};
+
+__device__ __forceinline__ void stage_tables(HuffTabs& t, const DevImage& im, const DevTableSet* ts)
+{
+    for (uint32_t c = 0; c < im.ns; c++) {
+        const uint4* s0 = reinterpret_cast<const uint4*>(ts->lut[im.slot_dc[c]]);
+        const uint4* s1 = reinterpret_cast<const uint4*>(ts->lut[im.slot_ac[c]]);
+        uint4* d0 = reinterpret_cast<uint4*>(t.lut[c * 2]);
+        uint4* d1 = reinterpret_cast<uint4*>(t.lut[c * 2 + 1]);
+        for (uint32_t i = threadIdx.x; i < JS_LUT_SIZE * 2 / 16; i += blockDim.x) { d0[i] = __ldg(s0 + i); d1[i] = __ldg(s1 + i); }
+        for (uint32_t i = threadIdx.x; i < 80; i += blockDim.x) t.qz[c][i] = (i < 64) ? ts->qz[im.dqt[c]][i] : (127u << 16);
+    }
+}
+
+// In-order entry search of ReadScanVal (ImgDecode.cpp:1145-1164) for prefixes the LUT cannot decide.
+__device__ __noinline__ uint32_t huff_slow(const DevTableSet* ts, uint32_t slot, uint32_t top)
+{
+    uint32_t n = ts->ent_n[slot];
+    for (uint32_t i = 0; i < n; i++) {
+        uint32_t l = ts->ent_len[slot][i];
+        if (l == 0 || l > 16) continue;
+        if ((top & (0xffffffffu << (32 - l))) == ts->ent_bits[slot][i]) return (l << 8) | ts->ent_sym[slot][i];
+    }
+    return 0;
+}
+
+// Second-level / exceptional look-up: e is the first-level entry (0 or 0x8000|offset).
+__device__ __forceinline__ uint32_t huff_level2(const DevTableSet* ts, uint32_t slot, uint32_t e, uint32_t top)
+{
+    if (e & 0x8000) {
+        if (ts->lut2_overflow[slot]) return huff_slow(ts, slot, top);
+        return __ldg(&ts->lut2[slot][(e & 0x7FFF) + ((top >> (32 - 16)) & ((1u << JS_LUT2_BITS) - 1))]);
+    }
+    return 0;     // no code has this prefix (the reference's search would fail too)
+}
+
+// Per-thread bit reader over an unstuffed, 4-byte aligned, 0xFF-padded interval.
+struct Bits {
+    unsigned long long w; int nb; const uint32_t* p; uint32_t words;
+    __device__ __forceinline__ void init(const uint8_t* base) {
+        p = reinterpret_cast<const uint32_t*>(base);
+        uint32_t a = __byte_perm(__ldg(p), 0, 0x0123), c = __byte_perm(__ldg(p + 1), 0, 0x0123);
+        w = ((unsigned long long)a << 32) | c; nb = 64; p += 2; words = 2;
+    }
+    __device__ __forceinline__ void refill() {          // call when nb <= 32
+        uint32_t x = __byte_perm(__ldg(p), 0, 0x0123);
+        w |= (unsigned long long)x << (32 - nb);
+        nb += 32; p++; words++;
+    }
+    __device__ __forceinline__ uint32_t consumed() const { return 32u * words - (uint32_t)nb; }
+    __device__ __forceinline__ uint32_t top32() const { return (uint32_t)(w >> 32); }
+};
+
+// value bits + T.81 F.12 EXTEND (HuffmanDc2Signed, ImgDecode.cpp:859-866) + precision divide (:1234-1238)
+__device__ __forceinline__ int take_value(Bits& s, uint32_t size, uint32_t precision)
+{
+    uint32_t t = s.top32();
+    uint32_t v = (size == 0) ? 0u : (t >> (32 - size));
+    int neg = ((int)~t) >> 31;                                   // all ones when the leading value bit is 0
+    int val = (int)v - (neg & (int)((1u << size) - 1));
+    s.w <<= size; s.nb -= (int)size;
+    if (precision > 8) val /= (1 << (precision - 8));
+    return val;
+}
+
+// ------------------------------------------------------------------------------------------------
+// warp per restart interval
+// ------------------------------------------------------------------------------------------------
+struct WarpShared { HuffTabs t; uint32_t histo[6][17]; };
+
+__device__ __forceinline__ void flush_histo(const DevBatch& b, uint32_t img, uint32_t (*histo)[17])
+{
+    const DevImage& pim = b.img[img];
+    for (uint32_t i = threadIdx.x; i < 6 * 17; i += blockDim.x) {
+        uint32_t c = i / 34, cls = (i / 17) & 1, l = i % 17;
+        uint32_t v = histo[c * 2 + cls][l];
+        if (v && c < pim.ns) { uint32_t slot = cls ? pim.slot_ac[c] : pim.slot_dc[c]; atomicAdd(&b.histo[((size_t)img * 8 + slot) * 17 + l], v); }
+    }
+}
+
+__global__ void __launch_bounds__(JS_HUFF_WARPS * 32) k_huff_warp(DevBatch b)
+{
+    __shared__ WarpShared sh;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t cur_img = 0xffffffffu;
+    for (uint32_t it = blockIdx.x; it < b.nitems; it += gridDim.x) {
+        const uint2 item = b.items[it];
+        const DevImage& gim = b.img[item.x];
+        const DevTableSet* ts = b.tables + gim.table_set;
+        if (item.x != cur_img) {
+            __syncthreads();
+            if (cur_img != 0xffffffffu && b.want_histo) { flush_histo(b, cur_img, sh.histo); __syncthreads(); }
+            for (uint32_t i = threadIdx.x; i < 6 * 17; i += blockDim.x) (&sh.histo[0][0])[i] = 0;
+            stage_tables(sh.t, gim, ts);
+            cur_img = item.x;
+            __syncthreads();
+        }
+        const uint32_t k = item.y + wid;
+        if (k >= gim.nseg) continue;
+        // hoist everything the hot loop needs into registers
+        const uint32_t ns = gim.ns, precision = gim.precision, ri = gim.ri, nmcu = gim.nmcu, mcu_xmax = gim.mcu_xmax;
+        const uint32_t sidx = gim.seg_first + k;
+        const uint32_t ulen = b.seg_ulen[sidx];
+        Bits s; s.init(b.ubits + b.seg_uoff[sidx]);
+        const uint32_t m0 = k * ri, m1 = min(m0 + ri, nmcu);
+        uint32_t mx = m0 % mcu_xmax, my = m0 / mcu_xmax;
+        int dcs[3] = {0, 0, 0};
+        uint32_t status = 0;
+        uint32_t* const coef32 = reinterpret_cast<uint32_t*>(b.coef);
+        const bool want_ac = b.decode_ac != 0;
+        for (uint32_t m = m0; m < m1 && !(status & 7); m++) {
+            if (lane == 0) b.mcu_bitpos[gim.mcu_off + m] = s.consumed();
+            #pragma unroll 1
+            for (uint32_t c = 0; c < ns; c++) {
+                const uint16_t* lut_dc = sh.t.lut[c * 2];
+                const uint16_t* lut_ac = sh.t.lut[c * 2 + 1];
+                const uint32_t* qz = sh.t.qz[c];
+                const uint32_t nh = gim.H[c], nv = gim.V[c], cw = gim.cw[c];
+                const uint32_t slot_dc = gim.slot_dc[c], slot_ac = gim.slot_ac[c];
+                const size_t row0 = gim.coef_row[c] + (size_t)(my * nv) * cw + mx * nh;
+                uint32_t hdc = 0, hac = 0;
+                int dc = dcs[c];
+                #pragma unroll 1
+                for (uint32_t bi = 0; bi < nh * nv; bi++) {
+                    uint32_t acc = 0;
+                    // ---- DC symbol ----
+                    if (s.nb <= 32) s.refill();
+                    uint32_t e = lut_dc[s.top32() >> (32 - JS_LUT_BITS)];
+                    if (e == 0 || (e & 0x8000)) e = huff_level2(ts, slot_dc, e, s.top32());
+                    if (e == 0) { status |= 1; break; }
+                    uint32_t len = e >> 8;
+                    s.w <<= len; s.nb -= (int)len;
+                    hdc += (lane == len);
+                    uint32_t pos;
+                    {
+                        uint32_t run = (e >> 4) & 15, size = e & 15;
+                        int val = take_value(s, size, precision);
+                        uint32_t q = qz[run];                      // run is 0 for every legal DC symbol
+                        int cf = (int)(short)(val * (int)(q & 0xFFFF));
+                        uint32_t nat = q >> 16;
+                        int dcdiff = 0;
+                        if (nat == 0) dcdiff = cf;
+                        else if (lane == (nat >> 1)) acc = (nat & 1) ? __byte_perm(acc, (uint32_t)cf, 0x5410) : __byte_perm(acc, (uint32_t)cf, 0x3254);
+                        dc = (int)(short)(dc + dcdiff);
+                        pos = 1 + run;
+                    }
+                    // ---- AC symbols ----
+                    while (pos < 64) {
+                        if (s.nb <= 32) s.refill();
+                        e = lut_ac[s.top32() >> (32 - JS_LUT_BITS)];
+                        if (e == 0 || (e & 0x8000)) e = huff_level2(ts, slot_ac, e, s.top32());
+                        if (e == 0) { status |= 1; break; }
+                        len = e >> 8;
+                        s.w <<= len; s.nb -= (int)len;
+                        hac += (lane == len);
+                        if ((e & 0xFF) == 0) break;               // EOB
+                        uint32_t run = (e >> 4) & 15, size = e & 15;
+                        int val = take_value(s, size, precision);
+                        uint32_t kk = pos + run;
+                        uint32_t q = qz[kk];                       // kk <= 78; entries >= 64 are no-ops
+                        uint32_t cf = (uint32_t)(val * (int)(q & 0xFFFF));
+                        uint32_t nat = q >> 16;
+                        if (want_ac && lane == (nat >> 1)) acc = (nat & 1) ? __byte_perm(acc, cf, 0x5410) : __byte_perm(acc, cf, 0x3254);
+                        pos = kk + 1;
+                    }
+                    if (pos > 64) status |= 4;
+                    if (lane == 0) acc = __byte_perm(acc, (uint32_t)dc, 0x3254);
+                    const uint32_t v = bi / nh, h = bi - v * nh;
+                    coef32[(row0 + (size_t)v * cw + h) * 32 + lane] = acc;
+                    if (status & 7) break;
+                }
+                dcs[c] = dc;
+                if (b.want_histo && lane >= 1 && lane <= 16) { atomicAdd(&sh.histo[c * 2][lane], hdc); atomicAdd(&sh.histo[c * 2 + 1][lane], hac); }
+                if (status & 7) break;
+            }
+            if (++mx == mcu_xmax) { mx = 0; my++; }
+        }
+        uint32_t consumed = s.consumed(), avail = ulen * 8;
+        if (consumed > avail) status |= 2;
+        else if (!(status & 5) && avail - consumed >= 8) status |= 16;
+        if (lane == 0) {
+            b.seg_endbits[sidx] = consumed;
+            b.seg_status[sidx] = status;
+            if (status) atomicOr(&b.img_status[item.x], status);
+        }
+    }
+    __syncthreads();
+    if (cur_img != 0xffffffffu && b.want_histo) flush_histo(b, cur_img, sh.histo);
+}
+
+int js_launch_huffman_warp(const DevBatch& b, int sm_count, cudaStream_t s)
+{
+    if (b.nitems == 0) return 0;
+    uint32_t grid = (uint32_t)sm_count * 8;
+    if (grid > b.nitems) grid = b.nitems;
+    k_huff_warp<<<grid, JS_HUFF_WARPS * 32, 0, s>>>(b);
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// lane per restart interval
+// ------------------------------------------------------------------------------------------------
+#define LN_WARPS   4
+#define ROW_PITCH  144                      // bytes per lane row (128 + 16): 16-byte aligned, bank-skewed
+struct LaneShared {
+    HuffTabs t;
+    uint32_t histo[6][17];
+    __align__(16) uint8_t rows[LN_WARPS][32 * ROW_PITCH];
+};
+
+__global__ void __launch_bounds__(LN_WARPS * 32) k_huff_lane(DevBatch b)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    LaneShared& sh = *reinterpret_cast<LaneShared*>(smem_raw);
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint8_t* const myrows = sh.rows[wid];
+    uint16_t* const myrow = reinterpret_cast<uint16_t*>(myrows + lane * ROW_PITCH);
+    // rows start zeroed and are re-zeroed by the write-out
+    for (uint32_t i = lane; i < 32 * ROW_PITCH / 4; i += 32) reinterpret_cast<uint32_t*>(myrows)[i] = 0;
+    uint32_t cur_img = 0xffffffffu;
+    for (uint32_t it = blockIdx.x; it < b.nlitems; it += gridDim.x) {
+        const uint2 item = b.litems[it];                      // (image, first interval); LN_WARPS*32 intervals per item
+        const DevImage& gim = b.img[item.x];
+        const DevTableSet* ts = b.tables + gim.table_set;
+        if (item.x != cur_img) {
+            __syncthreads();
+            if (cur_img != 0xffffffffu && b.want_histo) { flush_histo(b, cur_img, sh.histo); __syncthreads(); }
+            for (uint32_t i = threadIdx.x; i < 6 * 17; i += blockDim.x) (&sh.histo[0][0])[i] = 0;
+            stage_tables(sh.t, gim, ts);
+            cur_img = item.x;
+            __syncthreads();
+        }
+        const uint32_t kbase = item.y + wid * 32;
+        if (kbase >= gim.nseg) continue;                       // warp-uniform
+        const uint32_t k = kbase + lane;
+        const bool live = k < gim.nseg;
+        const uint32_t ns = gim.ns, precision = gim.precision, ri = gim.ri, nmcu = gim.nmcu, mcu_xmax = gim.mcu_xmax;
+        const uint32_t sidx = gim.seg_first + (live ? k : kbase);
+        const uint32_t ulen = b.seg_ulen[sidx];
+        Bits s; s.init(b.ubits + b.seg_uoff[sidx]);
+        const uint32_t m0 = k * ri;
+        const uint32_t nm = live ? (min(m0 + ri, nmcu) - m0) : 0;   // MCUs this lane decodes
+        uint32_t mx = m0 % mcu_xmax, my = m0 / mcu_xmax;
+        int dc0 = 0, dc1 = 0, dc2 = 0;
+        uint32_t status = 0;
+        const bool want_ac = b.decode_ac != 0;
+        const bool want_histo = b.want_histo != 0;
+        const uint32_t nm_max = min(ri, nmcu - kbase * ri);         // longest interval in this warp (the first lane's)
+        #pragma unroll 1
+        for (uint32_t mi = 0; mi < nm_max; mi++) {
+            const bool mlive = (mi < nm) && !(status & 7);
+            if (mlive) b.mcu_bitpos[gim.mcu_off + m0 + mi] = s.consumed();
+            #pragma unroll 1
+            for (uint32_t c = 0; c < ns; c++) {
+                const uint16_t* lut_dc = sh.t.lut[c * 2];
+                const uint16_t* lut_ac = sh.t.lut[c * 2 + 1];
+                const uint32_t* qz = sh.t.qz[c];
+                const uint32_t nh = gim.H[c], nv = gim.V[c], cw = gim.cw[c];
+                const uint32_t slot_dc = gim.slot_dc[c], slot_ac = gim.slot_ac[c];
+                int dc = (c == 0) ? dc0 : (c == 1) ? dc1 : dc2;
+                #pragma unroll 1
+                for (uint32_t bi = 0; bi < nh * nv; bi++) {
+                    bool active = mlive && !(status & 7);
+                    uint32_t pos = 64;
+                    if (active) {
+                        // ---- DC symbol ----
+                        if (s.nb <= 32) s.refill();
+                        uint32_t e = lut_dc[s.top32() >> (32 - JS_LUT_BITS)];
+                        if (e == 0 || (e & 0x8000)) e = huff_level2(ts, slot_dc, e, s.top32());
+                        if (e == 0) { status |= 1; active = false; }
+                        else {
+                            uint32_t len = e >> 8;
+                            s.w <<= len; s.nb -= (int)len;
+                            if (want_histo) atomicAdd(&sh.histo[c * 2][len], 1u);
+                            uint32_t run = (e >> 4) & 15, size = e & 15;
+                            int val = take_value(s, size, precision);
+                            uint32_t q = qz[run];
+                            int cf = (int)(short)(val * (int)(q & 0xFFFF));
+                            uint32_t nat = q >> 16;
+                            int dcdiff = 0;
+                            if (nat == 0) dcdiff = cf; else if (nat < 64) myrow[nat] = (uint16_t)cf;
+                            dc = (int)(short)(dc + dcdiff);
+                            pos = 1 + run;
+                        }
+                    }
+                    // ---- AC symbols: every lane advances its own interval by one symbol per step ----
+                    while (__any_sync(FULL, pos < 64)) {
+                        if (pos < 64) {
+                            if (s.nb <= 32) s.refill();
+                            uint32_t e = lut_ac[s.top32() >> (32 - JS_LUT_BITS)];
+                            if (e == 0 || (e & 0x8000)) e = huff_level2(ts, slot_ac, e, s.top32());
+                            if (e == 0) { status |= 1; pos = 64; }
+                            else {
+                                uint32_t len = e >> 8;
+                                s.w <<= len; s.nb -= (int)len;
+                                if (want_histo) atomicAdd(&sh.histo[c * 2 + 1][len], 1u);
+                                if ((e & 0xFF) == 0) pos = 64 + 64;          // EOB (distinguish from overflow)
+                                else {
+                                    uint32_t run = (e >> 4) & 15, size = e & 15;
+                                    int val = take_value(s, size, precision);
+                                    uint32_t kk = pos + run;
+                                    uint32_t q = qz[kk];
+                                    uint32_t nat = q >> 16;
+                                    if (want_ac && nat < 64) myrow[nat] = (uint16_t)(val * (int)(q & 0xFFFF));
+                                    pos = kk + 1;
+                                    if (pos > 64) { status |= 4; }
+                                }
+                            }
+                        }
+                    }
+                    if (active) myrow[0] = (uint16_t)dc;
+                    // ---- cooperative write-out: 4 rows per step, 16 bytes per lane, then re-zero ----
+                    const uint32_t v = bi / nh, h = bi - v * nh;
+                    const unsigned long long myaddr = active ? (unsigned long long)((gim.coef_row[c] + (size_t)(my * nv + v) * cw + (mx * nh + h)) * 128) : ~0ull;
+                    __syncwarp();
+                    #pragma unroll
+                    for (int r = 0; r < 8; r++) {
+                        const int src = r * 4 + (lane >> 3);
+                        unsigned long long a = __shfl_sync(FULL, myaddr, src);
+                        uint4* sp = reinterpret_cast<uint4*>(myrows + src * ROW_PITCH + (lane & 7) * 16);
+                        uint4 val = *sp;
+                        if (a != ~0ull) {
+                            *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(b.coef) + a + (lane & 7) * 16) = val;
+                            *sp = make_uint4(0, 0, 0, 0);
+                        }
+                    }
+                    __syncwarp();
+                }
+                if (c == 0) dc0 = dc; else if (c == 1) dc1 = dc; else dc2 = dc;
+            }
+            if (++mx == mcu_xmax) { mx = 0; my++; }
+        }
+        if (live) {
+            uint32_t consumed = s.consumed(), avail = ulen * 8;
+            if (consumed > avail) status |= 2;
+            else if (!(status & 5) && avail - consumed >= 8) status |= 16;
+            b.seg_endbits[sidx] = consumed;
+            b.seg_status[sidx] = status;
+            if (status) atomicOr(&b.img_status[item.x], status);
+        }
+    }
+    __syncthreads();
+    if (cur_img != 0xffffffffu && b.want_histo) flush_histo(b, cur_img, sh.histo);
+}
+
+int js_launch_huffman_lane(const DevBatch& b, int sm_count, cudaStream_t s)
+{
+    if (b.nlitems == 0) return 0;
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(k_huff_lane, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LaneShared)); attr_set = true; }
+    uint32_t grid = (uint32_t)sm_count * 4;
+    if (grid > b.nlitems) grid = b.nlitems;
+    k_huff_lane<<<grid, LN_WARPS * 32, sizeof(LaneShared), s>>>(b);
+    return 1;
+}

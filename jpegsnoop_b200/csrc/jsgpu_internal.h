@@ -4,14 +4,22 @@
 #include <stdint.h>
 #include <cuda_runtime.h>
 
-#define JS_LUT_BITS   10                 // direct Huffman look-up width (reference uses 9: ImgDecode.h:96)
+#define JS_LUT_BITS   11                 // direct Huffman look-up width (reference uses 9: ImgDecode.h:96)
 #define JS_LUT_SIZE   (1 << JS_LUT_BITS)
+#define JS_LUT2_BITS  (16 - JS_LUT_BITS)
+#define JS_LUT2_SIZE  8192               // second-level entries per slot (256 sub-tables of 32)
 #define JS_MAX_CODES  260
 #define JS_NSLOT      8                  // (class,Th) pairs: slot = class*4 + Th
 
 // Device form of one jsgpu_tables set.
 struct DevTableSet {
-    uint16_t lut[JS_NSLOT][JS_LUT_SIZE];     // (len<<8)|symbol for codes <= JS_LUT_BITS bits, 0 = take slow path
+    // two-level direct look-up (first match in SetDhtEntry order, exactly like ImgDecode.cpp:1145-1164):
+    //   lut[slot][top JS_LUT_BITS bits]: (len<<8)|symbol for a code of len <= JS_LUT_BITS,
+    //                                    0x8000|offset  -> second level, 0 -> no code has this prefix
+    //   lut2[slot][offset + next (16-JS_LUT_BITS) bits]: (len<<8)|symbol, 0 -> no code
+    uint16_t lut[JS_NSLOT][JS_LUT_SIZE];
+    uint16_t lut2[JS_NSLOT][JS_LUT2_SIZE];
+    uint32_t lut2_overflow[JS_NSLOT];        // 1: second level did not fit -> in-order entry search for 0x8000 prefixes
     uint32_t ent_bits[JS_NSLOT][JS_MAX_CODES];   // left-justified code bits, in SetDhtEntry order
     uint8_t  ent_len [JS_NSLOT][JS_MAX_CODES];
     uint8_t  ent_sym [JS_NSLOT][JS_MAX_CODES];
@@ -38,6 +46,10 @@ struct DevImage {
     uint64_t scan_off, scan_len;    // into the batch bitstream
     uint64_t coef_row[3];           // first 128-byte row of each component plane in the coef pool
     uint64_t pix_off, dib_off, blk_off, mcu_off;
+    uint64_t ubits_off;             // this image's region in the unstuffed-bitstream pool
+    uint32_t std_layout;            // 1 = every component has H in {1,Hmax} and V in {1,Vmax} (fused IDCT kernel applies)
+    uint32_t tile_mcus;             // MCUs per IDCT tile (32 / Hmax)
+    uint32_t tiles_per_row;
     uint32_t item_first, nitems;    // Huffman work items (groups of HUFF_WARPS segments)
     uint32_t tile_first, ntiles;    // IDCT tiles
 };
@@ -54,12 +66,17 @@ struct DevBatch {
     uint32_t*          seg_end;
     uint32_t*          seg_endbits; // unstuffed bit position where decoding of the segment stopped
     uint32_t*          seg_status;
+    uint32_t*          seg_ulen;    // unstuffed length of each interval
+    unsigned long long* seg_uoff;   // where its unstuffed copy starts in ubits
+    uint8_t*           ubits;       // unstuffed, 16-byte aligned, 0xFF-padded copies of all intervals
     uint32_t           nseg_total;
     uint32_t*          scan_end;    // [nimg] relative offset of the terminating marker
     uint32_t*          nseg_found;  // [nimg]
     // work lists
-    const uint2*       items;       // Huffman: (image, first segment)   [nitems]
+    const uint2*       items;       // Huffman, warp kernel: (image, first segment), JS_HUFF_WARPS per item
     uint32_t           nitems;
+    const uint2*       litems;      // Huffman, lane kernel: (image, first segment), JS_LANE_SEGS per item
+    uint32_t           nlitems;
     const uint4*       tiles;       // IDCT: (image, mcu_row, mcu_col0, nmcu) [ntiles]
     uint32_t           ntiles;
     // pools
@@ -76,16 +93,30 @@ struct DevBatch {
     uint32_t*          img_status;  // [nimg]
     // options
     int                decode_ac, want_histo, idct_mode;
+    int                simple_only_nonstd;   // simple IDCT kernels skip images the fused kernel handled
+    uint32_t           tile_plane_bytes;     // shared-memory plane bytes the largest tile needs
 };
 
-#define JS_HUFF_WARPS 4              // warps (= restart intervals in flight) per Huffman CTA
+#define JS_HUFF_WARPS 4              // warps (= restart intervals in flight) per Huffman CTA, warp kernel
+#define JS_LANE_SEGS  128            // restart intervals per CTA pass, lane kernel (4 warps x 32 lanes)
 
 // launchers (jsgpu_kernels.cu) — each returns the number of kernels it enqueued
 int js_launch_marker_scan(const DevBatch& b, uint64_t max_scan_len, cudaStream_t s);
+int js_launch_unstuff(const DevBatch& b, cudaStream_t s);
 int js_launch_huffman_warp(const DevBatch& b, int sm_count, cudaStream_t s);
 int js_launch_huffman_lane(const DevBatch& b, int sm_count, cudaStream_t s);
 int js_launch_idct_simple(const DevBatch& b, const int32_t* li, const float* lf, uint64_t total_blocks,
                           uint64_t total_pix, cudaStream_t s);
-int js_launch_idct_fused(const DevBatch& b, const int32_t* li, const float* lf, int sm_count, cudaStream_t s);
+struct IdctSym;
+int js_launch_idct_fused(const DevBatch& b, const IdctSym* sym, const int32_t* li, const float* lf, int sm_count, cudaStream_t s);
 int js_launch_finalize(const DevBatch& b, cudaStream_t s);
-int js_upload_idct_const(const int32_t* li, const float* lf, cudaStream_t s);
+
+// Quadrant-symmetric decomposition of the integer IDCT table (built on the host at table upload,
+// jsgpu_api.cu): Li[y][x][vu] = sign * S[min(y,7-y)][min(x,7-x)][vu] + D, where the sign flips with the
+// parity of u (x mirrored) and v (y mirrored), and D is non-zero only for `ncorr` coefficient positions.
+struct IdctSym {
+    int32_t s4[64][4][4];        // [vu][q/4][q%4]: S for quadrant sample q = y*4+x (y,x < 4), int4-friendly
+    int32_t ncorr;               // number of coefficient positions with a non-zero correction (<= 4), -1 = not decomposable
+    int32_t corr_pos[4];         // their natural indices
+    int32_t corr[4][64];         // D[j][yx]
+};

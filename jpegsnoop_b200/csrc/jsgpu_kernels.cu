@@ -106,301 +106,6 @@ int js_launch_marker_scan(const DevBatch& b, uint64_t, cudaStream_t s)
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1a: Huffman decode, one warp per restart interval.
-//
-// All 32 lanes run the same (warp-uniform) symbol loop, so the serial dependency chain costs one
-// warp's issue slots, and the lanes are used for the three data-parallel jobs around it:
-//   * fetch: a 128-byte raw chunk per load (lane i holds word i), FF00 unstuffing by
-//     __ballot_sync-derived prefix offsets (three ballots give the exclusive prefix of the
-//     per-lane kept-byte counts), compaction into a per-warp shared-memory ring;
-//   * table look-up: the DHT look-up tables of the image's components staged in shared memory;
-//   * store: lane i owns natural-order coefficients 2i,2i+1 of the current block, so a finished
-//     block leaves as ONE coalesced 128-byte row.
-// The DC predictor is a warp-uniform register: the running int16 sum the reference keeps
-// (m_nDcLum etc., ImgDecode.cpp:3280) — no cross-lane scan is needed for it in this kernel.
-// ------------------------------------------------------------------------------------------------
-#define RING_WORDS 64
-#define RING_BYTES (RING_WORDS * 4)
-
-struct WarpBits {
-    unsigned long long w;   // MSB-aligned bit window
-    int       nb;           // valid bits in w
-    uint32_t* ring;         // shared: RING_WORDS words of unstuffed stream
-    uint32_t  rd;           // words consumed from the ring (monotonic)
-    uint32_t  wr;           // unstuffed bytes produced (monotonic)
-    const uint8_t* seg;     // raw segment base (global)
-    uint32_t  len;          // raw segment length
-    uint32_t  misalign;     // (address of seg) & 3
-    uint32_t  rpos;         // next raw chunk offset (relative to aligned base, multiple of 128)
-    uint32_t  prev_ff;      // last raw byte of the previous chunk was 0xFF
-    uint32_t  next;         // prefetched raw word of this lane for chunk rpos
-    uint32_t  data_bytes;   // unstuffed data bytes of the segment once known
-    bool      drained;      // all raw bytes consumed into the ring
-};
-
-__device__ __forceinline__ uint32_t ld_raw_word(const WarpBits& s, uint32_t lane, uint32_t rpos)
-{
-    // aligned 32-bit load of raw bytes [rpos+4*lane, +4) relative to the aligned base
-    long long rel = (long long)rpos + 4 * lane - s.misalign;      // offset relative to seg
-    if (rel + 3 < 0 || rel >= (long long)s.len) return 0;
-    const uint32_t* a = reinterpret_cast<const uint32_t*>(s.seg - s.misalign + rpos + 4 * lane);
-    return __ldg(a);
-}
-
-__device__ __forceinline__ void wb_fill(WarpBits& s, uint32_t lane)
-{
-    uint32_t word = s.next;
-    uint32_t rpos = s.rpos;
-    s.rpos += 128;
-    s.next = ld_raw_word(s, lane, s.rpos);                 // prefetch the next chunk now
-    long long rel0 = (long long)rpos + 4 * lane - s.misalign;
-    uint32_t up = __shfl_up_sync(FULL, word, 1);
-    uint32_t prevb = (lane == 0) ? (s.prev_ff ? 0xFFu : 0u) : (up >> 24);
-    uint32_t keep = 0, cnt = 0;
-    #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        uint32_t bj = (word >> (8 * j)) & 0xFF;
-        long long rel = rel0 + j;
-        bool valid = rel >= 0 && rel < (long long)s.len;
-        bool drop = (bj == 0) && (prevb == 0xFF) && (rel > 0);   // stuffed zero after a data FF
-        if (valid && !drop) { keep |= 1u << j; cnt++; }
-        prevb = valid ? bj : 0;
-    }
-    // exclusive prefix of cnt (0..4) over lanes from three ballots
-    uint32_t lt = (1u << lane) - 1;
-    uint32_t b0 = __ballot_sync(FULL, cnt & 1), b1 = __ballot_sync(FULL, cnt & 2), b2 = __ballot_sync(FULL, cnt & 4);
-    uint32_t pre = __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
-    uint32_t tot = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
-    uint8_t* ringb = reinterpret_cast<uint8_t*>(s.ring);
-    uint32_t o = s.wr + pre;
-    #pragma unroll
-    for (int j = 0; j < 4; j++) if (keep >> j & 1) { ringb[o & (RING_BYTES - 1)] = (uint8_t)(word >> (8 * j)); o++; }
-    s.wr += tot;
-    uint32_t last = __shfl_sync(FULL, word, 31);
-    long long rel_last = (long long)rpos + 127 - s.misalign;
-    s.prev_ff = (rel_last >= 0 && rel_last < (long long)s.len && (last >> 24) == 0xFF) ? 1u : 0u;
-    if ((long long)s.rpos - (long long)s.misalign >= (long long)s.len && !s.drained) {
-        s.drained = true;
-        s.data_bytes = s.wr;
-    }
-    __syncwarp();
-}
-
-__device__ __forceinline__ void wb_pad(WarpBits& s, uint32_t lane)
-{
-    // past the end of the interval: feed 1-bits (the JPEG pad value; no valid code is all ones)
-    uint8_t* ringb = reinterpret_cast<uint8_t*>(s.ring);
-    if (lane < 16) ringb[(s.wr + lane) & (RING_BYTES - 1)] = 0xFF;
-    s.wr += 16;
-    __syncwarp();
-}
-
-__device__ __forceinline__ void wb_refill(WarpBits& s, uint32_t lane)
-{
-    // precondition: s.nb <= 32
-    while (4 * (s.rd + 1) > s.wr) { if (!s.drained) wb_fill(s, lane); else wb_pad(s, lane); }
-    uint32_t le = s.ring[s.rd & (RING_WORDS - 1)];
-    uint32_t be = __byte_perm(le, 0, 0x0123);
-    s.w |= (unsigned long long)be << (32 - s.nb);
-    s.nb += 32;
-    s.rd++;
-}
-
-__device__ __forceinline__ void wb_init(WarpBits& s, uint32_t* ring, const uint8_t* seg, uint32_t len, uint32_t lane)
-{
-    s.w = 0; s.nb = 0; s.ring = ring; s.rd = 0; s.wr = 0;
-    s.seg = seg; s.len = len;
-    s.misalign = (uint32_t)(reinterpret_cast<uintptr_t>(seg) & 3);
-    s.rpos = 0; s.prev_ff = 0; s.drained = false; s.data_bytes = 0;
-    s.next = ld_raw_word(s, lane, 0);
-    if (len == 0) { s.drained = true; s.data_bytes = 0; }
-    wb_refill(s, lane);
-    wb_refill(s, lane);     // nb = 64
-}
-
-// bits consumed so far
-__device__ __forceinline__ uint32_t wb_consumed(const WarpBits& s) { return 32u * s.rd - (uint32_t)s.nb; }
-
-// Decode one Huffman symbol with the shared-memory LUT; falls back to the in-order entry search
-// of ReadScanVal (ImgDecode.cpp:1145-1164) for codes longer than JS_LUT_BITS.  Returns the
-// symbol byte, or -1 when no code matches.
-__device__ __forceinline__ int huff_symbol(WarpBits& s, const uint16_t* lut, const DevTableSet* ts, uint32_t slot, uint32_t& len_out)
-{
-    uint32_t peek = (uint32_t)(s.w >> (64 - JS_LUT_BITS));
-    uint32_t e = lut[peek];
-    uint32_t len, sym;
-    if (e) { len = e >> 8; sym = e & 0xFF; }
-    else {
-        uint32_t top = (uint32_t)(s.w >> 32);
-        uint32_t n = ts->ent_n[slot];
-        len = 0; sym = 0;
-        for (uint32_t i = 0; i < n; i++) {
-            uint32_t l = ts->ent_len[slot][i];
-            uint32_t mask = 0xffffffffu << (32 - l);
-            if ((top & mask) == ts->ent_bits[slot][i]) { len = l; sym = ts->ent_sym[slot][i]; break; }
-        }
-        if (len == 0) { len_out = 0; return -1; }
-    }
-    s.w <<= len; s.nb -= len;
-    len_out = len;
-    return (int)sym;
-}
-
-// T.81 F.12 EXTEND as written in HuffmanDc2Signed (ImgDecode.cpp:859-866), then the precision
-// divide of ReadScanVal (:1234-1238).
-__device__ __forceinline__ int huff_value(WarpBits& s, uint32_t size, uint32_t precision)
-{
-    if (size == 0) return 0;
-    uint32_t v = (uint32_t)(s.w >> (64 - size));
-    s.w <<= size; s.nb -= size;
-    int val = (v >= (1u << (size - 1))) ? (int)v : (int)(v - ((1u << size) - 1));
-    if (precision > 8) val /= (1 << (precision - 8));
-    return val;
-}
-
-struct HuffShared {
-    uint16_t lut[6][JS_LUT_SIZE];    // [comp*2 + class]
-    uint32_t qz[3][64];
-    uint32_t ring[JS_HUFF_WARPS][RING_WORDS];
-    uint32_t histo[6][17];
-};
-
-__global__ void __launch_bounds__(JS_HUFF_WARPS * 32) k_huff_warp(DevBatch b)
-{
-    __shared__ HuffShared sh;
-    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint32_t cur_img = 0xffffffffu;
-    for (uint32_t it = blockIdx.x; it < b.nitems; it += gridDim.x) {
-        const uint2 item = b.items[it];
-        const DevImage& im = b.img[item.x];
-        const DevTableSet* ts = b.tables + im.table_set;
-        if (item.x != cur_img) {
-            // stage this image's look-up tables (shared-memory staged DHT + DQT)
-            __syncthreads();
-            if (cur_img != 0xffffffffu && b.want_histo) {
-                const DevImage& pim = b.img[cur_img];
-                for (uint32_t i = threadIdx.x; i < 6 * 17; i += blockDim.x) {
-                    uint32_t c = i / 34, cls = (i / 17) & 1, l = i % 17;
-                    uint32_t v = sh.histo[c * 2 + cls][l];
-                    if (v && c < pim.ns) { uint32_t slot = cls ? pim.slot_ac[c] : pim.slot_dc[c]; atomicAdd(&b.histo[((size_t)cur_img * 8 + slot) * 17 + l], v); }
-                }
-                __syncthreads();
-            }
-            for (uint32_t i = threadIdx.x; i < 6 * 17; i += blockDim.x) (&sh.histo[0][0])[i] = 0;
-            for (uint32_t c = 0; c < im.ns; c++) {
-                const uint4* s0 = reinterpret_cast<const uint4*>(ts->lut[im.slot_dc[c]]);
-                const uint4* s1 = reinterpret_cast<const uint4*>(ts->lut[im.slot_ac[c]]);
-                uint4* d0 = reinterpret_cast<uint4*>(sh.lut[c * 2]);
-                uint4* d1 = reinterpret_cast<uint4*>(sh.lut[c * 2 + 1]);
-                for (uint32_t i = threadIdx.x; i < JS_LUT_SIZE * 2 / 16; i += blockDim.x) { d0[i] = __ldg(s0 + i); d1[i] = __ldg(s1 + i); }
-                for (uint32_t i = threadIdx.x; i < 64; i += blockDim.x) sh.qz[c][i] = ts->qz[im.dqt[c]][i];
-            }
-            cur_img = item.x;
-            __syncthreads();
-        }
-        const uint32_t k = item.y + wid;                 // this warp's restart interval
-        if (k >= im.nseg) continue;
-        const uint32_t sidx = im.seg_first + k;
-        const uint32_t s0 = b.seg_start[sidx], s1 = b.seg_end[sidx];
-        WarpBits s;
-        wb_init(s, sh.ring[wid], b.bits + im.scan_off + s0, s1 - s0, lane);
-        const uint32_t m0 = k * im.ri;
-        const uint32_t m1 = min(m0 + im.ri, im.nmcu);
-        uint32_t mx = m0 % im.mcu_xmax, my = m0 / im.mcu_xmax;
-        int dc0 = 0, dc1 = 0, dc2 = 0;
-        uint32_t status = 0;
-        int16_t* coef = b.coef;
-        for (uint32_t m = m0; m < m1 && !(status & 3); m++) {
-            if (lane == 0) b.mcu_bitpos[im.mcu_off + m] = wb_consumed(s);
-            for (uint32_t c = 0; c < im.ns; c++) {
-                const uint16_t* lut_dc = sh.lut[c * 2];
-                const uint16_t* lut_ac = sh.lut[c * 2 + 1];
-                const uint32_t* qz = sh.qz[c];
-                const uint32_t nh = im.H[c], nv = im.V[c];
-                uint32_t hdc = 0, hac = 0;
-                int dc = (c == 0) ? dc0 : (c == 1) ? dc1 : dc2;
-                for (uint32_t v = 0; v < nv; v++) for (uint32_t h = 0; h < nh; h++) {
-                    uint32_t acc = 0;      // this lane's two coefficients (natural 2*lane, 2*lane+1)
-                    int dcdiff = 0;
-                    uint32_t pos = 0;
-                    bool dcphase = true, done = false;
-                    while (!done) {
-                        if (s.nb <= 32) wb_refill(s, lane);
-                        uint32_t len;
-                        int sym = huff_symbol(s, dcphase ? lut_dc : lut_ac, ts, dcphase ? im.slot_dc[c] : im.slot_ac[c], len);
-                        if (sym < 0) { status |= 1; break; }
-                        if (dcphase) hdc += (lane == len); else hac += (lane == len);
-                        uint32_t run = (uint32_t)sym >> 4, size = (uint32_t)sym & 15;
-                        bool eob = (sym == 0);
-                        if (!eob || dcphase) {
-                            int val = eob ? 0 : huff_value(s, size, im.precision);
-                            uint32_t kk = pos + run;
-                            if (kk < 64 && (dcphase || b.decode_ac)) {
-                                uint32_t q = qz[kk];
-                                int cf = (int)(short)((short)val * (int)(q & 0xFFFF));    // DecodeIdctSet, :2278
-                                uint32_t nat = q >> 16;
-                                if (nat == 0) dcdiff = cf;
-                                else if (lane == (nat >> 1)) acc = (nat & 1) ? ((acc & 0x0000FFFFu) | ((uint32_t)cf << 16)) : ((acc & 0xFFFF0000u) | ((uint32_t)cf & 0xFFFFu));
-                            }
-                        }
-                        if (eob && !dcphase) { done = true; }
-                        else {
-                            pos += 1 + run;
-                            if (pos == 64) done = true;
-                            else if (pos > 64) { status |= 4; done = true; }
-                        }
-                        dcphase = false;
-                    }
-                    dc = (int)(short)(dc + dcdiff);                    // m_nDcLum += m_anDctBlock[0], :3280
-                    if (lane == 0) acc = (acc & 0xFFFF0000u) | ((uint32_t)dc & 0xFFFFu);
-                    size_t row = im.coef_row[c] + (size_t)(my * nv + v) * im.cw[c] + (mx * nh + h);
-                    reinterpret_cast<uint32_t*>(coef)[row * 32 + lane] = acc;
-                    if (status & 1) break;
-                }
-                if (c == 0) dc0 = dc; else if (c == 1) dc1 = dc; else dc2 = dc;
-                if (b.want_histo && lane >= 1 && lane <= 16) { atomicAdd(&sh.histo[c * 2][lane], hdc); atomicAdd(&sh.histo[c * 2 + 1][lane], hac); }
-                if (status & 1) break;
-            }
-            if (++mx == im.mcu_xmax) { mx = 0; my++; }
-        }
-        // interval epilogue: overrun / leftover detection
-        while (!s.drained) wb_fill(s, lane);
-        uint32_t consumed = wb_consumed(s), avail = s.data_bytes * 8;
-        if (consumed > avail) status |= 2;
-        else if (!(status & 1) && avail - consumed >= 8) status |= 16;
-        if (lane == 0) {
-            b.seg_endbits[sidx] = consumed;
-            b.seg_status[sidx] = status;
-            if (status) atomicOr(&b.img_status[item.x], status);
-        }
-    }
-    // flush the histogram of the last image this CTA worked on
-    __syncthreads();
-    if (cur_img != 0xffffffffu && b.want_histo) {
-        const DevImage& pim = b.img[cur_img];
-        for (uint32_t i = threadIdx.x; i < 6 * 17; i += blockDim.x) {
-            uint32_t c = i / 34, cls = (i / 17) & 1, l = i % 17;
-            uint32_t v = sh.histo[c * 2 + cls][l];
-            if (v && c < pim.ns) { uint32_t slot = cls ? pim.slot_ac[c] : pim.slot_dc[c]; atomicAdd(&b.histo[((size_t)cur_img * 8 + slot) * 17 + l], v); }
-        }
-    }
-}
-
-int js_launch_huffman_warp(const DevBatch& b, int sm_count, cudaStream_t s)
-{
-    if (b.nitems == 0) return 0;
-    uint32_t grid = (uint32_t)sm_count * 8;
-    if (grid > b.nitems) grid = b.nitems;
-    k_huff_warp<<<grid, JS_HUFF_WARPS * 32, 0, s>>>(b);
-    return 1;
-}
-
-int js_launch_huffman_lane(const DevBatch& b, int sm_count, cudaStream_t s)
-{
-    return js_launch_huffman_warp(b, sm_count, s);   // lane-per-interval kernel: see jsgpu_huff_lane.cu (later)
-}
-
-// ------------------------------------------------------------------------------------------------
 // K2 (simple form): straightforward IDCT and colour kernels.  These are the readable,
 // obviously-correct statement of Appendix A.8-A.10 of SURVEY.md on the device; the fused tiled
 // kernel (js_launch_idct_fused) is checked against them and against the CPU oracle.
@@ -409,7 +114,7 @@ __global__ void __launch_bounds__(256) k_idct_simple(DevBatch b, const int32_t* 
 {
     // one thread per (block, sample); blockIdx.y = image
     const DevImage& im = b.img[blockIdx.y];
-    if (!im.valid) return;
+    if (!im.valid || (b.simple_only_nonstd && im.std_layout)) return;
     uint32_t nblk = im.nmcu * im.bpm;
     for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < nblk * 64; g += gridDim.x * blockDim.x) {
         uint32_t blk = g >> 6, yx = g & 63;
@@ -468,7 +173,7 @@ __global__ void __launch_bounds__(256) k_color_simple(DevBatch b)
 {
     // CalcChannelPreviewFull (ImgDecode.cpp:4693-4792), PREVIEW_RGB, no preview shift
     const DevImage& im = b.img[blockIdx.y];
-    if (!im.valid) return;
+    if (!im.valid || (b.simple_only_nonstd && im.std_layout)) return;
     const uint32_t npx = im.wp * im.hp;
     unsigned long long best = 0, sum = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += gridDim.x * blockDim.x) {
@@ -493,11 +198,6 @@ int js_launch_idct_simple(const DevBatch& b, const int32_t* li, const float* lf,
     k_idct_simple<<<grid, 256, 0, s>>>(b, li, lf);
     k_color_simple<<<grid, 256, 0, s>>>(b);
     return 2;
-}
-
-int js_launch_idct_fused(const DevBatch& b, const int32_t* li, const float* lf, int, cudaStream_t s)
-{
-    return js_launch_idct_simple(b, li, lf, 0, 0, s);     // replaced by the tiled kernel (jsgpu_idct.cu)
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -613,4 +313,3 @@ int js_launch_finalize(const DevBatch& b, cudaStream_t s)
     return 2;
 }
 
-int js_upload_idct_const(const int32_t*, const float*, cudaStream_t) { return 0; }

@@ -22,11 +22,12 @@ def cases():
     return JC.small_cases()
 
 
+@pytest.mark.parametrize("kernels", [(1, 1), (2, 2), (1, 2), (2, 1), (0, 0)], ids=["warp+simple", "lane+fused", "warp+fused", "lane+simple", "auto"])
 @pytest.mark.parametrize("fixed", [True, False], ids=["idct_fixed", "idct_float"])
-def test_single_image_dropin_matches_oracle(built, cases, fixed):
+def test_single_image_dropin_matches_oracle(built, cases, fixed, kernels):
     from jpegsnoop_b200 import CimgDecode
     orc = _oracle(fixed)
-    dec = CimgDecode(idct_fixedpt=fixed, idct_kernel=1)
+    dec = CimgDecode(idct_fixedpt=fixed, huff_kernel=kernels[0], idct_kernel=kernels[1])
     for name, j in cases:
         want = orc.decode(j)
         got = dec.decode(j)
@@ -37,10 +38,11 @@ def test_single_image_dropin_matches_oracle(built, cases, fixed):
         assert np.array_equal(want_stats, got_stats), (name, want_stats, got_stats)
 
 
-def test_batch_matches_oracle(built, cases):
+@pytest.mark.parametrize("kernels", [(1, 1), (2, 2), (0, 0)], ids=["warp+simple", "lane+fused", "auto"])
+def test_batch_matches_oracle(built, cases, kernels):
     from jpegsnoop_b200 import BatchDecoder
     orc = _oracle(True)
-    bd = BatchDecoder(idct_kernel=1)
+    bd = BatchDecoder(huff_kernel=kernels[0], idct_kernel=kernels[1])
     jpegs = [j for _, j in cases]
     bd.set_batch(jpegs)
     bd.decode(); bd.sync()
