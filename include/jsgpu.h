@@ -185,6 +185,10 @@ int jsgpu_batch_download(jsgpu_ctx* ctx, int which, uint32_t image, void* host_d
  * context stream: [0] marker scan, [1] Huffman, [2] IDCT+colour, [3] stats/map finalise,
  * [4] total.  Forces a sync. */
 int jsgpu_batch_stage_ms(jsgpu_ctx* ctx, float* ms5);
+/* Device stopwatch on the context stream (CUDA events): start records an event, stop records a
+ * second one, synchronises on it and returns the elapsed milliseconds. */
+int jsgpu_timer_start(jsgpu_ctx* ctx);
+int jsgpu_timer_stop(jsgpu_ctx* ctx, float* ms);
 /* Number of kernels launched by the last jsgpu_batch_decode. */
 int jsgpu_batch_launches(jsgpu_ctx* ctx);
 

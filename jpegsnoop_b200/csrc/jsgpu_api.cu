@@ -32,6 +32,7 @@ struct jsgpu_ctx {
     int device = 0, sm_count = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6] = {};
+    cudaEvent_t tev[2] = {};
     std::string err;
     jsgpu_options opt;
     bool have_idct = false;
@@ -96,6 +97,7 @@ int jsgpu_init(int device, jsgpu_ctx** out)
     ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return JSGPU_ECUDA; }
     for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+    for (auto& ev : ctx->tev) cudaEventCreate(&ev);
     memset(&ctx->opt, 0, sizeof ctx->opt);
     ctx->opt.decode_ac = 1; ctx->opt.want_histo = 1; ctx->opt.want_mcu_map = 1; ctx->opt.device_markers = 1;
     memset(&ctx->batch, 0, sizeof ctx->batch);
@@ -112,6 +114,7 @@ void jsgpu_free(jsgpu_ctx* ctx)
                        &ctx->d_coef, &ctx->d_mcubits, &ctx->d_pix, &ctx->d_dib, &ctx->d_blk, &ctx->d_mcumap, &ctx->d_histo, &ctx->d_stats, &ctx->d_misc };
     for (auto* b : bufs) b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->tev) if (ev) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -540,6 +543,23 @@ int jsgpu_batch_decode(jsgpu_ctx* ctx)
     CK(cudaGetLastError());
     ctx->launches = launches;
     ctx->decoded = true;
+    return JSGPU_OK;
+}
+
+int jsgpu_timer_start(jsgpu_ctx* ctx)
+{
+    if (!ctx) return JSGPU_EINVAL;
+    cudaSetDevice(ctx->device);
+    CK(cudaEventRecord(ctx->tev[0], ctx->stream));
+    return JSGPU_OK;
+}
+int jsgpu_timer_stop(jsgpu_ctx* ctx, float* ms)
+{
+    if (!ctx || !ms) return JSGPU_EINVAL;
+    cudaSetDevice(ctx->device);
+    CK(cudaEventRecord(ctx->tev[1], ctx->stream));
+    CK(cudaEventSynchronize(ctx->tev[1]));
+    CK(cudaEventElapsedTime(ms, ctx->tev[0], ctx->tev[1]));
     return JSGPU_OK;
 }
 

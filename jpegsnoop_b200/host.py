@@ -235,6 +235,20 @@ class BatchDecoder:
     def stream(self): return self.L.jsgpu_stream(self.ctx)
     def launches(self): return int(self.L.jsgpu_batch_launches(self.ctx))
 
+    def timer_start(self): self._ck(self.L.jsgpu_timer_start(self.ctx))
+
+    def timer_stop(self):
+        ms = C.c_float(0); self._ck(self.L.jsgpu_timer_stop(self.ctx, C.byref(ms))); return float(ms.value)
+
+    def decode_host(self, darr, bits, outs):
+        """One-call end-to-end form (jsgpu_decode_batch_host): host bitstream in, host buffers out.
+        outs: dict name -> numpy array (pinned or pageable) for any of the jsgpu_host_outputs fields."""
+        ho = B.jsgpu_host_outputs()
+        for k, a in outs.items():
+            setattr(ho, k, a.ctypes.data)
+        self.descs = darr; self.n = len(darr)
+        self._ck(self.L.jsgpu_decode_batch_host(self.ctx, C.byref(darr), self.n, bits.ctypes.data, bits.size, C.byref(ho)))
+
     def stage_ms(self):
         ms = np.zeros(5, np.float32); self._ck(self.L.jsgpu_batch_stage_ms(self.ctx, ms.ctypes.data)); return ms
 
