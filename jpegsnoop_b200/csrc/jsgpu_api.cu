@@ -37,6 +37,7 @@ struct jsgpu_ctx {
     jsgpu_options opt;
     bool have_idct = false;
     // device state
+    DevBuf d_ctab; bool have_ctab = false;
     DevBuf d_li, d_lf, d_sym, d_tables, d_img, d_items, d_litems, d_tiles, d_ubits, d_seg64;
     bool sym_ok = false;
     DevBuf d_bits, d_seg, d_coef, d_mcubits, d_pix, d_dib, d_blk, d_mcumap, d_histo, d_stats, d_misc;
@@ -110,7 +111,7 @@ void jsgpu_free(jsgpu_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = { &ctx->d_li, &ctx->d_lf, &ctx->d_sym, &ctx->d_tables, &ctx->d_img, &ctx->d_items, &ctx->d_litems, &ctx->d_tiles, &ctx->d_ubits, &ctx->d_seg64, &ctx->d_bits, &ctx->d_seg,
+    DevBuf* bufs[] = { &ctx->d_ctab, &ctx->d_li, &ctx->d_lf, &ctx->d_sym, &ctx->d_tables, &ctx->d_img, &ctx->d_items, &ctx->d_litems, &ctx->d_tiles, &ctx->d_ubits, &ctx->d_seg64, &ctx->d_bits, &ctx->d_seg,
                        &ctx->d_coef, &ctx->d_mcubits, &ctx->d_pix, &ctx->d_dib, &ctx->d_blk, &ctx->d_mcumap, &ctx->d_histo, &ctx->d_stats, &ctx->d_misc };
     for (auto* b : bufs) b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -175,6 +176,12 @@ int jsgpu_set_idct_tables(jsgpu_ctx* ctx, const int32_t* li, const float* lf)
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     delete sym;
     if (e != cudaSuccess) return fail(ctx, JSGPU_ECUDA, "idct table upload failed: %s", cudaGetErrorString(e));
+    if (!ctx->have_ctab) {      // colour tables: built and verified on the device once per context
+        if (ctx->d_ctab.reserve(sizeof(ColorTabs)) != cudaSuccess) return fail(ctx, JSGPU_ENOMEM, "colour table allocation failed");
+        js_launch_build_color_tables((ColorTabs*)ctx->d_ctab.p, ctx->stream);
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail(ctx, JSGPU_ECUDA, "colour table build failed");
+        ctx->have_ctab = true;
+    }
     ctx->have_idct = true;
     return JSGPU_OK;
 }
@@ -527,7 +534,7 @@ int jsgpu_batch_decode(jsgpu_ctx* ctx)
         // fused tile kernel: integer IDCT, standard sampling layouts, decomposable table; everything
         // else (float IDCT, exotic sampling, a libm whose table does not decompose) takes the simple kernels
         const bool fused = (ctx->opt.idct_kernel != 1) && ctx->opt.idct_mode == 0 && ctx->sym_ok && b.ntiles > 0;
-        if (fused) launches += js_launch_idct_fused(b, (const IdctSym*)ctx->d_sym.p, (const int32_t*)ctx->d_li.p, (const float*)ctx->d_lf.p, ctx->sm_count, s);
+        if (fused) launches += js_launch_idct_fused(b, (const IdctSym*)ctx->d_sym.p, (const ColorTabs*)ctx->d_ctab.p, ctx->sm_count, s);
         if (!fused || ctx->n_nonstd > 0) {
             DevBatch bs = b; bs.simple_only_nonstd = fused ? 1 : 0;
             launches += js_launch_idct_simple(bs, (const int32_t*)ctx->d_li.p, (const float*)ctx->d_lf.p, 0, 0, s);

@@ -122,14 +122,16 @@ __device__ __forceinline__ uint32_t huff_level2(const DevTableSet* ts, uint32_t 
 
 // Per-thread bit reader over an unstuffed, 4-byte aligned, 0xFF-padded interval.
 struct Bits {
-    unsigned long long w; int nb; const uint32_t* p; uint32_t words;
+    unsigned long long w; int nb; const uint32_t* p; uint32_t words; uint32_t nx;
     __device__ __forceinline__ void init(const uint8_t* base) {
         p = reinterpret_cast<const uint32_t*>(base);
         uint32_t a = __byte_perm(__ldg(p), 0, 0x0123), c = __byte_perm(__ldg(p + 1), 0, 0x0123);
-        w = ((unsigned long long)a << 32) | c; nb = 64; p += 2; words = 2;
+        nx = __ldg(p + 2);                                 // always one word ahead: the load latency hides behind ~6 symbols
+        w = ((unsigned long long)a << 32) | c; nb = 64; p += 3; words = 2;
     }
     __device__ __forceinline__ void refill() {          // call when nb <= 32
-        uint32_t x = __byte_perm(__ldg(p), 0, 0x0123);
+        uint32_t x = __byte_perm(nx, 0, 0x0123);
+        nx = __ldg(p);
         w |= (unsigned long long)x << (32 - nb);
         nb += 32; p++; words++;
     }

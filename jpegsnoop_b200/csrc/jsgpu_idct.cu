@@ -27,6 +27,8 @@ struct __align__(16) IdctSmemTables {
     int4 s4[64 * 4];            // [vu*4 + g] -> S for quadrant samples 4g..4g+3
     int4 corrT[64];             // [yx] -> D[0..3][yx]
     int  ncorr; int corr_pos[4];
+    int  rb_ok; int pad0, pad1;
+    int16_t tr[256], tb[256];   // chroma terms of R and B (+128 folded in)
 };
 
 // ConvertYCCtoRGBFastFloat (ImgDecode.cpp:4086-4139), one IEEE rounding per operation.
@@ -52,20 +54,111 @@ __device__ __forceinline__ uint32_t ycc_to_bgra(int py, int pcb, int pcr, uint32
 __device__ __forceinline__ uint32_t fin(int s, int dc)
 {
     int r = (s + ((s >> 31) & 3)) >> 12;          // trunc(s/4) then floor(>>10) == (s + (s<0?3:0)) >> 12
-    int n = (int)(short)r;
-    return (uint32_t)(n * 8 + dc) & 0xFFFFu;
+    return (uint32_t)(r * 8 + dc) & 0xFFFFu;      // (short)r*8 + dc and r*8 + dc agree in their low 16 bits
 }
 
-__global__ void __launch_bounds__(IDCT_THREADS, 4) k_idct_tile(DevBatch b, const IdctSym* __restrict__ sym)
+struct P2Args {
+    const uint8_t* planes; uint32_t pbase1, pbase2, ppitch0, ppitch1, ppitch2;
+    uint32_t opr, px0, py0, wp, hp, mcu_h, ns, evc;
+    int16_t* mapy; int16_t* mapcb; int16_t* mapcr; uint8_t* dib; const int16_t* tg;
+};
+
+// Phase 2 for chroma horizontal replication 1 << EHS.  lane = octet column of the tile (8 pixels), warps take
+// row groups (evc luma rows sharing one chroma row).  The colour terms are looked up once per distinct chroma
+// sample; pixels whose (cb,cr) pair is marked inexact in the verified table take the exact float routine.
+template <int EHS>
+__device__ __forceinline__ void phase2(const P2Args& a, const IdctSmemTables& T, uint32_t lane, uint32_t wid, unsigned long long& best, uint32_t& sum)
+{
+    constexpr int NC = 8 >> EHS;                 // distinct chroma samples under 8 pixels
+    const uint32_t nwarps = blockDim.x >> 5;
+    const uint32_t px = lane * 8;
+    for (uint32_t rg = wid; rg * a.evc < a.mcu_h; rg += nwarps) {
+        if (lane >= a.opr) continue;
+        int cbs[NC], crs[NC], tR[NC], tG[NC], tB[NC];
+        uint32_t cbw[4], crw[4];                  // replicated chroma, packed for the map stores
+        uint32_t unsafe = 0;
+        if (a.ns == 3) {
+            const uint8_t* pcb = a.planes + a.pbase1 + rg * a.ppitch1 + ((px >> EHS) << 1);
+            const uint8_t* pcr = a.planes + a.pbase2 + rg * a.ppitch2 + ((px >> EHS) << 1);
+            if (EHS == 0) {
+                const uint4 u = *reinterpret_cast<const uint4*>(pcb), v = *reinterpret_cast<const uint4*>(pcr);
+                cbw[0] = u.x; cbw[1] = u.y; cbw[2] = u.z; cbw[3] = u.w; crw[0] = v.x; crw[1] = v.y; crw[2] = v.z; crw[3] = v.w;
+                #pragma unroll
+                for (int j = 0; j < NC; j++) { cbs[j] = (j & 1) ? ((int)cbw[j >> 1] >> 16) : (int)(short)(cbw[j >> 1] & 0xFFFF); crs[j] = (j & 1) ? ((int)crw[j >> 1] >> 16) : (int)(short)(crw[j >> 1] & 0xFFFF); }
+            } else if (EHS == 1) {
+                const uint2 u = *reinterpret_cast<const uint2*>(pcb), v = *reinterpret_cast<const uint2*>(pcr);
+                const uint32_t uw[2] = {u.x, u.y}, vw[2] = {v.x, v.y};
+                #pragma unroll
+                for (int j = 0; j < NC; j++) { cbs[j] = (j & 1) ? ((int)uw[j >> 1] >> 16) : (int)(short)(uw[j >> 1] & 0xFFFF); crs[j] = (j & 1) ? ((int)vw[j >> 1] >> 16) : (int)(short)(vw[j >> 1] & 0xFFFF); }
+                cbw[0] = __byte_perm(u.x, 0, 0x1010); cbw[1] = __byte_perm(u.x, 0, 0x3232); cbw[2] = __byte_perm(u.y, 0, 0x1010); cbw[3] = __byte_perm(u.y, 0, 0x3232);
+                crw[0] = __byte_perm(v.x, 0, 0x1010); crw[1] = __byte_perm(v.x, 0, 0x3232); crw[2] = __byte_perm(v.y, 0, 0x1010); crw[3] = __byte_perm(v.y, 0, 0x3232);
+            } else {
+                const uint32_t u = *reinterpret_cast<const uint32_t*>(pcb), v = *reinterpret_cast<const uint32_t*>(pcr);
+                cbs[0] = (int)(short)(u & 0xFFFF); cbs[1] = (int)u >> 16; crs[0] = (int)(short)(v & 0xFFFF); crs[1] = (int)v >> 16;
+                cbw[0] = cbw[1] = __byte_perm(u, 0, 0x1010); cbw[2] = cbw[3] = __byte_perm(u, 0, 0x3232);
+                crw[0] = crw[1] = __byte_perm(v, 0, 0x1010); crw[2] = crw[3] = __byte_perm(v, 0, 0x3232);
+            }
+        } else {
+            #pragma unroll
+            for (int j = 0; j < NC; j++) { cbs[j] = 0; crs[j] = 0; }
+            cbw[0] = cbw[1] = cbw[2] = cbw[3] = 0; crw[0] = crw[1] = crw[2] = crw[3] = 0;
+        }
+        #pragma unroll
+        for (int j = 0; j < NC; j++) {
+            const int cbc = max(-128, min(127, cbs[j] >> 3)), crc = max(-128, min(127, crs[j] >> 3));
+            const int g = (short)__ldg(&a.tg[((cbc + 128) << 8) | (crc + 128)]);
+            tR[j] = T.tr[crc + 128]; tB[j] = T.tb[cbc + 128]; tG[j] = g;
+            if (g == 0x7FFF) unsafe |= ((1u << (1 << EHS)) - 1) << (j << EHS);
+        }
+        if (!T.rb_ok) unsafe = 0xFF;
+        for (uint32_t r2 = 0; r2 < a.evc; r2++) {
+            const uint32_t oy = rg * a.evc + r2;
+            const uint4 yv = *reinterpret_cast<const uint4*>(a.planes + oy * a.ppitch0 + px * 2);
+            const uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w};
+            const uint32_t ay = a.py0 + oy, ax = a.px0 + px;
+            const size_t mi = (size_t)ay * a.wp + ax;
+            *reinterpret_cast<uint4*>(a.mapy + mi) = yv;
+            if (a.ns == 3) {
+                *reinterpret_cast<uint4*>(a.mapcb + mi) = make_uint4(cbw[0], cbw[1], cbw[2], cbw[3]);
+                *reinterpret_cast<uint4*>(a.mapcr + mi) = make_uint4(crw[0], crw[1], crw[2], crw[3]);
+            }
+            uint32_t bgra[8]; int vmax = -0x7fffffff - 1;
+            #pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int yraw = (k & 1) ? ((int)yw[k >> 1] >> 16) : (int)(short)(yw[k >> 1] & 0xFFFF);
+                const int yc = max(-128, min(127, yraw >> 3));
+                const uint32_t r = (uint32_t)min(255, max(0, yc + tR[k >> EHS])), g = (uint32_t)min(255, max(0, yc + tG[k >> EHS])), bl = (uint32_t)min(255, max(0, yc + tB[k >> EHS]));
+                bgra[k] = bl | (g << 8) | (r << 16);
+                sum += (uint32_t)(yc + 128);
+                vmax = max(vmax, (yraw << 3) | (7 - k));              // first strict maximum in raster order
+            }
+            if (unsafe) {
+                #pragma unroll
+                for (int k = 0; k < 8; k++) if (unsafe >> k & 1) {
+                    const int yraw = (k & 1) ? ((int)yw[k >> 1] >> 16) : (int)(short)(yw[k >> 1] & 0xFFFF);
+                    uint32_t fy; bgra[k] = ycc_to_bgra(yraw, cbs[k >> EHS], crs[k >> EHS], fy);
+                }
+            }
+            const unsigned long long key = ((unsigned long long)(uint32_t)((vmax >> 3) + 32768) << 32) | (0xffffffffu - (uint32_t)(mi + (7 - (vmax & 7))));
+            best = max(best, key);
+            uint4* dp = reinterpret_cast<uint4*>(a.dib + ((size_t)(a.hp - 1 - ay) * a.wp + ax) * 4);
+            dp[0] = make_uint4(bgra[0], bgra[1], bgra[2], bgra[3]);
+            dp[1] = make_uint4(bgra[4], bgra[5], bgra[6], bgra[7]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(IDCT_THREADS, 4) k_idct_tile(DevBatch b, const IdctSym* __restrict__ sym, const ColorTabs* __restrict__ ctab)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     IdctSmemTables& T = *reinterpret_cast<IdctSmemTables*>(smem);
     uint8_t* const planes = smem + sizeof(IdctSmemTables);
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     // stage the decomposed table once per CTA
-    for (uint32_t i = tid; i < 64 * 4; i += IDCT_THREADS) T.s4[i] = reinterpret_cast<const int4*>(sym->s4)[i];
-    for (uint32_t i = tid; i < 64; i += IDCT_THREADS) T.corrT[i] = make_int4(sym->corr[0][i], sym->corr[1][i], sym->corr[2][i], sym->corr[3][i]);
-    if (tid == 0) { T.ncorr = sym->ncorr; for (int j = 0; j < 4; j++) T.corr_pos[j] = sym->corr_pos[j]; }
+    for (uint32_t i = tid; i < 64 * 4; i += blockDim.x) T.s4[i] = reinterpret_cast<const int4*>(sym->s4)[i];
+    for (uint32_t i = tid; i < 64; i += blockDim.x) T.corrT[i] = make_int4(sym->corr[0][i], sym->corr[1][i], sym->corr[2][i], sym->corr[3][i]);
+    if (tid == 0) { T.ncorr = sym->ncorr; for (int j = 0; j < 4; j++) T.corr_pos[j] = sym->corr_pos[j]; T.rb_ok = ctab->rb_ok; }
+    for (uint32_t i = tid; i < 256; i += blockDim.x) { T.tr[i] = ctab->tr[i]; T.tb[i] = ctab->tb[i]; }
     __syncthreads();
     const int ncorr = T.ncorr;
 
@@ -82,7 +175,7 @@ __global__ void __launch_bounds__(IDCT_THREADS, 4) k_idct_tile(DevBatch b, const
         const uint32_t ppitch0 = hu0 * 16, ppitch1 = hu1 * 16, ppitch2 = hu2 * 16;
         const uint32_t nblk = cnt0 + cnt1 + cnt2;
         // ---------------- phase 1: one block per lane ----------------
-        for (uint32_t g = wid; g * 32 < nblk; g += IDCT_THREADS / 32) {
+        for (uint32_t g = wid; g * 32 < nblk; g += (blockDim.x >> 5)) {
             uint32_t i = g * 32 + lane;
             uint32_t c = 0;
             if (i >= cnt0) { i -= cnt0; c = 1; if (i >= cnt1) { i -= cnt1; c = 2; } }
@@ -155,91 +248,75 @@ __global__ void __launch_bounds__(IDCT_THREADS, 4) k_idct_tile(DevBatch b, const
             }
         }
         __syncthreads();
-        // ---------------- phase 2: 8 pixels per thread, vector stores ----------------
+        // ---------------- phase 2: 8 pixels x (chroma row group) per thread, vector stores ----------------
         {
-            const uint32_t tw = nmt * im.mcu_w;                   // valid pixel columns of this tile
-            const uint32_t noct = (tw >> 3) * im.mcu_h;
-            const uint32_t px0 = mcol0 * im.mcu_w, py0 = trow * im.mcu_h;
-            int16_t* const mapy = b.pix_y + im.pix_off;
-            int16_t* const mapcb = b.pix_cb + im.pix_off;
-            int16_t* const mapcr = b.pix_cr + im.pix_off;
-            uint8_t* const dib = b.dib + im.dib_off;
-            unsigned long long best = 0, sum = 0;
-            const uint32_t ehc = (ns == 3) ? im.eh[1] : 1, evc = (ns == 3) ? im.ev[1] : 1;
-            for (uint32_t o = tid; o < noct; o += IDCT_THREADS) {
-                const uint32_t oy = o / (tw >> 3), ox = o - oy * (tw >> 3);
-                const uint32_t px = ox * 8;
-                // luma (eh = ev = 1 for the max-sampled component of a standard layout)
-                const uint4 yv = *reinterpret_cast<const uint4*>(planes + pbase0 + oy * ppitch0 + px * 2);
-                int ys[8] = { (short)(yv.x & 0xFFFF), (int)yv.x >> 16, (short)(yv.y & 0xFFFF), (int)yv.y >> 16,
-                              (short)(yv.z & 0xFFFF), (int)yv.z >> 16, (short)(yv.w & 0xFFFF), (int)yv.w >> 16 };
-                int cbs[8], crs[8];
-                if (ns == 3) {
-                    const uint8_t* pcb = planes + pbase1 + (oy / evc) * ppitch1 + (px / ehc) * 2;
-                    const uint8_t* pcr = planes + pbase2 + (oy / evc) * ppitch2 + (px / ehc) * 2;
-                    if (ehc == 1) {
-                        const uint4 a = *reinterpret_cast<const uint4*>(pcb), c4 = *reinterpret_cast<const uint4*>(pcr);
-                        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, cw2[4] = {c4.x, c4.y, c4.z, c4.w};
-                        #pragma unroll
-                        for (int k = 0; k < 4; k++) { cbs[2 * k] = (short)(aw[k] & 0xFFFF); cbs[2 * k + 1] = (int)aw[k] >> 16; crs[2 * k] = (short)(cw2[k] & 0xFFFF); crs[2 * k + 1] = (int)cw2[k] >> 16; }
-                    } else if (ehc == 2) {
-                        const uint2 a = *reinterpret_cast<const uint2*>(pcb), c2 = *reinterpret_cast<const uint2*>(pcr);
-                        const uint32_t aw[2] = {a.x, a.y}, cw2[2] = {c2.x, c2.y};
-                        #pragma unroll
-                        for (int k = 0; k < 2; k++) {
-                            int lo = (short)(aw[k] & 0xFFFF), hi = (int)aw[k] >> 16; cbs[4 * k] = cbs[4 * k + 1] = lo; cbs[4 * k + 2] = cbs[4 * k + 3] = hi;
-                            lo = (short)(cw2[k] & 0xFFFF); hi = (int)cw2[k] >> 16; crs[4 * k] = crs[4 * k + 1] = lo; crs[4 * k + 2] = crs[4 * k + 3] = hi;
-                        }
-                    } else {    // ehc == 4
-                        const uint32_t a = *reinterpret_cast<const uint32_t*>(pcb), c1 = *reinterpret_cast<const uint32_t*>(pcr);
-                        int lo = (short)(a & 0xFFFF), hi = (int)a >> 16;
-                        #pragma unroll
-                        for (int k = 0; k < 4; k++) { cbs[k] = lo; cbs[4 + k] = hi; }
-                        lo = (short)(c1 & 0xFFFF); hi = (int)c1 >> 16;
-                        #pragma unroll
-                        for (int k = 0; k < 4; k++) { crs[k] = lo; crs[4 + k] = hi; }
-                    }
-                } else {
-                    #pragma unroll
-                    for (int k = 0; k < 8; k++) { cbs[k] = 0; crs[k] = 0; }
-                }
-                const uint32_t ay = py0 + oy, ax = px0 + px;
-                const size_t mi = (size_t)ay * im.wp + ax;
-                *reinterpret_cast<uint4*>(mapy + mi) = yv;
-                if (ns == 3) {
-                    *reinterpret_cast<uint4*>(mapcb + mi) = make_uint4((cbs[0] & 0xFFFF) | (cbs[1] << 16), (cbs[2] & 0xFFFF) | (cbs[3] << 16), (cbs[4] & 0xFFFF) | (cbs[5] << 16), (cbs[6] & 0xFFFF) | (cbs[7] << 16));
-                    *reinterpret_cast<uint4*>(mapcr + mi) = make_uint4((crs[0] & 0xFFFF) | (crs[1] << 16), (crs[2] & 0xFFFF) | (crs[3] << 16), (crs[4] & 0xFFFF) | (crs[5] << 16), (crs[6] & 0xFFFF) | (crs[7] << 16));
-                }
-                uint32_t bgra[8];
-                #pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    uint32_t fy;
-                    bgra[k] = ycc_to_bgra(ys[k], cbs[k], crs[k], fy);
-                    sum += fy;
-                    unsigned long long key = ((unsigned long long)(uint32_t)(ys[k] + 32768) << 32) | (0xffffffffu - (uint32_t)(mi + k));
-                    best = max(best, key);
-                }
-                uint4* dp = reinterpret_cast<uint4*>(dib + ((size_t)(im.hp - 1 - ay) * im.wp + ax) * 4);
-                dp[0] = make_uint4(bgra[0], bgra[1], bgra[2], bgra[3]);
-                dp[1] = make_uint4(bgra[4], bgra[5], bgra[6], bgra[7]);
-            }
+            P2Args a;
+            a.planes = planes; a.pbase1 = pbase1; a.pbase2 = pbase2; a.ppitch0 = ppitch0; a.ppitch1 = ppitch1; a.ppitch2 = ppitch2;
+            a.opr = (nmt * im.mcu_w) >> 3; a.px0 = mcol0 * im.mcu_w; a.py0 = trow * im.mcu_h; a.wp = im.wp; a.hp = im.hp; a.mcu_h = im.mcu_h;
+            a.mapy = b.pix_y + im.pix_off; a.mapcb = b.pix_cb + im.pix_off; a.mapcr = b.pix_cr + im.pix_off; a.dib = b.dib + im.dib_off;
+            a.ns = ns; a.evc = (ns == 3) ? im.ev[1] : 1; a.tg = ctab->tg;
+            const uint32_t eh = (ns == 3) ? im.eh[1] : 1;
+            unsigned long long best = 0; uint32_t sum = 0;
+            if (eh == 1) phase2<0>(a, T, lane, wid, best, sum); else if (eh == 2) phase2<1>(a, T, lane, wid, best, sum); else phase2<2>(a, T, lane, wid, best, sum);
+            unsigned long long sum64 = sum;
             #pragma unroll
-            for (int d = 16; d; d >>= 1) { best = max(best, __shfl_xor_sync(FULL, best, d)); sum += __shfl_xor_sync(FULL, sum, d); }
-            if (lane == 0 && noct) { atomicMax(&b.bright_key[tile.x], best); atomicAdd(&b.sum_y[tile.x], sum); }
+            for (int d = 16; d; d >>= 1) { best = max(best, __shfl_xor_sync(FULL, best, d)); sum64 += __shfl_xor_sync(FULL, sum64, d); }
+            if (lane == 0 && best) { atomicMax(&b.bright_key[tile.x], best); atomicAdd(&b.sum_y[tile.x], sum64); }
         }
         __syncthreads();
     }
 }
 
-int js_launch_idct_fused(const DevBatch& b, const IdctSym* sym, const int32_t*, const float*, int sm_count, cudaStream_t s)
+// ------------------------------------------------------------------------------------------------
+// Colour tables.  ConvertYCCtoRGBFastFloat is a function of three 8-bit integers (y,cb,cr after >>3
+// and clamping).  Mathematically R = y + 1.402cr + 128, B = y + 1.772cb + 128, G = y - (0.114*1.772cb +
+// 0.299*1.402cr)/0.587 + 128, i.e. "y plus a chroma term", and the float evaluation agrees with that
+// integer form except where a rounding lands next to an integer.  This kernel evaluates the EXACT float
+// routine for all 2^24 inputs on the device, derives the additive terms, and verifies them: tr/tb are
+// used only if they reproduce R/B for every (y,c) pair (rb_ok), and each (cb,cr) pair whose G term is
+// not valid for all 256 y values is marked 0x7FFF so those pixels take the exact float path.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_build_color_tables(ColorTabs* t)
+{
+    const int idx = blockIdx.x * 256 + threadIdx.x;          // 0..65535
+    const int cb = (idx >> 8) - 128, cr = (idx & 255) - 128;
+    const float cR = 0.299f, cG = 0.587f, cB = 0.114f;
+    const float kR = __fsub_rn(2.0f, __fmul_rn(2.0f, cR)), kB = __fsub_rn(2.0f, __fmul_rn(2.0f, cB));
+    // candidate terms from y = 0 (floor of the unclamped float, +128 included)
+    const float vr0 = __fadd_rn(__fmul_rn((float)cr, kR), 0.f), vb0 = __fadd_rn(__fmul_rn((float)cb, kB), 0.f);
+    const float vg0 = __fdiv_rn(__fsub_rn(__fsub_rn(0.f, __fmul_rn(cB, vb0)), __fmul_rn(cR, vr0)), cG);
+    const int dR = (int)floorf(__fadd_rn(vr0, 128.f)), dB = (int)floorf(__fadd_rn(vb0, 128.f)), dG = (int)floorf(__fadd_rn(vg0, 128.f));
+    bool okR = true, okB = true, okG = true;
+    for (int y = -128; y <= 127; y++) {
+        uint32_t fy; const uint32_t px = ycc_to_bgra(y << 3, cb << 3, cr << 3, fy);
+        const int r = (px >> 16) & 255, g = (px >> 8) & 255, bl = px & 255;
+        okR = okR && (r == min(255, max(0, y + dR))); okB = okB && (bl == min(255, max(0, y + dB))); okG = okG && (g == min(255, max(0, y + dG)));
+    }
+    t->tg[idx] = okG ? (int16_t)dG : (int16_t)0x7FFF;
+    if (!okG) atomicAdd(&t->n_unsafe, 1);
+    if (cb == 0) { t->tr[cr + 128] = (int16_t)dR; if (!okR) atomicAnd(&t->rb_ok, 0); }
+    if (cr == 0) { t->tb[cb + 128] = (int16_t)dB; if (!okB) atomicAnd(&t->rb_ok, 0); }
+}
+
+int js_launch_build_color_tables(ColorTabs* t, cudaStream_t s)
+{
+    ColorTabs init; memset(&init, 0, sizeof(int16_t) * 512); init.rb_ok = 1; init.n_unsafe = 0;
+    cudaMemcpyAsync(t, &init, offsetof(ColorTabs, tg), cudaMemcpyHostToDevice, s);
+    cudaStreamSynchronize(s);
+    k_build_color_tables<<<256, 256, 0, s>>>(t);
+    return 1;
+}
+
+int js_launch_idct_fused(const DevBatch& b, const IdctSym* sym, const ColorTabs* ctab, int sm_count, cudaStream_t s)
 {
     if (b.ntiles == 0) return 0;
-    const size_t smem = sizeof(IdctSmemTables) + 48 * 1024;      // planes: 128 B per block, <= 384 blocks per tile
     static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(k_idct_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
-    (void)smem;
-    uint32_t grid = (uint32_t)sm_count * 4;
+    if (!attr_set) { cudaFuncSetAttribute(k_idct_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(IdctSmemTables) + 48 * 1024)); attr_set = true; }
+    // one warp per 32-block group of a tile, at most 4 warps (larger tiles loop)
+    uint32_t groups = (b.tile_plane_bytes / 128 + 31) / 32;
+    uint32_t threads = 32 * (groups < 1 ? 1 : groups > 4 ? 4 : groups);
+    uint32_t grid = (uint32_t)sm_count * (threads <= 96 ? 5 : 4);
     if (grid > b.ntiles) grid = b.ntiles;
-    k_idct_tile<<<grid, IDCT_THREADS, sizeof(IdctSmemTables) + (size_t)b.tile_plane_bytes, s>>>(b, sym);
+    k_idct_tile<<<grid, threads, sizeof(IdctSmemTables) + (size_t)b.tile_plane_bytes, s>>>(b, sym, ctab);
     return 1;
 }

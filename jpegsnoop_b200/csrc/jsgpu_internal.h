@@ -107,8 +107,9 @@ int js_launch_huffman_warp(const DevBatch& b, int sm_count, cudaStream_t s);
 int js_launch_huffman_lane(const DevBatch& b, int sm_count, cudaStream_t s);
 int js_launch_idct_simple(const DevBatch& b, const int32_t* li, const float* lf, uint64_t total_blocks,
                           uint64_t total_pix, cudaStream_t s);
-struct IdctSym;
-int js_launch_idct_fused(const DevBatch& b, const IdctSym* sym, const int32_t* li, const float* lf, int sm_count, cudaStream_t s);
+struct IdctSym; struct ColorTabs;
+int js_launch_idct_fused(const DevBatch& b, const IdctSym* sym, const ColorTabs* ctab, int sm_count, cudaStream_t s);
+int js_launch_build_color_tables(ColorTabs* t, cudaStream_t s);
 int js_launch_finalize(const DevBatch& b, cudaStream_t s);
 
 // Quadrant-symmetric decomposition of the integer IDCT table (built on the host at table upload,
@@ -119,4 +120,13 @@ struct IdctSym {
     int32_t ncorr;               // number of coefficient positions with a non-zero correction (<= 4), -1 = not decomposable
     int32_t corr_pos[4];         // their natural indices
     int32_t corr[4][64];         // D[j][yx]
+};
+
+// Verified integer form of ConvertYCCtoRGBFastFloat (built and checked on the device by
+// k_build_color_tables): R = clamp(y + tr[cr]), B = clamp(y + tb[cb]), G = clamp(y + tg[cb][cr]);
+// tg == 0x7FFF marks the (cb,cr) pairs for which the additive form is not exact for every y.
+struct ColorTabs {
+    int16_t tr[256], tb[256];
+    int32_t rb_ok, n_unsafe;
+    int16_t tg[65536];
 };
