@@ -147,6 +147,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-histo", action="store_true", help="debug: skip m_anDhtHisto (invalidates the headline)")
+    ap.add_argument("--no-mcu-map", action="store_true", help="debug: skip m_pMcuFileMap (invalidates the headline)")
     ap.add_argument("--huff-kernel", type=int, default=0)
     ap.add_argument("--idct-kernel", type=int, default=0)
     args = ap.parse_args()
@@ -175,7 +177,7 @@ def main():
     jpegs, (w, h, ss, q, ri) = make_batch(args.config, rank, nimg=args.batch)
     nimg = len(jpegs)
     t_gen = time.time() - t0
-    bd = BatchDecoder(device=local, huff_kernel=args.huff_kernel, idct_kernel=args.idct_kernel, want_histo=True, want_mcu_map=True)
+    bd = BatchDecoder(device=local, huff_kernel=args.huff_kernel, idct_kernel=args.idct_kernel, want_histo=not args.no_histo, want_mcu_map=not args.no_mcu_map)
     tarr, darr, bits = BatchDecoder.prepare(jpegs)
     # ---- shared Huffman/quant tables: broadcast rank 0's table blob over NCCL (NVLink) ---------------
     if world > 1:

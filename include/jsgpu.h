@@ -94,7 +94,8 @@ typedef struct {
     int32_t decode_ac;      /* m_bDecodeScanAc (ImgDecode.cpp:1723-1725,1818); default 1          */
     int32_t huff_kernel;    /* 0 = auto, 1 = one warp per restart interval, 2 = one lane per
                                restart interval                                                   */
-    int32_t idct_kernel;    /* 0 = auto, 1 = simple reference kernels, 2 = fused tiled kernel    */
+    int32_t idct_kernel;    /* 0 = auto, 1 = simple reference kernels, 2 = fused tile kernel with
+                               TMA-staged coefficients, 3 = fused tile kernel with plain loads    */
     int32_t want_histo;     /* accumulate m_anDhtHisto (ImgDecode.cpp:1190-1191); default 1      */
     int32_t want_mcu_map;   /* build m_pMcuFileMap (ImgDecode.cpp:3229); default 1               */
     int32_t device_markers; /* 1 = find RSTn/end-of-scan on the GPU (default), 0 = host walk      */

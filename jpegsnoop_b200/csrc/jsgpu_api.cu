@@ -39,7 +39,7 @@ struct jsgpu_ctx {
     // device state
     DevBuf d_ctab; bool have_ctab = false;
     DevBuf d_li, d_lf, d_sym, d_tables, d_img, d_items, d_litems, d_tiles, d_ubits, d_seg64;
-    bool sym_ok = false;
+    bool sym_ok = false, baked_ok = false; int tab_mode = 0;
     DevBuf d_bits, d_seg, d_coef, d_mcubits, d_pix, d_dib, d_blk, d_mcumap, d_histo, d_stats, d_misc;
     uint32_t nsets = 0;
     // batch state
@@ -49,6 +49,7 @@ struct jsgpu_ctx {
     DevBatch batch;
     uint64_t bits_len = 0, pix_total = 0, dib_total = 0, blk_total = 0, mcu_total = 0, coef_rows = 0;
     uint64_t max_scan_len = 0, ubits_total = 0;
+    alignas(64) unsigned char tmap[128]; bool tmap_ok = false;
     uint32_t n_nonstd = 0, n_std = 0;
     int launches = 0;
     float ms[5] = {0, 0, 0, 0, 0};
@@ -168,11 +169,18 @@ int jsgpu_set_idct_tables(jsgpu_ctx* ctx, const int32_t* li, const float* lf)
     cudaSetDevice(ctx->device);
     IdctSym* sym = new IdctSym;
     ctx->sym_ok = build_idct_sym(li, *sym);
+    ctx->baked_ok = js_idct_baked_matches(li) != 0;
+    {   // table source of the LDG tile kernel: env override for experiments, else immediates when the baked copy matches
+        const char* e = getenv("JSGPU_IDCT_TABLE");
+        ctx->tab_mode = e ? atoi(e) : (ctx->baked_ok ? 2 : 0);
+        if (ctx->tab_mode == 2 && !ctx->baked_ok) ctx->tab_mode = 0;
+    }
     cudaError_t e1 = ctx->d_li.reserve(64 * 64 * 4), e2 = ctx->d_lf.reserve(64 * 64 * 4), e3 = ctx->d_sym.reserve(sizeof(IdctSym));
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { delete sym; return fail(ctx, JSGPU_ENOMEM, "idct table allocation failed"); }
     cudaMemcpyAsync(ctx->d_li.p, li, 64 * 64 * 4, cudaMemcpyHostToDevice, ctx->stream);
     cudaMemcpyAsync(ctx->d_lf.p, lf, 64 * 64 * 4, cudaMemcpyHostToDevice, ctx->stream);
     cudaMemcpyAsync(ctx->d_sym.p, sym, sizeof(IdctSym), cudaMemcpyHostToDevice, ctx->stream);
+    js_upload_idct_constants(sym, ctx->stream);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     delete sym;
     if (e != cudaSuccess) return fail(ctx, JSGPU_ECUDA, "idct table upload failed: %s", cudaGetErrorString(e));
@@ -324,6 +332,7 @@ static bool plan_image(const jsgpu_image_desc& d, uint32_t nsets, DevImage& im)
     im.std_layout = stdl ? 1 : 0;
     im.tile_mcus = 32 / hmax;
     im.tiles_per_row = (im.mcu_xmax + im.tile_mcus - 1) / im.tile_mcus;
+    im.tile_groups = (im.bpm * im.tile_mcus + 31) / 32;
     im.valid = 1;
     return true;
 }
@@ -340,7 +349,7 @@ int jsgpu_batch_begin(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, 
     uint64_t pix = 0, dib = 0, blk = 0, mcu = 0, rows = 0, max_scan = 0, ub = 0;
     uint32_t seg = 0, n_std = 0, n_nonstd = 0, plane_bytes = 0;
     std::vector<uint2> items, litems;
-    std::vector<uint4> tiles;
+    std::vector<uint4> tiles, tcls[3];
     for (uint32_t i = 0; i < n; i++) {
         DevImage& im = ctx->himg[i];
         jsgpu_image_layout& lo = ctx->layout[i];
@@ -364,12 +373,12 @@ int jsgpu_batch_begin(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, 
         im.ubits_off = ub; ub += align_up(im.scan_len + 32ull * im.nseg + 64, 256);
         if (im.std_layout) {
             n_std++;
-            im.tile_first = (uint32_t)tiles.size();
+            const uint32_t ehc = (im.ns == 3) ? im.eh[1] : 1, cls = (ehc == 1) ? 0 : (ehc == 2) ? 1 : 2;
             for (uint32_t r = 0; r < im.mcu_ymax; r++) for (uint32_t t = 0; t < im.tiles_per_row; t++) {
                 uint32_t c0 = t * im.tile_mcus;
-                tiles.push_back(make_uint4(i, r, c0, std::min(im.tile_mcus, im.mcu_xmax - c0)));
+                tcls[cls].push_back(make_uint4(i, r, c0, std::min(im.tile_mcus, im.mcu_xmax - c0)));
             }
-            im.ntiles = (uint32_t)tiles.size() - im.tile_first;
+            im.ntiles = im.mcu_ymax * im.tiles_per_row;
             uint32_t bpt = 0; for (uint32_t c = 0; c < im.ns; c++) bpt += im.H[c] * im.V[c] * im.tile_mcus;
             plane_bytes = std::max(plane_bytes, bpt * 128);
         } else n_nonstd++;
@@ -377,6 +386,8 @@ int jsgpu_batch_begin(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, 
         lo.blk_xmax = im.blk_xmax; lo.blk_ymax = im.blk_ymax; lo.img_x = im.wp; lo.img_y = im.hp;
         lo.num_segments = im.nseg; lo.pix_off = im.pix_off; lo.dib_off = im.dib_off; lo.blk_off = im.blk_off; lo.mcu_off = im.mcu_off;
     }
+    uint32_t tcls_first[3], tcls_count[3];
+    for (int k = 0; k < 3; k++) { tcls_first[k] = (uint32_t)tiles.size(); tcls_count[k] = (uint32_t)tcls[k].size(); tiles.insert(tiles.end(), tcls[k].begin(), tcls[k].end()); }
     ctx->bits_len = bitstream_bytes; ctx->pix_total = pix; ctx->dib_total = dib; ctx->blk_total = blk; ctx->mcu_total = mcu;
     ctx->coef_rows = rows; ctx->max_scan_len = max_scan; ctx->ubits_total = ub; ctx->n_std = n_std; ctx->n_nonstd = n_nonstd;
     // allocate
@@ -387,8 +398,8 @@ int jsgpu_batch_begin(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, 
     CK(ctx->d_litems.reserve(sizeof(uint2) * std::max<size_t>(litems.size(), 1)));
     CK(ctx->d_tiles.reserve(sizeof(uint4) * std::max<size_t>(tiles.size(), 1)));
     CK(ctx->d_seg64.reserve(8 * (size_t)seg + 16));
-    CK(ctx->d_seg.reserve(sizeof(uint32_t) * (5 * (size_t)seg + 2 * (size_t)n + 16)));
-    CK(ctx->d_coef.reserve(rows * 128 + 128));
+    CK(ctx->d_seg.reserve(sizeof(uint32_t) * ((6 + JS_STUFF_LIST) * (size_t)seg + 2 * (size_t)n + 16)));
+    CK(ctx->d_coef.reserve(rows * 128 + 4096));      // + slack: a TMA box may start at the last rows and spans 8
     CK(ctx->d_mcubits.reserve(mcu * 4 + 16));
     CK(ctx->d_pix.reserve(pix * 2 * 3 + 64));
     CK(ctx->d_dib.reserve(dib + 64));
@@ -410,9 +421,12 @@ int jsgpu_batch_begin(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, 
     b.seg_start = sp; b.seg_end = sp + seg; b.seg_endbits = sp + 2 * (size_t)seg; b.seg_status = sp + 3 * (size_t)seg;
     b.seg_ulen = sp + 4 * (size_t)seg;
     b.scan_end = sp + 5 * (size_t)seg; b.nseg_found = b.scan_end + n; b.nseg_total = seg;
+    b.seg_nstuff = b.nseg_found + n; b.seg_stuff = b.seg_nstuff + seg;
     b.seg_uoff = (unsigned long long*)ctx->d_seg64.p; b.ubits = (uint8_t*)ctx->d_ubits.p;
     b.litems = (const uint2*)ctx->d_litems.p; b.nlitems = (uint32_t)litems.size();
     b.tiles = (const uint4*)ctx->d_tiles.p; b.ntiles = (uint32_t)tiles.size(); b.tile_plane_bytes = plane_bytes;
+    for (int k = 0; k < 3; k++) { b.tcls_first[k] = tcls_first[k]; b.tcls_count[k] = tcls_count[k]; }
+    ctx->tmap_ok = (js_make_coef_tensor_map(ctx->tmap, ctx->d_coef.p, rows + 8) == 0);
     b.items = (const uint2*)ctx->d_items.p; b.nitems = (uint32_t)items.size();
     b.coef = (int16_t*)ctx->d_coef.p; b.mcu_bitpos = (uint32_t*)ctx->d_mcubits.p;
     b.pix_y = (int16_t*)ctx->d_pix.p; b.pix_cb = b.pix_y + pix; b.pix_cr = b.pix_cb + pix;
@@ -506,6 +520,7 @@ int jsgpu_batch_decode(jsgpu_ctx* ctx)
     cudaSetDevice(ctx->device);
     DevBatch& b = ctx->batch;
     b.decode_ac = ctx->opt.decode_ac; b.want_histo = ctx->opt.want_histo; b.idct_mode = ctx->opt.idct_mode;
+    b.any_p12 = 0; for (const DevImage& im : ctx->himg) if (im.valid && im.precision > 8) b.any_p12 = 1;
     cudaStream_t s = ctx->stream;
     int launches = 0;
     CK(cudaEventRecord(ctx->ev[0], s));
@@ -514,6 +529,7 @@ int jsgpu_batch_decode(jsgpu_ctx* ctx)
     CK(cudaMemsetAsync(b.stats, 0, (size_t)b.nimg * 16 * 4, s));
     CK(cudaMemsetAsync(b.bright_key, 0, (size_t)b.nimg * (8 + 8 + 4), s));
     CK(cudaMemsetAsync(b.mcu_map, 0, ctx->mcu_total * 4, s));
+    CK(cudaMemsetAsync(b.blk_y, 0, ctx->blk_total * 2 * 3, s));
     if (ctx->opt.device_markers) launches += js_launch_marker_scan(b, ctx->max_scan_len, s);
     else {
         std::vector<uint8_t> hb(ctx->bits_len);
@@ -530,11 +546,15 @@ int jsgpu_batch_decode(jsgpu_ctx* ctx)
         else launches += js_launch_huffman_warp(b, ctx->sm_count, s);
     }
     CK(cudaEventRecord(ctx->ev[2], s));
+    bool fused_all = false;
     {
         // fused tile kernel: integer IDCT, standard sampling layouts, decomposable table; everything
         // else (float IDCT, exotic sampling, a libm whose table does not decompose) takes the simple kernels
         const bool fused = (ctx->opt.idct_kernel != 1) && ctx->opt.idct_mode == 0 && ctx->sym_ok && b.ntiles > 0;
-        if (fused) launches += js_launch_idct_fused(b, (const IdctSym*)ctx->d_sym.p, (const ColorTabs*)ctx->d_ctab.p, ctx->sm_count, s);
+        fused_all = fused && ctx->n_nonstd == 0;
+        // idct_kernel: 2 = TMA-staged tile kernel, 0/3 = tile kernel with per-lane vector loads (measured faster, profiles/r1_idct.md)
+        if (fused && ctx->opt.idct_kernel == 2 && ctx->tmap_ok) launches += js_launch_idct_tma(b, (const IdctSym*)ctx->d_sym.p, (const ColorTabs*)ctx->d_ctab.p, ctx->tmap, ctx->sm_count, s);
+        else if (fused) launches += js_launch_idct_fused(b, (const IdctSym*)ctx->d_sym.p, (const ColorTabs*)ctx->d_ctab.p, ctx->sm_count, ctx->tab_mode, s);
         if (!fused || ctx->n_nonstd > 0) {
             DevBatch bs = b; bs.simple_only_nonstd = fused ? 1 : 0;
             launches += js_launch_idct_simple(bs, (const int32_t*)ctx->d_li.p, (const float*)ctx->d_lf.p, 0, 0, s);
@@ -544,6 +564,8 @@ int jsgpu_batch_decode(jsgpu_ctx* ctx)
     {
         DevBatch bf = b;
         if (!ctx->opt.want_mcu_map) bf.mcu_map = nullptr;
+        bf.blkdc_by_gather = 0; bf.stuff_overflow_possible = 1;     // block-DC maps are written by the Huffman kernels
+        (void)fused_all;
         launches += js_launch_finalize(bf, s);
     }
     CK(cudaEventRecord(ctx->ev[4], s));

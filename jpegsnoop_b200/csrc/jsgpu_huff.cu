@@ -38,37 +38,54 @@ __global__ void __launch_bounds__(128) k_unstuff(DevBatch b)
     uint8_t* dst = b.ubits + dst0;
     const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(seg) & 3);
     const uint8_t* abase = seg - mis;
-    uint32_t wr = 0, prev_ff = 0;
+    uint32_t wr = 0, prev_ff = 0, nstuff = 0;
+    const uint32_t lt = (1u << lane) - 1;
     for (uint32_t rpos = 0; rpos < len + mis; rpos += 128) {
-        long long rel0 = (long long)rpos + 4 * lane - mis;
+        const int rel0 = (int)(rpos + 4 * lane) - (int)mis;         // segment offset of this lane's byte 0
         uint32_t word = 0;
-        if (rel0 + 3 >= 0 && rel0 < (long long)len) word = __ldg(reinterpret_cast<const uint32_t*>(abase + rpos + 4 * lane));
+        if (rel0 + 3 >= 0 && rel0 < (int)len) word = __ldg(reinterpret_cast<const uint32_t*>(abase + rpos + 4 * lane));
+        // byte flags live in bit 7 of each byte.  valid bytes: 0 <= rel0+j < len
+        const int lo = max(0, -rel0), hi = min(4, (int)len - rel0);
+        uint32_t vmask = 0;
+        if (hi > lo) vmask = (0x80808080u >> (32 - 8 * hi)) & ~((lo > 0) ? (0x80808080u >> (32 - 8 * lo)) : 0u);
         uint32_t up = __shfl_up_sync(FULL, word, 1);
-        uint32_t prevb = (lane == 0) ? (prev_ff ? 0xFFu : 0u) : (up >> 24);
-        uint32_t keep = 0, cnt = 0;
-        #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            uint32_t bj = (word >> (8 * j)) & 0xFF;
-            long long rel = rel0 + j;
-            bool valid = rel >= 0 && rel < (long long)len;
-            bool drop = (bj == 0) && (prevb == 0xFF) && (rel > 0);
-            if (valid && !drop) { keep |= 1u << j; cnt++; }
-            prevb = valid ? bj : 0;
-        }
-        uint32_t lt = (1u << lane) - 1;
-        uint32_t b0 = __ballot_sync(FULL, cnt & 1), b1 = __ballot_sync(FULL, cnt & 2), b2 = __ballot_sync(FULL, cnt & 4);
-        uint32_t pre = __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
-        uint32_t tot = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+        if (lane == 0) up = prev_ff ? 0xFF000000u : 0u;
+        const uint32_t pw = __byte_perm(up, word, 0x6543);           // byte j = the byte before word's byte j
+        const uint32_t npw = ~pw;
+        const uint32_t z = ~(((word & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | word | 0x7F7F7F7Fu);   // byte == 0x00
+        const uint32_t f = ~(((npw & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | npw | 0x7F7F7F7Fu);     // previous byte == 0xFF
+        uint32_t drop = z & f & vmask;
+        if (rel0 <= 0 && rel0 > -4) drop &= ~(0x80u << (8 * (-rel0)));                     // the first byte has no predecessor in the interval
+        const uint32_t keep = vmask & ~drop;
+        const uint32_t cnt = __popc(keep);
+        const uint32_t b0 = __ballot_sync(FULL, cnt & 1), b1 = __ballot_sync(FULL, cnt & 2), b2 = __ballot_sync(FULL, cnt & 4);
+        const uint32_t pre = __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
+        const uint32_t tot = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
         uint32_t o = wr + pre;
-        #pragma unroll
-        for (int j = 0; j < 4; j++) if (keep >> j & 1) { dst[o] = (uint8_t)(word >> (8 * j)); o++; }
+        if (keep == 0x80808080u && (o & 3) == 0) *reinterpret_cast<uint32_t*>(dst + o) = word;   // common case: one aligned word store
+        else {
+            #pragma unroll
+            for (int j = 0; j < 4; j++) if (keep >> (8 * j + 7) & 1) { dst[o] = (uint8_t)(word >> (8 * j)); o++; }
+        }
+        // record where bytes were dropped (for the MCU file map): unstuffed index of the preceding FF
+        if (__ballot_sync(FULL, drop != 0)) {
+            const uint32_t dc = __popc(drop);                               // 0..2 per lane
+            const uint32_t d0 = __ballot_sync(FULL, dc & 1), d1 = __ballot_sync(FULL, dc & 2);
+            uint32_t dr = nstuff + __popc(d0 & lt) + 2 * __popc(d1 & lt);
+            uint32_t oo = wr + pre;
+            #pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (drop >> (8 * j + 7) & 1) { if (dr < JS_STUFF_LIST) b.seg_stuff[(size_t)gw * JS_STUFF_LIST + dr] = oo - 1; dr++; }
+                else if (keep >> (8 * j + 7) & 1) oo++;
+            }
+            nstuff += __popc(d0) + 2 * __popc(d1);
+        }
         wr += tot;
-        uint32_t last = __shfl_sync(FULL, word, 31);
-        prev_ff = ((last >> 24) == 0xFF) ? 1u : 0u;
+        prev_ff = ((__shfl_sync(FULL, word, 31) >> 24) == 0xFF) ? 1u : 0u;
     }
     // pad with 1-bits (the JPEG pad value; no valid code is all ones) so readers can over-fetch
     if (lane < 16) dst[wr + lane] = 0xFF;      // 16 bytes: the most a reader can over-fetch, and what the 32-byte slack allows
-    if (lane == 0) { b.seg_ulen[gw] = wr; b.seg_uoff[gw] = dst0; }
+    if (lane == 0) { b.seg_ulen[gw] = wr; b.seg_uoff[gw] = dst0; b.seg_nstuff[gw] = nstuff; }
 }
 
 int js_launch_unstuff(const DevBatch& b, cudaStream_t s)
@@ -94,7 +111,7 @@ __device__ __forceinline__ void stage_tables(HuffTabs& t, const DevImage& im, co
         uint4* d0 = reinterpret_cast<uint4*>(t.lut[c * 2]);
         uint4* d1 = reinterpret_cast<uint4*>(t.lut[c * 2 + 1]);
         for (uint32_t i = threadIdx.x; i < JS_LUT_SIZE * 2 / 16; i += blockDim.x) { d0[i] = __ldg(s0 + i); d1[i] = __ldg(s1 + i); }
-        for (uint32_t i = threadIdx.x; i < 80; i += blockDim.x) t.qz[c][i] = (i < 64) ? ts->qz[im.dqt[c]][i] : (127u << 16);
+        for (uint32_t i = threadIdx.x; i < 80; i += blockDim.x) t.qz[c][i] = (i < 64) ? ts->qz[im.dqt[c]][i] : ((64u + (i & 7)) << 16);   // k >= 64: dummy slot past the row
     }
 }
 
@@ -254,6 +271,8 @@ __global__ void __launch_bounds__(JS_HUFF_WARPS * 32) k_huff_warp(DevBatch b)
                     if (pos > 64) status |= 4;
                     if (lane == 0) acc = __byte_perm(acc, (uint32_t)dc, 0x3254);
                     const uint32_t v = bi / nh, h = bi - v * nh;
+                    if (lane == 0 && (h < gim.eh[c] || mx == mcu_xmax - 1) && (v < gim.ev[c] || my == gim.mcu_ymax - 1))
+                        (((c == 0) ? b.blk_y : (c == 1) ? b.blk_cb : b.blk_cr) + gim.blk_off)[(my * gim.ev[c] + v) * gim.blk_xmax + (mx * gim.eh[c] + h)] = (int16_t)dc;
                     coef32[(row0 + (size_t)v * cw + h) * 32 + lane] = acc;
                     if (status & 7) break;
                 }
@@ -289,31 +308,59 @@ int js_launch_huffman_warp(const DevBatch& b, int sm_count, cudaStream_t s)
 // lane per restart interval
 // ------------------------------------------------------------------------------------------------
 #define LN_WARPS   4
-#define ROW_PITCH  144                      // bytes per lane row (128 + 16): 16-byte aligned, bank-skewed
+#define ROW_PITCH  144                      // bytes per lane row: 64 coefficients + 8 dummy slots; 16-byte aligned
 struct LaneShared {
     HuffTabs t;
     uint32_t histo[6][17];
     __align__(16) uint8_t rows[LN_WARPS][32 * ROW_PITCH];
+    // code-length histogram staging: one byte counter per (class, length 1..16, lane); a lane increments only
+    // its own column, so no atomics; flushed per block (a block has <= 64 symbols, so a byte cannot overflow)
+    __align__(16) uint8_t hb[LN_WARPS][2 * 16 * 32];
 };
 
-__global__ void __launch_bounds__(LN_WARPS * 32) k_huff_lane(DevBatch b)
+// Bit window as two 32-bit registers (hi = next 32 bits, lo = the 32 after), funnel-shift consume.
+struct Win {
+    uint32_t hi, lo; int nb; uint32_t nx; uint32_t idx; const uint32_t* base;
+    __device__ __forceinline__ void init(const uint8_t* b) {
+        base = reinterpret_cast<const uint32_t*>(b);
+        hi = __byte_perm(__ldg(base), 0, 0x0123); lo = __byte_perm(__ldg(base + 1), 0, 0x0123);
+        nx = __ldg(base + 2); idx = 3; nb = 64;
+    }
+    __device__ __forceinline__ void refill() {            // precondition: 6 <= nb <= 32
+        const uint32_t x = __byte_perm(nx, 0, 0x0123);
+        nx = __ldg(base + idx); idx++;
+        hi |= __funnelshift_rc(x, 0, nb);                  // x >> nb, 0 when nb == 32
+        lo = x << (32 - nb);
+        nb += 32;
+    }
+    __device__ __forceinline__ void consume(uint32_t n) { hi = __funnelshift_l(lo, hi, n); lo <<= n; nb -= (int)n; }
+    __device__ __forceinline__ uint32_t consumed() const { return 32u * (idx - 1) - (uint32_t)nb; }
+};
+
+// GENERIC = false: the common case compiled without run-time feature checks (AC decode on, 8-bit
+// precision, no code-length histogram).  GENERIC = true: every option honoured at run time.
+template <bool GENERIC>
+__global__ void __launch_bounds__(LN_WARPS * 32, 6) k_huff_lane(DevBatch b)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     LaneShared& sh = *reinterpret_cast<LaneShared*>(smem_raw);
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint8_t* const myrows = sh.rows[wid];
-    uint16_t* const myrow = reinterpret_cast<uint16_t*>(myrows + lane * ROW_PITCH);
-    // rows start zeroed and are re-zeroed by the write-out
+    uint8_t* const myrow = myrows + lane * ROW_PITCH;
     for (uint32_t i = lane; i < 32 * ROW_PITCH / 4; i += 32) reinterpret_cast<uint32_t*>(myrows)[i] = 0;
+    uint8_t* const myhb = sh.hb[wid];
+    for (uint32_t i = lane; i < 2 * 16 * 32 / 4; i += 32) reinterpret_cast<uint32_t*>(myhb)[i] = 0;
+    const bool want_ac = GENERIC ? (b.decode_ac != 0) : true;
+    const bool want_histo = GENERIC ? (b.want_histo != 0) : false;
     uint32_t cur_img = 0xffffffffu;
     for (uint32_t it = blockIdx.x; it < b.nlitems; it += gridDim.x) {
-        const uint2 item = b.litems[it];                      // (image, first interval); LN_WARPS*32 intervals per item
+        const uint2 item = b.litems[it];                      // (image, first interval); JS_LANE_SEGS intervals per item
         const DevImage& gim = b.img[item.x];
         const DevTableSet* ts = b.tables + gim.table_set;
         if (item.x != cur_img) {
             __syncthreads();
-            if (cur_img != 0xffffffffu && b.want_histo) { flush_histo(b, cur_img, sh.histo); __syncthreads(); }
-            for (uint32_t i = threadIdx.x; i < 6 * 17; i += blockDim.x) (&sh.histo[0][0])[i] = 0;
+            if (GENERIC && cur_img != 0xffffffffu && want_histo) { flush_histo(b, cur_img, sh.histo); __syncthreads(); }
+            if (GENERIC) for (uint32_t i = threadIdx.x; i < 6 * 17; i += blockDim.x) (&sh.histo[0][0])[i] = 0;
             stage_tables(sh.t, gim, ts);
             cur_img = item.x;
             __syncthreads();
@@ -322,17 +369,15 @@ __global__ void __launch_bounds__(LN_WARPS * 32) k_huff_lane(DevBatch b)
         if (kbase >= gim.nseg) continue;                       // warp-uniform
         const uint32_t k = kbase + lane;
         const bool live = k < gim.nseg;
-        const uint32_t ns = gim.ns, precision = gim.precision, ri = gim.ri, nmcu = gim.nmcu, mcu_xmax = gim.mcu_xmax;
+        const uint32_t ns = gim.ns, ri = gim.ri, nmcu = gim.nmcu, mcu_xmax = gim.mcu_xmax;
+        const uint32_t pshift = (GENERIC && gim.precision > 8) ? gim.precision - 8 : 0;
         const uint32_t sidx = gim.seg_first + (live ? k : kbase);
-        const uint32_t ulen = b.seg_ulen[sidx];
-        Bits s; s.init(b.ubits + b.seg_uoff[sidx]);
+        Win s; s.init(b.ubits + b.seg_uoff[sidx]);
         const uint32_t m0 = k * ri;
         const uint32_t nm = live ? (min(m0 + ri, nmcu) - m0) : 0;   // MCUs this lane decodes
         uint32_t mx = m0 % mcu_xmax, my = m0 / mcu_xmax;
         int dc0 = 0, dc1 = 0, dc2 = 0;
         uint32_t status = 0;
-        const bool want_ac = b.decode_ac != 0;
-        const bool want_histo = b.want_histo != 0;
         const uint32_t nm_max = min(ri, nmcu - kbase * ri);         // longest interval in this warp (the first lane's)
         #pragma unroll 1
         for (uint32_t mi = 0; mi < nm_max; mi++) {
@@ -344,7 +389,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32) k_huff_lane(DevBatch b)
                 const uint16_t* lut_ac = sh.t.lut[c * 2 + 1];
                 const uint32_t* qz = sh.t.qz[c];
                 const uint32_t nh = gim.H[c], nv = gim.V[c], cw = gim.cw[c];
-                const uint32_t slot_dc = gim.slot_dc[c], slot_ac = gim.slot_ac[c];
+                const uint32_t ehc = gim.eh[c], evc = gim.ev[c], blk_xmax = gim.blk_xmax, mcu_ymax = gim.mcu_ymax;
+                int16_t* const blkmap = ((c == 0) ? b.blk_y : (c == 1) ? b.blk_cb : b.blk_cr) + gim.blk_off;
                 int dc = (c == 0) ? dc0 : (c == 1) ? dc1 : dc2;
                 #pragma unroll 1
                 for (uint32_t bi = 0; bi < nh * nv; bi++) {
@@ -353,20 +399,24 @@ __global__ void __launch_bounds__(LN_WARPS * 32) k_huff_lane(DevBatch b)
                     if (active) {
                         // ---- DC symbol ----
                         if (s.nb <= 32) s.refill();
-                        uint32_t e = lut_dc[s.top32() >> (32 - JS_LUT_BITS)];
-                        if (e == 0 || (e & 0x8000)) e = huff_level2(ts, slot_dc, e, s.top32());
+                        uint32_t e = lut_dc[s.hi >> (32 - JS_LUT_BITS)];
+                        if (e == 0 || (e & 0x8000)) e = huff_level2(ts, gim.slot_dc[c], e, s.hi);
                         if (e == 0) { status |= 1; active = false; }
                         else {
-                            uint32_t len = e >> 8;
-                            s.w <<= len; s.nb -= (int)len;
-                            if (want_histo) atomicAdd(&sh.histo[c * 2][len], 1u);
-                            uint32_t run = (e >> 4) & 15, size = e & 15;
-                            int val = take_value(s, size, precision);
-                            uint32_t q = qz[run];
-                            int cf = (int)(short)(val * (int)(q & 0xFFFF));
-                            uint32_t nat = q >> 16;
+                            const uint32_t len = e >> 8, run = (e >> 4) & 15, size = e & 15;
+                            if (GENERIC && want_histo) myhb[(16 + len - 1) * 32 + lane]++;
+                            s.consume(len);
+                            if (s.nb <= 32) s.refill();          // a 16-bit code + 16 value bits can exceed what is left
+                            const uint32_t t = s.hi;
+                            const uint32_t v = (size == 0) ? 0u : (t >> (32 - size));
+                            int val = (int)v - (((int)~t >> 31) & (int)((1u << size) - 1));
+                            s.consume(size);
+                            if (GENERIC && pshift) val /= (1 << pshift);
+                            const uint32_t q = qz[run];
+                            const int cf = (int)(short)(val * (int)(q & 0xFFFF));
+                            const uint32_t nat = q >> 16;
                             int dcdiff = 0;
-                            if (nat == 0) dcdiff = cf; else if (nat < 64) myrow[nat] = (uint16_t)cf;
+                            if (nat == 0) dcdiff = cf; else *reinterpret_cast<uint16_t*>(myrow + nat * 2) = (uint16_t)cf;
                             dc = (int)(short)(dc + dcdiff);
                             pos = 1 + run;
                         }
@@ -375,30 +425,45 @@ __global__ void __launch_bounds__(LN_WARPS * 32) k_huff_lane(DevBatch b)
                     while (__any_sync(FULL, pos < 64)) {
                         if (pos < 64) {
                             if (s.nb <= 32) s.refill();
-                            uint32_t e = lut_ac[s.top32() >> (32 - JS_LUT_BITS)];
-                            if (e == 0 || (e & 0x8000)) e = huff_level2(ts, slot_ac, e, s.top32());
-                            if (e == 0) { status |= 1; pos = 64; }
-                            else {
-                                uint32_t len = e >> 8;
-                                s.w <<= len; s.nb -= (int)len;
-                                if (want_histo) atomicAdd(&sh.histo[c * 2 + 1][len], 1u);
-                                if ((e & 0xFF) == 0) pos = 64 + 64;          // EOB (distinguish from overflow)
-                                else {
-                                    uint32_t run = (e >> 4) & 15, size = e & 15;
-                                    int val = take_value(s, size, precision);
-                                    uint32_t kk = pos + run;
-                                    uint32_t q = qz[kk];
-                                    uint32_t nat = q >> 16;
-                                    if (want_ac && nat < 64) myrow[nat] = (uint16_t)(val * (int)(q & 0xFFFF));
-                                    pos = kk + 1;
-                                    if (pos > 64) { status |= 4; }
-                                }
-                            }
+                            uint32_t e = lut_ac[s.hi >> (32 - JS_LUT_BITS)];
+                            if (e == 0 || (e & 0x8000)) e = huff_level2(ts, gim.slot_ac[c], e, s.hi);
+                            const uint32_t len = e >> 8, size = e & 15, run = (e >> 4) & 15;
+                            if (GENERIC && want_histo && e) myhb[(len - 1) * 32 + lane]++;
+                            // value bits follow the code: take them from the window before consuming both at once
+                            const uint32_t t = __funnelshift_l(s.lo, s.hi, len);
+                            uint32_t v; asm("shr.u32 %0, %1, %2;" : "=r"(v) : "r"(t), "r"(32u - size));   // 0 when size == 0 (shift clamps at 32)
+                            uint32_t msk; asm("shr.u32 %0, %1, %2;" : "=r"(msk) : "r"(0xffffffffu), "r"(32u - size));
+                            int val = (int)v - (((int)~t >> 31) & (int)msk);
+                            if (GENERIC && pshift) val /= (1 << pshift);
+                            s.consume(len + size);
+                            const uint32_t kk = pos + run;
+                            const uint32_t q = qz[kk];                                   // kk <= 78; entries >= 64 point at dummy slots
+                            if (want_ac) *reinterpret_cast<uint16_t*>(myrow + (q >> 16) * 2) = (uint16_t)(val * (int)(q & 0xFFFF));
+                            pos = ((e & 0xFF) == 0) ? 128u : kk + 1;                     // EOB ends the block (its dummy store hit slot >= 64 or rewrote 0*q)
+                            if (e == 0) { status |= 1; pos = 128; }
                         }
                     }
-                    if (active) myrow[0] = (uint16_t)dc;
-                    // ---- cooperative write-out: 4 rows per step, 16 bytes per lane, then re-zero ----
+                    if (pos > 64 && pos < 128) status |= 4;
                     const uint32_t v = bi / nh, h = bi - v * nh;
+                    if (active) {
+                        *reinterpret_cast<uint16_t*>(myrow) = (uint16_t)dc;
+                        // block-DC map (ImgDecode.cpp:3524-3608 in gather form): cell (mx*eh+h, my*ev+v) keeps this
+                        // block's DC iff no later MCU overwrites it: (h < eh or last MCU column) and (v < ev or last MCU row)
+                        if ((h < ehc || mx == mcu_xmax - 1) && (v < evc || my == mcu_ymax - 1))
+                            blkmap[(my * evc + v) * blk_xmax + (mx * ehc + h)] = (int16_t)dc;
+                    }
+                    if (GENERIC && want_histo) {
+                        // lane l < 16 owns AC length l+1, lane l >= 16 owns DC length l-15: sum that bin over the 32 lanes
+                        __syncwarp();
+                        uint4* hp = reinterpret_cast<uint4*>(myhb + lane * 32);
+                        const uint4 h0 = hp[0], h1 = hp[1];
+                        uint32_t tot = 0;
+                        tot = __dp4a(h0.x, 0x01010101u, tot); tot = __dp4a(h0.y, 0x01010101u, tot); tot = __dp4a(h0.z, 0x01010101u, tot); tot = __dp4a(h0.w, 0x01010101u, tot);
+                        tot = __dp4a(h1.x, 0x01010101u, tot); tot = __dp4a(h1.y, 0x01010101u, tot); tot = __dp4a(h1.z, 0x01010101u, tot); tot = __dp4a(h1.w, 0x01010101u, tot);
+                        if (tot) { atomicAdd(&sh.histo[c * 2 + (lane < 16 ? 1 : 0)][(lane & 15) + 1], tot); hp[0] = make_uint4(0, 0, 0, 0); hp[1] = make_uint4(0, 0, 0, 0); }
+                        __syncwarp();
+                    }
+                    // ---- cooperative write-out: 4 rows per step, 16 bytes per lane, then re-zero ----
                     const unsigned long long myaddr = active ? (unsigned long long)((gim.coef_row[c] + (size_t)(my * nv + v) * cw + (mx * nh + h)) * 128) : ~0ull;
                     __syncwarp();
                     #pragma unroll
@@ -407,10 +472,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32) k_huff_lane(DevBatch b)
                         unsigned long long a = __shfl_sync(FULL, myaddr, src);
                         uint4* sp = reinterpret_cast<uint4*>(myrows + src * ROW_PITCH + (lane & 7) * 16);
                         uint4 val = *sp;
-                        if (a != ~0ull) {
-                            *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(b.coef) + a + (lane & 7) * 16) = val;
-                            *sp = make_uint4(0, 0, 0, 0);
-                        }
+                        *sp = make_uint4(0, 0, 0, 0);
+                        if (a != ~0ull) *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(b.coef) + a + (lane & 7) * 16) = val;
                     }
                     __syncwarp();
                 }
@@ -419,6 +482,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) k_huff_lane(DevBatch b)
             if (++mx == mcu_xmax) { mx = 0; my++; }
         }
         if (live) {
+            const uint32_t ulen = b.seg_ulen[sidx];
             uint32_t consumed = s.consumed(), avail = ulen * 8;
             if (consumed > avail) status |= 2;
             else if (!(status & 5) && avail - consumed >= 8) status |= 16;
@@ -428,16 +492,22 @@ __global__ void __launch_bounds__(LN_WARPS * 32) k_huff_lane(DevBatch b)
         }
     }
     __syncthreads();
-    if (cur_img != 0xffffffffu && b.want_histo) flush_histo(b, cur_img, sh.histo);
+    if (GENERIC && cur_img != 0xffffffffu && want_histo) flush_histo(b, cur_img, sh.histo);
 }
 
 int js_launch_huffman_lane(const DevBatch& b, int sm_count, cudaStream_t s)
 {
     if (b.nlitems == 0) return 0;
     static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(k_huff_lane, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LaneShared)); attr_set = true; }
-    uint32_t grid = (uint32_t)sm_count * 4;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_huff_lane<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LaneShared));
+        cudaFuncSetAttribute(k_huff_lane<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LaneShared));
+        attr_set = true;
+    }
+    uint32_t grid = (uint32_t)sm_count * 5;
     if (grid > b.nlitems) grid = b.nlitems;
-    k_huff_lane<<<grid, LN_WARPS * 32, sizeof(LaneShared), s>>>(b);
+    const bool generic = b.want_histo || !b.decode_ac || b.any_p12;
+    if (generic) k_huff_lane<true><<<grid, LN_WARPS * 32, sizeof(LaneShared), s>>>(b);
+    else k_huff_lane<false><<<grid, LN_WARPS * 32, sizeof(LaneShared), s>>>(b);
     return 1;
 }

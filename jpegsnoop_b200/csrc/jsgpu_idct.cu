@@ -18,18 +18,15 @@
 //     static accumulator indices: ~1 IMAD per MAC, no per-coefficient control flow.
 // Phase 2 (whole CTA): the tile's samples, staged in shared memory as planes, are read back 8 pixels
 // per thread and leave as 16-byte stores: three int16 map rows and two BGRA quads.
-#include "jsgpu_internal.h"
+#include "jsgpu_idct_common.cuh"
+#include "build/idct_baked.h"
+#include <cstring>
 
-#define FULL 0xffffffffu
 #define IDCT_THREADS 128
 
-struct __align__(16) IdctSmemTables {
-    int4 s4[64 * 4];            // [vu*4 + g] -> S for quadrant samples 4g..4g+3
-    int4 corrT[64];             // [yx] -> D[0..3][yx]
-    int  ncorr; int corr_pos[4];
-    int  rb_ok; int pad0, pad1;
-    int16_t tr[256], tb[256];   // chroma terms of R and B (+128 folded in)
-};
+// The quadrant table as kernel constants: every lane multiplies by the SAME entry, so it can be a
+// constant-bank operand of the IMAD itself (no load instruction, no shared-memory bandwidth).
+__constant__ int4 c_s4[64 * 4];
 
 // ConvertYCCtoRGBFastFloat (ImgDecode.cpp:4086-4139), one IEEE rounding per operation.
 __device__ __forceinline__ uint32_t ycc_to_bgra(int py, int pcb, int pcr, uint32_t& fy)
@@ -50,115 +47,20 @@ __device__ __forceinline__ uint32_t ycc_to_bgra(int py, int pcb, int pcr, uint32
     return bl | (g << 8) | (r << 16);
 }
 
-// finalise one sample: (sum/4)>>10 with C semantics, then SetFullRes's int16 arithmetic (:2513-2515)
-__device__ __forceinline__ uint32_t fin(int s, int dc)
-{
-    int r = (s + ((s >> 31) & 3)) >> 12;          // trunc(s/4) then floor(>>10) == (s + (s<0?3:0)) >> 12
-    return (uint32_t)(r * 8 + dc) & 0xFFFFu;      // (short)r*8 + dc and r*8 + dc agree in their low 16 bits
-}
-
-struct P2Args {
-    const uint8_t* planes; uint32_t pbase1, pbase2, ppitch0, ppitch1, ppitch2;
-    uint32_t opr, px0, py0, wp, hp, mcu_h, ns, evc;
-    int16_t* mapy; int16_t* mapcb; int16_t* mapcr; uint8_t* dib; const int16_t* tg;
-};
-
-// Phase 2 for chroma horizontal replication 1 << EHS.  lane = octet column of the tile (8 pixels), warps take
-// row groups (evc luma rows sharing one chroma row).  The colour terms are looked up once per distinct chroma
-// sample; pixels whose (cb,cr) pair is marked inexact in the verified table take the exact float routine.
-template <int EHS>
-__device__ __forceinline__ void phase2(const P2Args& a, const IdctSmemTables& T, uint32_t lane, uint32_t wid, unsigned long long& best, uint32_t& sum)
-{
-    constexpr int NC = 8 >> EHS;                 // distinct chroma samples under 8 pixels
-    const uint32_t nwarps = blockDim.x >> 5;
-    const uint32_t px = lane * 8;
-    for (uint32_t rg = wid; rg * a.evc < a.mcu_h; rg += nwarps) {
-        if (lane >= a.opr) continue;
-        int cbs[NC], crs[NC], tR[NC], tG[NC], tB[NC];
-        uint32_t cbw[4], crw[4];                  // replicated chroma, packed for the map stores
-        uint32_t unsafe = 0;
-        if (a.ns == 3) {
-            const uint8_t* pcb = a.planes + a.pbase1 + rg * a.ppitch1 + ((px >> EHS) << 1);
-            const uint8_t* pcr = a.planes + a.pbase2 + rg * a.ppitch2 + ((px >> EHS) << 1);
-            if (EHS == 0) {
-                const uint4 u = *reinterpret_cast<const uint4*>(pcb), v = *reinterpret_cast<const uint4*>(pcr);
-                cbw[0] = u.x; cbw[1] = u.y; cbw[2] = u.z; cbw[3] = u.w; crw[0] = v.x; crw[1] = v.y; crw[2] = v.z; crw[3] = v.w;
-                #pragma unroll
-                for (int j = 0; j < NC; j++) { cbs[j] = (j & 1) ? ((int)cbw[j >> 1] >> 16) : (int)(short)(cbw[j >> 1] & 0xFFFF); crs[j] = (j & 1) ? ((int)crw[j >> 1] >> 16) : (int)(short)(crw[j >> 1] & 0xFFFF); }
-            } else if (EHS == 1) {
-                const uint2 u = *reinterpret_cast<const uint2*>(pcb), v = *reinterpret_cast<const uint2*>(pcr);
-                const uint32_t uw[2] = {u.x, u.y}, vw[2] = {v.x, v.y};
-                #pragma unroll
-                for (int j = 0; j < NC; j++) { cbs[j] = (j & 1) ? ((int)uw[j >> 1] >> 16) : (int)(short)(uw[j >> 1] & 0xFFFF); crs[j] = (j & 1) ? ((int)vw[j >> 1] >> 16) : (int)(short)(vw[j >> 1] & 0xFFFF); }
-                cbw[0] = __byte_perm(u.x, 0, 0x1010); cbw[1] = __byte_perm(u.x, 0, 0x3232); cbw[2] = __byte_perm(u.y, 0, 0x1010); cbw[3] = __byte_perm(u.y, 0, 0x3232);
-                crw[0] = __byte_perm(v.x, 0, 0x1010); crw[1] = __byte_perm(v.x, 0, 0x3232); crw[2] = __byte_perm(v.y, 0, 0x1010); crw[3] = __byte_perm(v.y, 0, 0x3232);
-            } else {
-                const uint32_t u = *reinterpret_cast<const uint32_t*>(pcb), v = *reinterpret_cast<const uint32_t*>(pcr);
-                cbs[0] = (int)(short)(u & 0xFFFF); cbs[1] = (int)u >> 16; crs[0] = (int)(short)(v & 0xFFFF); crs[1] = (int)v >> 16;
-                cbw[0] = cbw[1] = __byte_perm(u, 0, 0x1010); cbw[2] = cbw[3] = __byte_perm(u, 0, 0x3232);
-                crw[0] = crw[1] = __byte_perm(v, 0, 0x1010); crw[2] = crw[3] = __byte_perm(v, 0, 0x3232);
-            }
-        } else {
-            #pragma unroll
-            for (int j = 0; j < NC; j++) { cbs[j] = 0; crs[j] = 0; }
-            cbw[0] = cbw[1] = cbw[2] = cbw[3] = 0; crw[0] = crw[1] = crw[2] = crw[3] = 0;
-        }
-        #pragma unroll
-        for (int j = 0; j < NC; j++) {
-            const int cbc = max(-128, min(127, cbs[j] >> 3)), crc = max(-128, min(127, crs[j] >> 3));
-            const int g = (short)__ldg(&a.tg[((cbc + 128) << 8) | (crc + 128)]);
-            tR[j] = T.tr[crc + 128]; tB[j] = T.tb[cbc + 128]; tG[j] = g;
-            if (g == 0x7FFF) unsafe |= ((1u << (1 << EHS)) - 1) << (j << EHS);
-        }
-        if (!T.rb_ok) unsafe = 0xFF;
-        for (uint32_t r2 = 0; r2 < a.evc; r2++) {
-            const uint32_t oy = rg * a.evc + r2;
-            const uint4 yv = *reinterpret_cast<const uint4*>(a.planes + oy * a.ppitch0 + px * 2);
-            const uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w};
-            const uint32_t ay = a.py0 + oy, ax = a.px0 + px;
-            const size_t mi = (size_t)ay * a.wp + ax;
-            *reinterpret_cast<uint4*>(a.mapy + mi) = yv;
-            if (a.ns == 3) {
-                *reinterpret_cast<uint4*>(a.mapcb + mi) = make_uint4(cbw[0], cbw[1], cbw[2], cbw[3]);
-                *reinterpret_cast<uint4*>(a.mapcr + mi) = make_uint4(crw[0], crw[1], crw[2], crw[3]);
-            }
-            uint32_t bgra[8]; int vmax = -0x7fffffff - 1;
-            #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const int yraw = (k & 1) ? ((int)yw[k >> 1] >> 16) : (int)(short)(yw[k >> 1] & 0xFFFF);
-                const int yc = max(-128, min(127, yraw >> 3));
-                const uint32_t r = (uint32_t)min(255, max(0, yc + tR[k >> EHS])), g = (uint32_t)min(255, max(0, yc + tG[k >> EHS])), bl = (uint32_t)min(255, max(0, yc + tB[k >> EHS]));
-                bgra[k] = bl | (g << 8) | (r << 16);
-                sum += (uint32_t)(yc + 128);
-                vmax = max(vmax, (yraw << 3) | (7 - k));              // first strict maximum in raster order
-            }
-            if (unsafe) {
-                #pragma unroll
-                for (int k = 0; k < 8; k++) if (unsafe >> k & 1) {
-                    const int yraw = (k & 1) ? ((int)yw[k >> 1] >> 16) : (int)(short)(yw[k >> 1] & 0xFFFF);
-                    uint32_t fy; bgra[k] = ycc_to_bgra(yraw, cbs[k >> EHS], crs[k >> EHS], fy);
-                }
-            }
-            const unsigned long long key = ((unsigned long long)(uint32_t)((vmax >> 3) + 32768) << 32) | (0xffffffffu - (uint32_t)(mi + (7 - (vmax & 7))));
-            best = max(best, key);
-            uint4* dp = reinterpret_cast<uint4*>(a.dib + ((size_t)(a.hp - 1 - ay) * a.wp + ax) * 4);
-            dp[0] = make_uint4(bgra[0], bgra[1], bgra[2], bgra[3]);
-            dp[1] = make_uint4(bgra[4], bgra[5], bgra[6], bgra[7]);
-        }
-    }
-}
-
+// TAB: where the quadrant table comes from — 0 = shared memory (broadcast LDS.128), 1 = constant bank (LDCU),
+// 2 = baked into the instruction stream as immediates (valid only when the host table equals the build-time copy)
+template <int TAB>
 __global__ void __launch_bounds__(IDCT_THREADS, 4) k_idct_tile(DevBatch b, const IdctSym* __restrict__ sym, const ColorTabs* __restrict__ ctab)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    IdctSmemTables& T = *reinterpret_cast<IdctSmemTables*>(smem);
-    uint8_t* const planes = smem + sizeof(IdctSmemTables);
+    Idct2Tables& T = *reinterpret_cast<Idct2Tables*>(smem);
+    uint8_t* const planes = smem + sizeof(Idct2Tables);
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     // stage the decomposed table once per CTA
     for (uint32_t i = tid; i < 64 * 4; i += blockDim.x) T.s4[i] = reinterpret_cast<const int4*>(sym->s4)[i];
     for (uint32_t i = tid; i < 64; i += blockDim.x) T.corrT[i] = make_int4(sym->corr[0][i], sym->corr[1][i], sym->corr[2][i], sym->corr[3][i]);
     if (tid == 0) { T.ncorr = sym->ncorr; for (int j = 0; j < 4; j++) T.corr_pos[j] = sym->corr_pos[j]; T.rb_ok = ctab->rb_ok; }
-    for (uint32_t i = tid; i < 256; i += blockDim.x) { T.tr[i] = ctab->tr[i]; T.tb[i] = ctab->tb[i]; }
+    for (uint32_t i = tid; i < 256; i += blockDim.x) { T.tr[i] = (int16_t)(ctab->tr[i] - 128); T.tb[i] = (int16_t)(ctab->tb[i] - 128); }
     __syncthreads();
     const int ncorr = T.ncorr;
 
@@ -203,15 +105,21 @@ __global__ void __launch_bounds__(IDCT_THREADS, 4) k_idct_tile(DevBatch b, const
             for (int p = 0; p < 4; p++)
                 #pragma unroll
                 for (int q = 0; q < 16; q++) acc[p][q] = 0;
-            #pragma unroll
-            for (int n = 1; n < 64; n++) {
-                const int cn = (n & 1) ? ((int)cw[n >> 1] >> 16) : (int)(short)(cw[n >> 1] & 0xFFFF);
-                const int p = ((n >> 3) & 1) * 2 + (n & 1);        // parity class of (v,u)
+            if (TAB == 2) {
+#define JS_COEF(n) (((n) & 1) ? ((int)cw[(n) >> 1] >> 16) : (int)(short)(cw[(n) >> 1] & 0xFFFF))
+                JS_BAKED_MACS(acc, JS_COEF)                       // 63 x 16 IMADs with immediate operands
+#undef JS_COEF
+            } else {
                 #pragma unroll
-                for (int gq = 0; gq < 4; gq++) {
-                    const int4 t = T.s4[n * 4 + gq];               // warp-uniform address: broadcast
-                    acc[p][gq * 4 + 0] += t.x * cn; acc[p][gq * 4 + 1] += t.y * cn;
-                    acc[p][gq * 4 + 2] += t.z * cn; acc[p][gq * 4 + 3] += t.w * cn;
+                for (int n = 1; n < 64; n++) {
+                    const int cn = (n & 1) ? ((int)cw[n >> 1] >> 16) : (int)(short)(cw[n >> 1] & 0xFFFF);
+                    const int p = ((n >> 3) & 1) * 2 + (n & 1);        // parity class of (v,u)
+                    #pragma unroll
+                    for (int gq = 0; gq < 4; gq++) {
+                        const int4 t = (TAB == 1) ? c_s4[n * 4 + gq] : T.s4[n * 4 + gq];      // warp-uniform
+                        acc[p][gq * 4 + 0] += t.x * cn; acc[p][gq * 4 + 1] += t.y * cn;
+                        acc[p][gq * 4 + 2] += t.z * cn; acc[p][gq * 4 + 3] += t.w * cn;
+                    }
                 }
             }
             // corrections: coefficients at the (<=4) positions whose table entries are not mirror-symmetric
@@ -239,7 +147,7 @@ __global__ void __launch_bounds__(IDCT_THREADS, 4) k_idct_tile(DevBatch b, const
                         s2 += d2.x * cj[0] + d2.y * cj[1] + d2.z * cj[2] + d2.w * cj[3];
                         s3 += d3.x * cj[0] + d3.y * cj[1] + d3.z * cj[2] + d3.w * cj[3];
                     }
-                    top[x] = fin(s0, dc); top[7 - x] = fin(s1, dc); bot[x] = fin(s2, dc); bot[7 - x] = fin(s3, dc);
+                    top[x] = fin2(s0, dc); top[7 - x] = fin2(s1, dc); bot[x] = fin2(s2, dc); bot[7 - x] = fin2(s3, dc);
                 }
                 if (valid) {
                     *reinterpret_cast<uint4*>(pl + y * ppc) = make_uint4(top[0] | (top[1] << 16), top[2] | (top[3] << 16), top[4] | (top[5] << 16), top[6] | (top[7] << 16));
@@ -250,14 +158,15 @@ __global__ void __launch_bounds__(IDCT_THREADS, 4) k_idct_tile(DevBatch b, const
         __syncthreads();
         // ---------------- phase 2: 8 pixels x (chroma row group) per thread, vector stores ----------------
         {
-            P2Args a;
+            P2x a;
             a.planes = planes; a.pbase1 = pbase1; a.pbase2 = pbase2; a.ppitch0 = ppitch0; a.ppitch1 = ppitch1; a.ppitch2 = ppitch2;
             a.opr = (nmt * im.mcu_w) >> 3; a.px0 = mcol0 * im.mcu_w; a.py0 = trow * im.mcu_h; a.wp = im.wp; a.hp = im.hp; a.mcu_h = im.mcu_h;
             a.mapy = b.pix_y + im.pix_off; a.mapcb = b.pix_cb + im.pix_off; a.mapcr = b.pix_cr + im.pix_off; a.dib = b.dib + im.dib_off;
-            a.ns = ns; a.evc = (ns == 3) ? im.ev[1] : 1; a.tg = ctab->tg;
+            a.ns = ns; a.evc = (ns == 3) ? im.ev[1] : 1; a.gflag = ctab->gflag;
             const uint32_t eh = (ns == 3) ? im.eh[1] : 1;
             unsigned long long best = 0; uint32_t sum = 0;
-            if (eh == 1) phase2<0>(a, T, lane, wid, best, sum); else if (eh == 2) phase2<1>(a, T, lane, wid, best, sum); else phase2<2>(a, T, lane, wid, best, sum);
+            if (eh == 1) phase2x<0>(a, T, lane, wid, best, sum); else if (eh == 2) phase2x<1>(a, T, lane, wid, best, sum); else phase2x<2>(a, T, lane, wid, best, sum);
+            sum = (sum & 0xFFFF) + (sum >> 16);
             unsigned long long sum64 = sum;
             #pragma unroll
             for (int d = 16; d; d >>= 1) { best = max(best, __shfl_xor_sync(FULL, best, d)); sum64 += __shfl_xor_sync(FULL, sum64, d); }
@@ -294,29 +203,48 @@ __global__ void __launch_bounds__(256) k_build_color_tables(ColorTabs* t)
     }
     t->tg[idx] = okG ? (int16_t)dG : (int16_t)0x7FFF;
     if (!okG) atomicAdd(&t->n_unsafe, 1);
+    const int cand = (-(JS_GA * cb + JS_GB * cr)) >> 23;               // arithmetic candidate for dG - 128
+    if (!okG || cand != dG - 128) { atomicOr(&t->gflag[idx >> 5], 1u << (idx & 31)); atomicAdd(&t->n_gflag, 1); }
     if (cb == 0) { t->tr[cr + 128] = (int16_t)dR; if (!okR) atomicAnd(&t->rb_ok, 0); }
     if (cr == 0) { t->tb[cb + 128] = (int16_t)dB; if (!okB) atomicAnd(&t->rb_ok, 0); }
 }
 
 int js_launch_build_color_tables(ColorTabs* t, cudaStream_t s)
 {
-    ColorTabs init; memset(&init, 0, sizeof(int16_t) * 512); init.rb_ok = 1; init.n_unsafe = 0;
-    cudaMemcpyAsync(t, &init, offsetof(ColorTabs, tg), cudaMemcpyHostToDevice, s);
+    cudaMemsetAsync(t, 0, sizeof(ColorTabs), s);
+    const int32_t one = 1;
+    cudaMemcpyAsync(&t->rb_ok, &one, sizeof one, cudaMemcpyHostToDevice, s);
     cudaStreamSynchronize(s);
     k_build_color_tables<<<256, 256, 0, s>>>(t);
     return 1;
 }
 
-int js_launch_idct_fused(const DevBatch& b, const IdctSym* sym, const ColorTabs* ctab, int sm_count, cudaStream_t s)
+int js_upload_idct_constants(const IdctSym* host_sym, cudaStream_t s)
+{
+    return cudaMemcpyToSymbolAsync(c_s4, host_sym->s4, sizeof(int) * 64 * 16, 0, cudaMemcpyHostToDevice, s) == cudaSuccess ? 0 : -1;
+}
+
+int js_idct_baked_matches(const int32_t* li) { return memcmp(li, kBakedLi, sizeof kBakedLi) == 0; }
+
+int js_launch_idct_fused(const DevBatch& b, const IdctSym* sym, const ColorTabs* ctab, int sm_count, int tab_mode, cudaStream_t s)
 {
     if (b.ntiles == 0) return 0;
     static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(k_idct_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(IdctSmemTables) + 48 * 1024)); attr_set = true; }
+    if (!attr_set) {
+        const int mx = (int)(sizeof(Idct2Tables) + 48 * 1024);
+        cudaFuncSetAttribute(k_idct_tile<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(k_idct_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(k_idct_tile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        attr_set = true;
+    }
     // one warp per 32-block group of a tile, at most 4 warps (larger tiles loop)
     uint32_t groups = (b.tile_plane_bytes / 128 + 31) / 32;
     uint32_t threads = 32 * (groups < 1 ? 1 : groups > 4 ? 4 : groups);
     uint32_t grid = (uint32_t)sm_count * (threads <= 96 ? 5 : 4);
     if (grid > b.ntiles) grid = b.ntiles;
-    k_idct_tile<<<grid, threads, sizeof(IdctSmemTables) + (size_t)b.tile_plane_bytes, s>>>(b, sym, ctab);
+    const size_t smem = sizeof(Idct2Tables) + (size_t)b.tile_plane_bytes;
+    if (tab_mode == 2) k_idct_tile<2><<<grid, threads, smem, s>>>(b, sym, ctab);
+    else if (tab_mode == 1) k_idct_tile<1><<<grid, threads, smem, s>>>(b, sym, ctab);
+    else k_idct_tile<0><<<grid, threads, smem, s>>>(b, sym, ctab);
     return 1;
 }

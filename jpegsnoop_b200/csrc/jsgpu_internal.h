@@ -4,11 +4,12 @@
 #include <stdint.h>
 #include <cuda_runtime.h>
 
-#define JS_LUT_BITS   11                 // direct Huffman look-up width (reference uses 9: ImgDecode.h:96)
+#define JS_LUT_BITS   10                 // direct Huffman look-up width (reference uses 9: ImgDecode.h:96)
 #define JS_LUT_SIZE   (1 << JS_LUT_BITS)
 #define JS_LUT2_BITS  (16 - JS_LUT_BITS)
 #define JS_LUT2_SIZE  8192               // second-level entries per slot (256 sub-tables of 32)
 #define JS_MAX_CODES  260
+#define JS_STUFF_LIST 6                  // stuffed-byte positions recorded per restart interval
 #define JS_NSLOT      8                  // (class,Th) pairs: slot = class*4 + Th
 
 // Device form of one jsgpu_tables set.
@@ -50,6 +51,7 @@ struct DevImage {
     uint32_t std_layout;            // 1 = every component has H in {1,Hmax} and V in {1,Vmax} (fused IDCT kernel applies)
     uint32_t tile_mcus;             // MCUs per IDCT tile (32 / Hmax)
     uint32_t tiles_per_row;
+    uint32_t tile_groups;           // 32-block groups per IDCT tile
     uint32_t item_first, nitems;    // Huffman work items (groups of HUFF_WARPS segments)
     uint32_t tile_first, ntiles;    // IDCT tiles
 };
@@ -67,6 +69,8 @@ struct DevBatch {
     uint32_t*          seg_endbits; // unstuffed bit position where decoding of the segment stopped
     uint32_t*          seg_status;
     uint32_t*          seg_ulen;    // unstuffed length of each interval
+    uint32_t*          seg_nstuff;  // number of stuffed zeros in each interval
+    uint32_t*          seg_stuff;   // [nseg][JS_STUFF_LIST] unstuffed index of the FF before each stuffed zero
     unsigned long long* seg_uoff;   // where its unstuffed copy starts in ubits
     uint8_t*           ubits;       // unstuffed, 16-byte aligned, 0xFF-padded copies of all intervals
     uint32_t           nseg_total;
@@ -77,8 +81,9 @@ struct DevBatch {
     uint32_t           nitems;
     const uint2*       litems;      // Huffman, lane kernel: (image, first segment), JS_LANE_SEGS per item
     uint32_t           nlitems;
-    const uint4*       tiles;       // IDCT: (image, mcu_row, mcu_col0, nmcu) [ntiles]
+    const uint4*       tiles;       // IDCT: (image, mcu_row, mcu_col0, nmcu) [ntiles], grouped by chroma replication class
     uint32_t           ntiles;
+    uint32_t           tcls_first[3], tcls_count[3];   // tiles whose images have chroma eh = 1, 2, 4
     // pools
     int16_t*           coef;        // 64 int16 per block, natural order, slot 0 = cumulative DC
     uint32_t*          mcu_bitpos;  // unstuffed bit offset of each MCU start within its segment
@@ -93,6 +98,9 @@ struct DevBatch {
     uint32_t*          img_status;  // [nimg]
     // options
     int                decode_ac, want_histo, idct_mode;
+    int                any_p12;              // some image has sample precision > 8 (ReadScanVal's divide, ID:1234-1238)
+    int                blkdc_by_gather;      // 1: block-DC maps by the gather kernel (simple IDCT path), 0: written by k_idct_tile
+    int                stuff_overflow_possible;
     int                simple_only_nonstd;   // simple IDCT kernels skip images the fused kernel handled
     uint32_t           tile_plane_bytes;     // shared-memory plane bytes the largest tile needs
 };
@@ -108,8 +116,12 @@ int js_launch_huffman_lane(const DevBatch& b, int sm_count, cudaStream_t s);
 int js_launch_idct_simple(const DevBatch& b, const int32_t* li, const float* lf, uint64_t total_blocks,
                           uint64_t total_pix, cudaStream_t s);
 struct IdctSym; struct ColorTabs;
-int js_launch_idct_fused(const DevBatch& b, const IdctSym* sym, const ColorTabs* ctab, int sm_count, cudaStream_t s);
+int js_launch_idct_fused(const DevBatch& b, const IdctSym* sym, const ColorTabs* ctab, int sm_count, int tab_mode, cudaStream_t s);
+int js_idct_baked_matches(const int32_t* li);
 int js_launch_build_color_tables(ColorTabs* t, cudaStream_t s);
+int js_upload_idct_constants(const IdctSym* host_sym, cudaStream_t s);
+int js_make_coef_tensor_map(void* out_tmap, void* coef, uint64_t rows);
+int js_launch_idct_tma(const DevBatch& b, const IdctSym* sym, const ColorTabs* ctab, const void* tmap_host, int sm_count, cudaStream_t s);
 int js_launch_finalize(const DevBatch& b, cudaStream_t s);
 
 // Quadrant-symmetric decomposition of the integer IDCT table (built on the host at table upload,
@@ -129,4 +141,10 @@ struct ColorTabs {
     int16_t tr[256], tb[256];
     int32_t rb_ok, n_unsafe;
     int16_t tg[65536];
+    // arithmetic form of the G term: tg - 128 == (-(JS_GA*cb + JS_GB*cr)) >> 23 wherever the matching bit of
+    // gflag is clear (verified on the device for all 65536 pairs); set bits (and tg == 0x7FFF) take the exact path
+    uint32_t gflag[2048];
+    int32_t n_gflag;
 };
+#define JS_GA 2886824        // 0.114f*(2-2*0.114f)/0.587f * 2^23
+#define JS_GB 5990609        // 0.299f*(2-2*0.299f)/0.587f * 2^23

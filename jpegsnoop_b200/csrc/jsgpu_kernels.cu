@@ -28,13 +28,12 @@ __global__ void __launch_bounds__(MS_THREADS) k_marker_scan(DevBatch b)
     if (!im.valid) return;
     __shared__ uint32_t s_warp[MS_THREADS / 32];
     __shared__ uint32_t s_term;
-    __shared__ uint32_t s_base;
     const uint8_t* p = b.bits + im.scan_off;
     const uint64_t n = im.scan_len;
     const uint32_t t = threadIdx.x, lane = t & 31, wid = t >> 5;
     uint32_t* seg_start = b.seg_start + im.seg_first;
     uint32_t* seg_end   = b.seg_end + im.seg_first;
-    if (t == 0) { s_base = 0; seg_start[0] = 0; }
+    if (t == 0) seg_start[0] = 0;
     uint32_t found = 0;            // RST markers accepted so far (uniform after each iteration)
     uint32_t term = 0xffffffffu;
     for (uint64_t base = 0; base < n; base += MS_THREADS * 16) {
@@ -42,17 +41,26 @@ __global__ void __launch_bounds__(MS_THREADS) k_marker_scan(DevBatch b)
         if (t == 0) s_term = 0xffffffffu;
         __syncthreads();
         uint64_t off = base + (uint64_t)t * 16;
-        uint8_t by[17];
-        #pragma unroll
-        for (int i = 0; i < 17; i++) by[i] = (off + i < n) ? p[off + i] : 0;
-        // vector form is not needed here: the bytes come through L1 and this kernel moves
-        // ~0.3 B/px; see DESIGN.md for its share of the step.
+        // 16 bytes per thread as four words (scan_off is 16-byte aligned); FF bytes are rare (~1/200), so
+        // test a whole word for "any byte == FF" first and only then look at its bytes.
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (off + 16 <= n) v = __ldg(reinterpret_cast<const uint4*>(p + off));
+        else { uint32_t w[4] = {0, 0, 0, 0}; for (int i = 0; i < 16; i++) if (off + i < n) w[i >> 2] |= (uint32_t)p[off + i] << (8 * (i & 3)); v = make_uint4(w[0], w[1], w[2], w[3]); }
+        uint32_t nextb = __shfl_down_sync(FULL, v.x, 1) & 0xFF;           // first byte of the next thread's chunk
+        if (lane == 31) nextb = (off + 16 < n) ? p[off + 16] : 0;
         uint32_t mask = 0;         // bit i: RST marker starts at off+i
         uint32_t myterm = 0xffffffffu;
+        const uint32_t ws[5] = {v.x, v.y, v.z, v.w, nextb};
         #pragma unroll
-        for (int i = 0; i < 16; i++) {
-            if (off + i + 1 < n && by[i] == 0xFF) {
-                uint32_t m = by[i + 1];
+        for (int wi = 0; wi < 4; wi++) {
+            const uint32_t w = ws[wi];
+            if (((~w - 0x01010101u) & w & 0x80808080u) == 0) continue;     // no byte of w is 0xFF
+            #pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (((w >> (8 * j)) & 0xFF) != 0xFF) continue;
+                const int i = wi * 4 + j;
+                if (off + i + 1 >= n) continue;
+                const uint32_t m = (j < 3) ? ((w >> (8 * j + 8)) & 0xFF) : (ws[wi + 1] & 0xFF);
                 if (m >= 0xD0 && m <= 0xD7) mask |= 1u << i;
                 else if (m != 0x00 && m != 0xFF && myterm == 0xffffffffu) myterm = (uint32_t)(off + i);
             }
@@ -258,6 +266,7 @@ __global__ void __launch_bounds__(128) k_finalize_mcumap(DevBatch b)
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (gw >= b.nseg_total) return;
+    if (b.seg_nstuff[gw] <= JS_STUFF_LIST) return;          // k_finalize_mcumap_fast did this interval
     uint32_t lo = 0, hi = b.nimg - 1;                       // image owning segment gw
     while (lo < hi) { uint32_t mid = (lo + hi + 1) >> 1; if (b.img[mid].seg_first <= gw) lo = mid; else hi = mid - 1; }
     const DevImage& im = b.img[lo];
@@ -303,13 +312,45 @@ __global__ void __launch_bounds__(128) k_finalize_mcumap(DevBatch b)
     }
 }
 
+// Fast MCU file map: one thread per MCU, using the stuffed-byte list k_unstuff recorded per interval
+// (raw offset of unstuffed byte u = u + number of stuffed zeros before it).  Intervals with more
+// stuffed bytes than the list holds are left to k_finalize_mcumap (the raw re-walk above).
+__global__ void __launch_bounds__(256) k_finalize_mcumap_fast(DevBatch b)
+{
+    const DevImage& im = b.img[blockIdx.y];
+    if (!im.valid) return;
+    for (uint32_t m = blockIdx.x * blockDim.x + threadIdx.x; m < im.nmcu; m += gridDim.x * blockDim.x) {
+        uint32_t k = m / im.ri, t = m - k * im.ri, bit;
+        if (t > 0) bit = b.mcu_bitpos[im.mcu_off + m];
+        else if (k == 0) bit = 0;
+        else { k -= 1; bit = b.seg_endbits[im.seg_first + k]; }       // lazy restart: end state of the previous interval
+        const uint32_t sidx = im.seg_first + k;
+        const uint32_t ns = b.seg_nstuff[sidx];
+        if (ns > JS_STUFF_LIST) continue;                               // handled by the raw re-walk kernel
+        const uint32_t D = b.seg_ulen[sidx];
+        uint32_t u = bit >> 3, al = bit & 7;
+        uint32_t val;
+        if (u >= D) {                                                   // accumulator emptied (ImgDecode.cpp:934-953)
+            if (D < 4) { val = 0; b.mcu_map[im.mcu_off + m] = val; continue; }   // pos[] still holds the zeros of the last reset
+            u = D - 1; al = 0;
+        }
+        uint32_t raw = u;
+        for (uint32_t j = 0; j < ns; j++) raw += (b.seg_stuff[(size_t)sidx * JS_STUFF_LIST + j] < u) ? 1u : 0u;
+        val = ((im.file_pos + b.seg_start[sidx] + raw) << 4) + al;
+        b.mcu_map[im.mcu_off + m] = val;
+    }
+}
+
 int js_launch_finalize(const DevBatch& b, cudaStream_t s)
 {
     if (b.nimg == 0) return 0;
-    dim3 grid(64, b.nimg);
-    k_finalize_blkdc<<<grid, 256, 0, s>>>(b);
-    k_finalize_stats<<<(b.nimg + 127) / 128, 128, 0, s>>>(b);
-    if (b.mcu_map && b.nseg_total) { k_finalize_mcumap<<<(b.nseg_total + 3) / 4, 128, 0, s>>>(b); return 3; }
-    return 2;
+    int n = 0;
+    if (b.blkdc_by_gather) { dim3 grid(64, b.nimg); k_finalize_blkdc<<<grid, 256, 0, s>>>(b); n++; }
+    k_finalize_stats<<<(b.nimg + 127) / 128, 128, 0, s>>>(b); n++;
+    if (b.mcu_map && b.nseg_total) {
+        dim3 grid(32, b.nimg);
+        k_finalize_mcumap_fast<<<grid, 256, 0, s>>>(b); n++;
+        if (b.stuff_overflow_possible) { k_finalize_mcumap<<<(b.nseg_total + 3) / 4, 128, 0, s>>>(b); n++; }
+    }
+    return n;
 }
-

@@ -22,7 +22,7 @@ def cases():
     return JC.small_cases()
 
 
-@pytest.mark.parametrize("kernels", [(1, 1), (2, 2), (1, 2), (2, 1), (0, 0)], ids=["warp+simple", "lane+fused", "warp+fused", "lane+simple", "auto"])
+@pytest.mark.parametrize("kernels", [(1, 1), (2, 2), (1, 3), (2, 1), (0, 0)], ids=["warp+simple", "lane+tma_tile", "warp+ldg_tile", "lane+simple", "auto"])
 @pytest.mark.parametrize("fixed", [True, False], ids=["idct_fixed", "idct_float"])
 def test_single_image_dropin_matches_oracle(built, cases, fixed, kernels):
     from jpegsnoop_b200 import CimgDecode
@@ -38,7 +38,7 @@ def test_single_image_dropin_matches_oracle(built, cases, fixed, kernels):
         assert np.array_equal(want_stats, got_stats), (name, want_stats, got_stats)
 
 
-@pytest.mark.parametrize("kernels", [(1, 1), (2, 2), (0, 0)], ids=["warp+simple", "lane+fused", "auto"])
+@pytest.mark.parametrize("kernels", [(1, 1), (2, 2), (2, 3), (0, 0)], ids=["warp+simple", "lane+tma_tile", "lane+ldg_tile", "auto"])
 def test_batch_matches_oracle(built, cases, kernels):
     from jpegsnoop_b200 import BatchDecoder
     orc = _oracle(True)
