@@ -49,8 +49,9 @@ __device__ __forceinline__ uint32_t ycc_to_bgra(int py, int pcb, int pcr, uint32
 
 // TAB: where the quadrant table comes from — 0 = shared memory (broadcast LDS.128), 1 = constant bank (LDCU),
 // 2 = baked into the instruction stream as immediates (valid only when the host table equals the build-time copy)
-template <int TAB>
-__global__ void __launch_bounds__(IDCT_THREADS, 4) k_idct_tile(DevBatch b, const IdctSym* __restrict__ sym, const ColorTabs* __restrict__ ctab)
+template <int TAB, int EHS>
+__global__ void __launch_bounds__(IDCT_THREADS, 4) k_idct_tile(DevBatch b, const IdctSym* __restrict__ sym, const ColorTabs* __restrict__ ctab,
+                                                                uint32_t tile_first, uint32_t tile_count)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     Idct2Tables& T = *reinterpret_cast<Idct2Tables*>(smem);
@@ -64,8 +65,8 @@ __global__ void __launch_bounds__(IDCT_THREADS, 4) k_idct_tile(DevBatch b, const
     __syncthreads();
     const int ncorr = T.ncorr;
 
-    for (uint32_t ti = blockIdx.x; ti < b.ntiles; ti += gridDim.x) {
-        const uint4 tile = b.tiles[ti];                    // (image, mcu row, first mcu col, mcus in tile)
+    for (uint32_t ti = blockIdx.x; ti < tile_count; ti += gridDim.x) {
+        const uint4 tile = b.tiles[tile_first + ti];       // (image, mcu row, first mcu col, mcus in tile)
         const DevImage& im = b.img[tile.x];
         const uint32_t ns = im.ns, U = im.tile_mcus;
         const uint32_t trow = tile.y, mcol0 = tile.z, nmt = tile.w;
@@ -89,6 +90,14 @@ __global__ void __launch_bounds__(IDCT_THREADS, 4) k_idct_tile(DevBatch b, const
             const uint32_t v = i / huc, col = i - v * huc;
             const bool valid = (g * 32 + lane < nblk) && (col < nmt * Hc);
             const size_t row = im.coef_row[c] + (size_t)(trow * im.V[c] + v) * im.cw[c] + (mcol0 * Hc + col);
+            // pull this lane's row of the CTA's NEXT tile towards L2 while the current one is being computed
+            if (ti + gridDim.x < tile_count) {
+                const uint4 nt = b.tiles[tile_first + ti + gridDim.x];
+                if (nt.x == tile.x && col < nt.w * Hc) {
+                    const size_t nrow = im.coef_row[c] + (size_t)(nt.y * im.V[c] + v) * im.cw[c] + (nt.z * Hc + col);
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(b.coef + nrow * 64));
+                }
+            }
             uint4 cw4[8];
             if (valid) {
                 const uint4* rp = reinterpret_cast<const uint4*>(b.coef + row * 64);
@@ -163,9 +172,8 @@ __global__ void __launch_bounds__(IDCT_THREADS, 4) k_idct_tile(DevBatch b, const
             a.opr = (nmt * im.mcu_w) >> 3; a.px0 = mcol0 * im.mcu_w; a.py0 = trow * im.mcu_h; a.wp = im.wp; a.hp = im.hp; a.mcu_h = im.mcu_h;
             a.mapy = b.pix_y + im.pix_off; a.mapcb = b.pix_cb + im.pix_off; a.mapcr = b.pix_cr + im.pix_off; a.dib = b.dib + im.dib_off;
             a.ns = ns; a.evc = (ns == 3) ? im.ev[1] : 1; a.gflag = ctab->gflag;
-            const uint32_t eh = (ns == 3) ? im.eh[1] : 1;
             unsigned long long best = 0; uint32_t sum = 0;
-            if (eh == 1) phase2x<0>(a, T, lane, wid, best, sum); else if (eh == 2) phase2x<1>(a, T, lane, wid, best, sum); else phase2x<2>(a, T, lane, wid, best, sum);
+            phase2x<EHS>(a, T, lane, wid, best, sum);
             sum = (sum & 0xFFFF) + (sum >> 16);
             unsigned long long sum64 = sum;
             #pragma unroll
@@ -226,25 +234,39 @@ int js_upload_idct_constants(const IdctSym* host_sym, cudaStream_t s)
 
 int js_idct_baked_matches(const int32_t* li) { return memcmp(li, kBakedLi, sizeof kBakedLi) == 0; }
 
-int js_launch_idct_fused(const DevBatch& b, const IdctSym* sym, const ColorTabs* ctab, int sm_count, int tab_mode, cudaStream_t s)
+template <int TAB>
+static int launch_tab(const DevBatch& b, const IdctSym* sym, const ColorTabs* ctab, int sm_count, cudaStream_t s)
 {
-    if (b.ntiles == 0) return 0;
     static bool attr_set = false;
+    const int mx = (int)(sizeof(Idct2Tables) + 48 * 1024);
     if (!attr_set) {
-        const int mx = (int)(sizeof(Idct2Tables) + 48 * 1024);
-        cudaFuncSetAttribute(k_idct_tile<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-        cudaFuncSetAttribute(k_idct_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-        cudaFuncSetAttribute(k_idct_tile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(k_idct_tile<TAB, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(k_idct_tile<TAB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(k_idct_tile<TAB, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         attr_set = true;
     }
     // one warp per 32-block group of a tile, at most 4 warps (larger tiles loop)
     uint32_t groups = (b.tile_plane_bytes / 128 + 31) / 32;
     uint32_t threads = 32 * (groups < 1 ? 1 : groups > 4 ? 4 : groups);
-    uint32_t grid = (uint32_t)sm_count * (threads <= 96 ? 5 : 4);
-    if (grid > b.ntiles) grid = b.ntiles;
     const size_t smem = sizeof(Idct2Tables) + (size_t)b.tile_plane_bytes;
-    if (tab_mode == 2) k_idct_tile<2><<<grid, threads, smem, s>>>(b, sym, ctab);
-    else if (tab_mode == 1) k_idct_tile<1><<<grid, threads, smem, s>>>(b, sym, ctab);
-    else k_idct_tile<0><<<grid, threads, smem, s>>>(b, sym, ctab);
-    return 1;
+    int n = 0;
+    for (int cls = 0; cls < 3; cls++) {
+        const uint32_t cnt = b.tcls_count[cls];
+        if (!cnt) continue;
+        uint32_t grid = (uint32_t)sm_count * (threads <= 96 ? 5 : 4);
+        if (grid > cnt) grid = cnt;
+        if (cls == 0) k_idct_tile<TAB, 0><<<grid, threads, smem, s>>>(b, sym, ctab, b.tcls_first[cls], cnt);
+        else if (cls == 1) k_idct_tile<TAB, 1><<<grid, threads, smem, s>>>(b, sym, ctab, b.tcls_first[cls], cnt);
+        else k_idct_tile<TAB, 2><<<grid, threads, smem, s>>>(b, sym, ctab, b.tcls_first[cls], cnt);
+        n++;
+    }
+    return n;
+}
+
+int js_launch_idct_fused(const DevBatch& b, const IdctSym* sym, const ColorTabs* ctab, int sm_count, int tab_mode, cudaStream_t s)
+{
+    if (b.ntiles == 0) return 0;
+    if (tab_mode == 2) return launch_tab<2>(b, sym, ctab, sm_count, s);
+    if (tab_mode == 1) return launch_tab<1>(b, sym, ctab, sm_count, s);
+    return launch_tab<0>(b, sym, ctab, sm_count, s);
 }

@@ -14,7 +14,7 @@ struct __align__(16) Idct2Tables {
 };
 
 // ConvertYCCtoRGBFastFloat (ImgDecode.cpp:4086-4139), one IEEE rounding per operation (exact path).
-__device__ __forceinline__ uint32_t ycc_exact(int py, int pcb, int pcr)
+static __device__ __noinline__ uint32_t ycc_exact(int py, int pcb, int pcr)
 {
     int y = py >> 3, cb = pcb >> 3, cr = pcr >> 3;
     y = max(-128, min(127, y)); cb = max(-128, min(127, cb)); cr = max(-128, min(127, cr));
@@ -124,7 +124,7 @@ __device__ __forceinline__ void phase2x(const P2x& a, const Idct2Tables& T, uint
                 bgra[2 * p]     = __byte_perm(__byte_perm(bp, gp, 0x0040), rp, 0x5410);
                 bgra[2 * p + 1] = __byte_perm(__byte_perm(bp, gp, 0x0062), rp, 0x7610);
             }
-            if (unsafe) {
+            if (unsafe) {              // rare (a handful of (cb,cr) pairs): the exact float routine, out of line
                 #pragma unroll
                 for (int k = 0; k < 8; k++) if (unsafe >> k & 1) {
                     const int yraw = (k & 1) ? ((int)yw[k >> 1] >> 16) : (int)(short)(yw[k >> 1] & 0xFFFF);
