@@ -10,6 +10,7 @@
 #include <cstdarg>
 #include <string>
 #include <vector>
+#include <array>
 #include <algorithm>
 
 #define JSGPU_VERSION 100
@@ -42,6 +43,7 @@ struct jsgpu_ctx {
     bool sym_ok = false, baked_ok = false; int tab_mode = 0;
     DevBuf d_bits, d_seg, d_coef, d_mcubits, d_pix, d_dib, d_blk, d_mcumap, d_histo, d_stats, d_misc;
     uint32_t nsets = 0;
+    std::vector<std::array<uint32_t, JS_NSLOT>> set_l2;   // per table set and slot: second-level entries used (0xffffffff = overflowed)
     // batch state
     bool planned = false, decoded = false;
     std::vector<DevImage> himg;
@@ -254,6 +256,7 @@ static void build_table_set(const jsgpu_tables& t, DevTableSet& d)
             }
         }
         d.lut2_overflow[slot] = overflow ? 1 : 0;
+        d.lut2_used[slot] = nsub << JS_LUT2_BITS;
         if (overflow) {       // pathological table: every long prefix goes to the in-order search
             memset(d.lut[slot], 0, sizeof d.lut[slot]);
             for (uint32_t p = 0; p < JS_LUT_SIZE; p++) {
@@ -279,6 +282,8 @@ int jsgpu_upload_tables(jsgpu_ctx* ctx, const jsgpu_tables* sets, uint32_t nsets
     CK(ctx->d_tables.reserve(sizeof(DevTableSet) * (size_t)nsets));
     CK(cudaMemcpyAsync(ctx->d_tables.p, h.data(), sizeof(DevTableSet) * (size_t)nsets, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    ctx->set_l2.assign(nsets, {});
+    for (uint32_t i = 0; i < nsets; i++) for (int k = 0; k < JS_NSLOT; k++) ctx->set_l2[i][k] = h[i].lut2_overflow[k] ? 0xffffffffu : h[i].lut2_used[k];
     ctx->nsets = nsets;
     return JSGPU_OK;
 }
@@ -320,6 +325,8 @@ static bool plan_image(const jsgpu_image_desc& d, uint32_t nsets, DevImage& im)
         im.slot_dc[c] = d.dht_dc_sel[c]; im.slot_ac[c] = 4 + d.dht_ac_sel[c];
         im.dqt[c] = d.dqt_sel[c];
     }
+    im.tab_sig = ns;
+    for (uint32_t c = 0; c < ns; c++) im.tab_sig = (im.tab_sig << 6) | (im.slot_dc[c] & 3) << 4 | (im.slot_ac[c] & 3) << 2 | (im.dqt[c] & 3);
     im.restart_en = (d.restart_en && d.restart_interval) ? 1 : 0;
     im.ri = im.restart_en ? d.restart_interval : im.nmcu;
     im.nseg = (im.nmcu + im.ri - 1) / im.ri;
@@ -521,6 +528,15 @@ int jsgpu_batch_decode(jsgpu_ctx* ctx)
     DevBatch& b = ctx->batch;
     b.decode_ac = ctx->opt.decode_ac; b.want_histo = ctx->opt.want_histo; b.idct_mode = ctx->opt.idct_mode;
     b.any_p12 = 0; for (const DevImage& im : ctx->himg) if (im.valid && im.precision > 8) b.any_p12 = 1;
+    b.lane_nlut = 1; b.lane_l2_smem = 1;
+    for (const DevImage& im : ctx->himg) if (im.valid) {
+        uint32_t seen = 0, nl = 0;
+        for (uint32_t c = 0; c < im.ns; c++) for (int cls = 0; cls < 2; cls++) {
+            const uint32_t slot = cls ? im.slot_ac[c] : im.slot_dc[c];
+            if (!(seen >> slot & 1)) { seen |= 1u << slot; nl++; if (ctx->set_l2[im.table_set][slot] > JS_LANE_L2S) b.lane_l2_smem = 0; }
+        }
+        b.lane_nlut = std::max(b.lane_nlut, nl);
+    }
     cudaStream_t s = ctx->stream;
     int launches = 0;
     CK(cudaEventRecord(ctx->ev[0], s));

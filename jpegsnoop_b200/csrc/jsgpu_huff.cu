@@ -307,16 +307,25 @@ int js_launch_huffman_warp(const DevBatch& b, int sm_count, cudaStream_t s)
 // ------------------------------------------------------------------------------------------------
 // lane per restart interval
 // ------------------------------------------------------------------------------------------------
-#define LN_WARPS   4
+#define LN_WARPS   (JS_LANE_SEGS / 32)
 #define ROW_PITCH  144                      // bytes per lane row: 64 coefficients + 8 dummy slots; 16-byte aligned
-struct LaneShared {
-    HuffTabs t;
+// Dynamic shared memory of the lane kernel:
+//   LaneHdr | coefficient rows [LN_WARPS][32][ROW_PITCH] | lut [nl][JS_LUT_SIZE] | lut2 [nl][JS_LANE_L2S] | (HISTO) hw [LN_WARPS][16][32]
+// nl = DevBatch::lane_nlut: the distinct (class,Th) tables an image selects are staged once each (Cb and Cr
+// normally share theirs).  hw: AC code-length counters, one 32-bit word per (length 1..16, lane); a lane only
+// touches its own column, so the result-less shared atomic is conflict-free and nothing waits on it; the
+// columns are summed into LaneHdr::histo once per (MCU, component).
+struct LaneHdr {
     uint32_t histo[6][17];
-    __align__(16) uint8_t rows[LN_WARPS][32 * ROW_PITCH];
-    // code-length histogram staging: one byte counter per (class, length 1..16, lane); a lane increments only
-    // its own column, so no atomics; flushed per block (a block has <= 64 symbols, so a byte cannot overflow)
-    __align__(16) uint8_t hb[LN_WARPS][2 * 16 * 32];
+    uint32_t qz[3][80];                     // quantiser | natural index<<16 ; entries 64..79 -> dummy slots past the row
+    uint32_t li[6];                         // [comp*2 + class] -> staged table index
+    uint32_t lslot[6];                      // staged table index -> slot
+    uint32_t nl, pad;
 };
+static inline size_t lane_smem_bytes(uint32_t nl, bool histo)
+{
+    return sizeof(LaneHdr) + (size_t)LN_WARPS * 32 * ROW_PITCH + (size_t)nl * (JS_LUT_SIZE + JS_LANE_L2S) * 2 + (histo ? (size_t)LN_WARPS * 16 * 32 * 4 : 0);
+}
 
 // Bit window as two 32-bit registers (hi = next 32 bits, lo = the 32 after), funnel-shift consume.
 struct Win {
@@ -338,30 +347,64 @@ struct Win {
 };
 
 // GENERIC = false: the common case compiled without run-time feature checks (AC decode on, 8-bit
-// precision, no code-length histogram).  GENERIC = true: every option honoured at run time.
-template <bool GENERIC>
-__global__ void __launch_bounds__(LN_WARPS * 32, 6) k_huff_lane(DevBatch b)
+// precision).  GENERIC = true: DC-only mode and 12-bit precision honoured at run time.
+// HISTO: also count code lengths per (class, table) (CimgDecode::m_anDhtHisto, ImgDecode.cpp:1217).
+template <bool GENERIC, bool HISTO>
+__global__ void __launch_bounds__(LN_WARPS * 32, 3) k_huff_lane(DevBatch b)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    LaneShared& sh = *reinterpret_cast<LaneShared*>(smem_raw);
+    LaneHdr& sh = *reinterpret_cast<LaneHdr*>(smem_raw);
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint8_t* const myrows = sh.rows[wid];
+    const uint32_t nlut = b.lane_nlut;
+    uint8_t* const rows0 = smem_raw + sizeof(LaneHdr);
+    uint16_t* const lutb = reinterpret_cast<uint16_t*>(rows0 + LN_WARPS * 32 * ROW_PITCH);
+    uint16_t* const l2b = lutb + nlut * JS_LUT_SIZE;
+    uint32_t* const myhw = reinterpret_cast<uint32_t*>(l2b + nlut * JS_LANE_L2S) + (HISTO ? wid * 16 * 32 : 0);
+    uint8_t* const myrows = rows0 + wid * 32 * ROW_PITCH;
     uint8_t* const myrow = myrows + lane * ROW_PITCH;
     for (uint32_t i = lane; i < 32 * ROW_PITCH / 4; i += 32) reinterpret_cast<uint32_t*>(myrows)[i] = 0;
-    uint8_t* const myhb = sh.hb[wid];
-    for (uint32_t i = lane; i < 2 * 16 * 32 / 4; i += 32) reinterpret_cast<uint32_t*>(myhb)[i] = 0;
+    if (HISTO) for (uint32_t i = lane; i < 16 * 32; i += 32) myhw[i] = 0;
     const bool want_ac = GENERIC ? (b.decode_ac != 0) : true;
-    const bool want_histo = GENERIC ? (b.want_histo != 0) : false;
-    uint32_t cur_img = 0xffffffffu;
+    const bool l2s = b.lane_l2_smem != 0;
+    uint32_t cur_img = 0xffffffffu, cur_sig = 0xffffffffu, cur_set = 0xffffffffu;
     for (uint32_t it = blockIdx.x; it < b.nlitems; it += gridDim.x) {
         const uint2 item = b.litems[it];                      // (image, first interval); JS_LANE_SEGS intervals per item
         const DevImage& gim = b.img[item.x];
         const DevTableSet* ts = b.tables + gim.table_set;
         if (item.x != cur_img) {
             __syncthreads();
-            if (GENERIC && cur_img != 0xffffffffu && want_histo) { flush_histo(b, cur_img, sh.histo); __syncthreads(); }
-            if (GENERIC) for (uint32_t i = threadIdx.x; i < 6 * 17; i += blockDim.x) (&sh.histo[0][0])[i] = 0;
-            stage_tables(sh.t, gim, ts);
+            if (HISTO && cur_img != 0xffffffffu) { flush_histo(b, cur_img, sh.histo); __syncthreads(); }
+            if (HISTO) for (uint32_t i = threadIdx.x; i < 6 * 17; i += blockDim.x) (&sh.histo[0][0])[i] = 0;
+            if (gim.tab_sig != cur_sig || gim.table_set != cur_set) {   // a different table selection: restage
+                if (threadIdx.x == 0) {
+                    uint32_t n = 0;
+                    for (uint32_t c = 0; c < gim.ns; c++) for (uint32_t cls = 0; cls < 2; cls++) {
+                        const uint32_t slot = cls ? gim.slot_ac[c] : gim.slot_dc[c];
+                        uint32_t j = 0;
+                        while (j < n && sh.lslot[j] != slot) j++;
+                        if (j == n) sh.lslot[n++] = slot;
+                        sh.li[c * 2 + cls] = j;
+                    }
+                    sh.nl = n;
+                }
+                __syncthreads();
+                const uint32_t nl = sh.nl;
+                for (uint32_t j = 0; j < nl; j++) {
+                    const uint32_t slot = sh.lslot[j];
+                    const uint4* s0 = reinterpret_cast<const uint4*>(ts->lut[slot]);
+                    uint4* d0 = reinterpret_cast<uint4*>(lutb + j * JS_LUT_SIZE);
+                    for (uint32_t i = threadIdx.x; i < JS_LUT_SIZE * 2 / 16; i += blockDim.x) d0[i] = __ldg(s0 + i);
+                    if (l2s) {
+                        const uint4* s1 = reinterpret_cast<const uint4*>(ts->lut2[slot]);
+                        uint4* d1 = reinterpret_cast<uint4*>(l2b + j * JS_LANE_L2S);
+                        const uint32_t used = ts->lut2_used[slot];          // <= JS_LANE_L2S (checked at batch_begin)
+                        for (uint32_t i = threadIdx.x; i < used * 2 / 16; i += blockDim.x) d1[i] = __ldg(s1 + i);
+                    }
+                }
+                for (uint32_t c = 0; c < gim.ns; c++)
+                    for (uint32_t i = threadIdx.x; i < 80; i += blockDim.x) sh.qz[c][i] = (i < 64) ? ts->qz[gim.dqt[c]][i] : ((64u + (i & 7)) << 16);
+                cur_sig = gim.tab_sig; cur_set = gim.table_set;
+            }
             cur_img = item.x;
             __syncthreads();
         }
@@ -385,9 +428,11 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 6) k_huff_lane(DevBatch b)
             if (mlive) b.mcu_bitpos[gim.mcu_off + m0 + mi] = s.consumed();
             #pragma unroll 1
             for (uint32_t c = 0; c < ns; c++) {
-                const uint16_t* lut_dc = sh.t.lut[c * 2];
-                const uint16_t* lut_ac = sh.t.lut[c * 2 + 1];
-                const uint32_t* qz = sh.t.qz[c];
+                const uint16_t* lut_dc = lutb + sh.li[c * 2] * JS_LUT_SIZE;
+                const uint16_t* lut_ac = lutb + sh.li[c * 2 + 1] * JS_LUT_SIZE;
+                const uint16_t* l2_dc = l2b + sh.li[c * 2] * JS_LANE_L2S;
+                const uint16_t* l2_ac = l2b + sh.li[c * 2 + 1] * JS_LANE_L2S;
+                const uint32_t* qz = sh.qz[c];
                 const uint32_t nh = gim.H[c], nv = gim.V[c], cw = gim.cw[c];
                 const uint32_t ehc = gim.eh[c], evc = gim.ev[c], blk_xmax = gim.blk_xmax, mcu_ymax = gim.mcu_ymax;
                 int16_t* const blkmap = ((c == 0) ? b.blk_y : (c == 1) ? b.blk_cb : b.blk_cr) + gim.blk_off;
@@ -400,11 +445,11 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 6) k_huff_lane(DevBatch b)
                         // ---- DC symbol ----
                         if (s.nb <= 32) s.refill();
                         uint32_t e = lut_dc[s.hi >> (32 - JS_LUT_BITS)];
-                        if (e == 0 || (e & 0x8000)) e = huff_level2(ts, gim.slot_dc[c], e, s.hi);
+                        if ((int)(short)e < 0) e = l2s ? l2_dc[(e & 0x7FFF) + ((s.hi >> 16) & ((1u << JS_LUT2_BITS) - 1))] : huff_level2(ts, gim.slot_dc[c], e, s.hi);
                         if (e == 0) { status |= 1; active = false; }
                         else {
                             const uint32_t len = e >> 8, run = (e >> 4) & 15, size = e & 15;
-                            if (GENERIC && want_histo) myhb[(16 + len - 1) * 32 + lane]++;
+                            if (HISTO) atomicAdd(&sh.histo[c * 2][len], 1u);
                             s.consume(len);
                             if (s.nb <= 32) s.refill();          // a 16-bit code + 16 value bits can exceed what is left
                             const uint32_t t = s.hi;
@@ -426,9 +471,9 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 6) k_huff_lane(DevBatch b)
                         if (pos < 64) {
                             if (s.nb <= 32) s.refill();
                             uint32_t e = lut_ac[s.hi >> (32 - JS_LUT_BITS)];
-                            if (e == 0 || (e & 0x8000)) e = huff_level2(ts, gim.slot_ac[c], e, s.hi);
+                            if ((int)(short)e < 0) e = l2s ? l2_ac[(e & 0x7FFF) + ((s.hi >> 16) & ((1u << JS_LUT2_BITS) - 1))] : huff_level2(ts, gim.slot_ac[c], e, s.hi);
                             const uint32_t len = e >> 8, size = e & 15, run = (e >> 4) & 15;
-                            if (GENERIC && want_histo && e) myhb[(len - 1) * 32 + lane]++;
+                            if (HISTO && e) atomicAdd(&myhw[(len - 1) * 32 + lane], 1u);
                             // value bits follow the code: take them from the window before consuming both at once
                             const uint32_t t = __funnelshift_l(s.lo, s.hi, len);
                             uint32_t v; asm("shr.u32 %0, %1, %2;" : "=r"(v) : "r"(t), "r"(32u - size));   // 0 when size == 0 (shift clamps at 32)
@@ -452,17 +497,6 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 6) k_huff_lane(DevBatch b)
                         if ((h < ehc || mx == mcu_xmax - 1) && (v < evc || my == mcu_ymax - 1))
                             blkmap[(my * evc + v) * blk_xmax + (mx * ehc + h)] = (int16_t)dc;
                     }
-                    if (GENERIC && want_histo) {
-                        // lane l < 16 owns AC length l+1, lane l >= 16 owns DC length l-15: sum that bin over the 32 lanes
-                        __syncwarp();
-                        uint4* hp = reinterpret_cast<uint4*>(myhb + lane * 32);
-                        const uint4 h0 = hp[0], h1 = hp[1];
-                        uint32_t tot = 0;
-                        tot = __dp4a(h0.x, 0x01010101u, tot); tot = __dp4a(h0.y, 0x01010101u, tot); tot = __dp4a(h0.z, 0x01010101u, tot); tot = __dp4a(h0.w, 0x01010101u, tot);
-                        tot = __dp4a(h1.x, 0x01010101u, tot); tot = __dp4a(h1.y, 0x01010101u, tot); tot = __dp4a(h1.z, 0x01010101u, tot); tot = __dp4a(h1.w, 0x01010101u, tot);
-                        if (tot) { atomicAdd(&sh.histo[c * 2 + (lane < 16 ? 1 : 0)][(lane & 15) + 1], tot); hp[0] = make_uint4(0, 0, 0, 0); hp[1] = make_uint4(0, 0, 0, 0); }
-                        __syncwarp();
-                    }
                     // ---- cooperative write-out: 4 rows per step, 16 bytes per lane, then re-zero ----
                     const unsigned long long myaddr = active ? (unsigned long long)((gim.coef_row[c] + (size_t)(my * nv + v) * cw + (mx * nh + h)) * 128) : ~0ull;
                     __syncwarp();
@@ -478,6 +512,17 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 6) k_huff_lane(DevBatch b)
                     __syncwarp();
                 }
                 if (c == 0) dc0 = dc; else if (c == 1) dc1 = dc; else dc2 = dc;
+                if (HISTO) {
+                    // lane l sums AC length (l & 15) + 1 over lanes [16 * (l >> 4), +16); rotated so that the 32 lanes hit 32 banks
+                    __syncwarp();
+                    uint32_t* hp = myhw + (lane & 15) * 32 + (lane >> 4) * 16;
+                    uint32_t tot = 0;
+                    #pragma unroll
+                    for (int k2 = 0; k2 < 16; k2++) { const uint32_t j = (k2 + lane) & 15; tot += hp[j]; hp[j] = 0; }
+                    tot += __shfl_xor_sync(FULL, tot, 16);
+                    if (lane < 16 && tot) atomicAdd(&sh.histo[c * 2 + 1][lane + 1], tot);
+                    __syncwarp();
+                }
             }
             if (++mx == mcu_xmax) { mx = 0; my++; }
         }
@@ -492,7 +537,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 6) k_huff_lane(DevBatch b)
         }
     }
     __syncthreads();
-    if (GENERIC && cur_img != 0xffffffffu && want_histo) flush_histo(b, cur_img, sh.histo);
+    if (HISTO && cur_img != 0xffffffffu) flush_histo(b, cur_img, sh.histo);
 }
 
 int js_launch_huffman_lane(const DevBatch& b, int sm_count, cudaStream_t s)
@@ -500,14 +545,22 @@ int js_launch_huffman_lane(const DevBatch& b, int sm_count, cudaStream_t s)
     if (b.nlitems == 0) return 0;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(k_huff_lane<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LaneShared));
-        cudaFuncSetAttribute(k_huff_lane<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LaneShared));
+        const int mx = (int)lane_smem_bytes(6, true);
+        cudaFuncSetAttribute(k_huff_lane<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(k_huff_lane<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(k_huff_lane<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(k_huff_lane<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         attr_set = true;
     }
-    uint32_t grid = (uint32_t)sm_count * 5;
+    const size_t smem = lane_smem_bytes(b.lane_nlut, b.want_histo != 0);
+    uint32_t grid = (uint32_t)sm_count * 3;
     if (grid > b.nlitems) grid = b.nlitems;
-    const bool generic = b.want_histo || !b.decode_ac || b.any_p12;
-    if (generic) k_huff_lane<true><<<grid, LN_WARPS * 32, sizeof(LaneShared), s>>>(b);
-    else k_huff_lane<false><<<grid, LN_WARPS * 32, sizeof(LaneShared), s>>>(b);
+    const bool generic = !b.decode_ac || b.any_p12;
+    const dim3 blk(LN_WARPS * 32);
+    if (b.want_histo) {
+        if (generic) k_huff_lane<true, true><<<grid, blk, smem, s>>>(b); else k_huff_lane<false, true><<<grid, blk, smem, s>>>(b);
+    } else {
+        if (generic) k_huff_lane<true, false><<<grid, blk, smem, s>>>(b); else k_huff_lane<false, false><<<grid, blk, smem, s>>>(b);
+    }
     return 1;
 }

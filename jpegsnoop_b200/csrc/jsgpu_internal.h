@@ -21,6 +21,7 @@ struct DevTableSet {
     uint16_t lut[JS_NSLOT][JS_LUT_SIZE];
     uint16_t lut2[JS_NSLOT][JS_LUT2_SIZE];
     uint32_t lut2_overflow[JS_NSLOT];        // 1: second level did not fit -> in-order entry search for 0x8000 prefixes
+    uint32_t lut2_used[JS_NSLOT];            // second-level entries in use (a multiple of 1 << JS_LUT2_BITS)
     uint32_t ent_bits[JS_NSLOT][JS_MAX_CODES];   // left-justified code bits, in SetDhtEntry order
     uint8_t  ent_len [JS_NSLOT][JS_MAX_CODES];
     uint8_t  ent_sym [JS_NSLOT][JS_MAX_CODES];
@@ -40,6 +41,7 @@ struct DevImage {
     uint32_t bpm;                   // blocks per MCU
     uint32_t H[3], V[3], eh[3], ev[3];
     uint32_t slot_dc[3], slot_ac[3];// LUT slot per component
+    uint32_t tab_sig;               // ns, slots and DQT selectors packed: equal (table_set, tab_sig) <=> same staged decode tables
     uint32_t dqt[3];
     uint32_t table_set;
     uint32_t file_pos;              // file offset of scan_off
@@ -98,6 +100,8 @@ struct DevBatch {
     uint32_t*          img_status;  // [nimg]
     // options
     int                decode_ac, want_histo, idct_mode;
+    uint32_t           lane_nlut;            // lane Huffman kernel: most distinct (class,Th) tables any image uses (<= 6)
+    int                lane_l2_smem;         // ... and every used table's second level fits JS_LANE_L2S entries
     int                any_p12;              // some image has sample precision > 8 (ReadScanVal's divide, ID:1234-1238)
     int                blkdc_by_gather;      // 1: block-DC maps by the gather kernel (simple IDCT path), 0: written by k_idct_tile
     int                stuff_overflow_possible;
@@ -106,7 +110,8 @@ struct DevBatch {
 };
 
 #define JS_HUFF_WARPS 4              // warps (= restart intervals in flight) per Huffman CTA, warp kernel
-#define JS_LANE_SEGS  128            // restart intervals per CTA pass, lane kernel (4 warps x 32 lanes)
+#define JS_LANE_SEGS  256            // restart intervals per CTA pass, lane kernel (8 warps x 32 lanes)
+#define JS_LANE_L2S   512            // second-level entries per table the lane kernel stages in shared memory
 
 // launchers (jsgpu_kernels.cu) — each returns the number of kernels it enqueued
 int js_launch_marker_scan(const DevBatch& b, uint64_t max_scan_len, cudaStream_t s);
