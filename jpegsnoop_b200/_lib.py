@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libjsgpu.so")
+LIB_PATH = os.environ.get("JSGPU_LIB") or os.path.join(HERE, "libjsgpu.so")   # JSGPU_LIB: kernel-variant experiments only
 
 MAX_DHT_CODES = 260
 

@@ -22,7 +22,10 @@
 #include "build/idct_baked.h"
 #include <cstring>
 
-#define IDCT_THREADS 128
+#define IDCT_THREADS 96        // 3 warps: one 32-block group each per pass over a tile
+#ifndef IDCT_MIN_CTAS
+#define IDCT_MIN_CTAS 5
+#endif
 
 // The quadrant table as kernel constants: every lane multiplies by the SAME entry, so it can be a
 // constant-bank operand of the IMAD itself (no load instruction, no shared-memory bandwidth).
@@ -50,7 +53,7 @@ __device__ __forceinline__ uint32_t ycc_to_bgra(int py, int pcb, int pcr, uint32
 // TAB: where the quadrant table comes from — 0 = shared memory (broadcast LDS.128), 1 = constant bank (LDCU),
 // 2 = baked into the instruction stream as immediates (valid only when the host table equals the build-time copy)
 template <int TAB, int EHS>
-__global__ void __launch_bounds__(IDCT_THREADS, 4) k_idct_tile(DevBatch b, const IdctSym* __restrict__ sym, const ColorTabs* __restrict__ ctab,
+__global__ void __launch_bounds__(IDCT_THREADS, IDCT_MIN_CTAS) k_idct_tile(DevBatch b, const IdctSym* __restrict__ sym, const ColorTabs* __restrict__ ctab,
                                                                 uint32_t tile_first, uint32_t tile_count)
 {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -114,10 +117,9 @@ __global__ void __launch_bounds__(IDCT_THREADS, 4) k_idct_tile(DevBatch b, const
             for (int p = 0; p < 4; p++)
                 #pragma unroll
                 for (int q = 0; q < 16; q++) acc[p][q] = 0;
-            if (TAB == 2) {
 #define JS_COEF(n) (((n) & 1) ? ((int)cw[(n) >> 1] >> 16) : (int)(short)(cw[(n) >> 1] & 0xFFFF))
+            if (TAB == 2) {
                 JS_BAKED_MACS(acc, JS_COEF)                       // 63 x 16 IMADs with immediate operands
-#undef JS_COEF
             } else {
                 #pragma unroll
                 for (int n = 1; n < 64; n++) {
@@ -133,7 +135,7 @@ __global__ void __launch_bounds__(IDCT_THREADS, 4) k_idct_tile(DevBatch b, const
             }
             // corrections: coefficients at the (<=4) positions whose table entries are not mirror-symmetric
             int cj[4] = {0, 0, 0, 0};
-            if (valid) {
+            if (TAB != 2 && valid) {
                 const int16_t* r16 = b.coef + row * 64;
                 #pragma unroll
                 for (int j = 0; j < 4; j++) if (j < ncorr) cj[j] = r16[T.corr_pos[j]];
@@ -149,7 +151,12 @@ __global__ void __launch_bounds__(IDCT_THREADS, 4) k_idct_tile(DevBatch b, const
                     const int a00 = acc[0][q], a01 = acc[1][q], a10 = acc[2][q], a11 = acc[3][q];
                     const int A = a00 + a01, B = a00 - a01, C2 = a10 + a11, D = a10 - a11;
                     int s0 = A + C2, s1 = B + D, s2 = A - C2, s3 = B - D;     // (y,x) (y,7-x) (7-y,x) (7-y,7-x)
-                    if (ncorr > 0) {
+                    if (TAB == 2) {         // the baked table's asymmetric entries, as immediates (a few +-coefficient adds)
+                        int t0, t1, t2, t3;
+                        JS_BAKED_CORR_TERM(y * 8 + x, JS_COEF, t0) JS_BAKED_CORR_TERM(y * 8 + 7 - x, JS_COEF, t1)
+                        JS_BAKED_CORR_TERM((7 - y) * 8 + x, JS_COEF, t2) JS_BAKED_CORR_TERM((7 - y) * 8 + 7 - x, JS_COEF, t3)
+                        s0 += t0; s1 += t1; s2 += t2; s3 += t3;
+                    } else if (ncorr > 0) {
                         const int4 d0 = T.corrT[y * 8 + x], d1 = T.corrT[y * 8 + 7 - x], d2 = T.corrT[(7 - y) * 8 + x], d3 = T.corrT[(7 - y) * 8 + 7 - x];
                         s0 += d0.x * cj[0] + d0.y * cj[1] + d0.z * cj[2] + d0.w * cj[3];
                         s1 += d1.x * cj[0] + d1.y * cj[1] + d1.z * cj[2] + d1.w * cj[3];
@@ -164,6 +171,7 @@ __global__ void __launch_bounds__(IDCT_THREADS, 4) k_idct_tile(DevBatch b, const
                 }
             }
         }
+#undef JS_COEF
         __syncthreads();
         // ---------------- phase 2: 8 pixels x (chroma row group) per thread, vector stores ----------------
         {
@@ -247,13 +255,13 @@ static int launch_tab(const DevBatch& b, const IdctSym* sym, const ColorTabs* ct
     }
     // one warp per 32-block group of a tile, at most 4 warps (larger tiles loop)
     uint32_t groups = (b.tile_plane_bytes / 128 + 31) / 32;
-    uint32_t threads = 32 * (groups < 1 ? 1 : groups > 4 ? 4 : groups);
+    uint32_t threads = 32 * (groups < 1 ? 1 : groups > IDCT_THREADS / 32 ? IDCT_THREADS / 32 : groups);
     const size_t smem = sizeof(Idct2Tables) + (size_t)b.tile_plane_bytes;
     int n = 0;
     for (int cls = 0; cls < 3; cls++) {
         const uint32_t cnt = b.tcls_count[cls];
         if (!cnt) continue;
-        uint32_t grid = (uint32_t)sm_count * (threads <= 96 ? 5 : 4);
+        uint32_t grid = (uint32_t)sm_count * IDCT_MIN_CTAS;
         if (grid > cnt) grid = cnt;
         if (cls == 0) k_idct_tile<TAB, 0><<<grid, threads, smem, s>>>(b, sym, ctab, b.tcls_first[cls], cnt);
         else if (cls == 1) k_idct_tile<TAB, 1><<<grid, threads, smem, s>>>(b, sym, ctab, b.tcls_first[cls], cnt);
