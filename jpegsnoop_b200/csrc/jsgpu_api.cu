@@ -405,7 +405,7 @@ int jsgpu_batch_begin(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, 
     CK(ctx->d_litems.reserve(sizeof(uint2) * std::max<size_t>(litems.size(), 1)));
     CK(ctx->d_tiles.reserve(sizeof(uint4) * std::max<size_t>(tiles.size(), 1)));
     CK(ctx->d_seg64.reserve(8 * (size_t)seg + 16));
-    CK(ctx->d_seg.reserve(sizeof(uint32_t) * ((6 + JS_STUFF_LIST) * (size_t)seg + 2 * (size_t)n + 16)));
+    CK(ctx->d_seg.reserve(sizeof(uint32_t) * ((7 + JS_STUFF_LIST) * (size_t)seg + 2 * (size_t)n + 16)));
     CK(ctx->d_coef.reserve(rows * 128 + 4096));      // + slack: a TMA box may start at the last rows and spans 8
     CK(ctx->d_mcubits.reserve(mcu * 4 + 16));
     CK(ctx->d_pix.reserve(pix * 2 * 3 + 64));
@@ -428,7 +428,7 @@ int jsgpu_batch_begin(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, 
     b.seg_start = sp; b.seg_end = sp + seg; b.seg_endbits = sp + 2 * (size_t)seg; b.seg_status = sp + 3 * (size_t)seg;
     b.seg_ulen = sp + 4 * (size_t)seg;
     b.scan_end = sp + 5 * (size_t)seg; b.nseg_found = b.scan_end + n; b.nseg_total = seg;
-    b.seg_nstuff = b.nseg_found + n; b.seg_stuff = b.seg_nstuff + seg;
+    b.seg_nstuff = b.nseg_found + n; b.seg_stuff = b.seg_nstuff + seg; b.ovf_list = b.seg_stuff + (size_t)JS_STUFF_LIST * seg;
     b.seg_uoff = (unsigned long long*)ctx->d_seg64.p; b.ubits = (uint8_t*)ctx->d_ubits.p;
     b.litems = (const uint2*)ctx->d_litems.p; b.nlitems = (uint32_t)litems.size();
     b.tiles = (const uint4*)ctx->d_tiles.p; b.ntiles = (uint32_t)tiles.size(); b.tile_plane_bytes = plane_bytes;
@@ -441,7 +441,7 @@ int jsgpu_batch_begin(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, 
     b.blk_y = (int16_t*)ctx->d_blk.p; b.blk_cb = b.blk_y + blk; b.blk_cr = b.blk_cb + blk;
     b.mcu_map = (uint32_t*)ctx->d_mcumap.p;
     b.histo = (uint32_t*)ctx->d_histo.p; b.stats = (int32_t*)ctx->d_stats.p;
-    b.bright_key = (unsigned long long*)ctx->d_misc.p; b.sum_y = b.bright_key + n; b.img_status = (uint32_t*)(b.sum_y + n);
+    b.bright_key = (unsigned long long*)ctx->d_misc.p; b.sum_y = b.bright_key + n; b.img_status = (uint32_t*)(b.sum_y + n); b.ovf_count = b.img_status + n;
     ctx->planned = true;
     return JSGPU_OK;
 }
@@ -528,7 +528,8 @@ int jsgpu_batch_decode(jsgpu_ctx* ctx)
     DevBatch& b = ctx->batch;
     b.decode_ac = ctx->opt.decode_ac; b.want_histo = ctx->opt.want_histo; b.idct_mode = ctx->opt.idct_mode;
     b.any_p12 = 0; for (const DevImage& im : ctx->himg) if (im.valid && im.precision > 8) b.any_p12 = 1;
-    b.lane_nlut = 1; b.lane_l2_smem = 1;
+    b.lane_nlut = 1; b.lane_l2_smem = 1; b.max_nseg = 0;
+    for (const DevImage& im : ctx->himg) if (im.valid) b.max_nseg = std::max(b.max_nseg, im.nseg);
     for (const DevImage& im : ctx->himg) if (im.valid) {
         uint32_t seen = 0, nl = 0;
         for (uint32_t c = 0; c < im.ns; c++) for (int cls = 0; cls < 2; cls++) {
@@ -543,7 +544,7 @@ int jsgpu_batch_decode(jsgpu_ctx* ctx)
     // clear accumulators (the reference memsets its maps: ImgDecode.cpp:2900,2924-2928,2965)
     CK(cudaMemsetAsync(b.histo, 0, (size_t)b.nimg * 2 * 4 * 17 * 4, s));
     CK(cudaMemsetAsync(b.stats, 0, (size_t)b.nimg * 16 * 4, s));
-    CK(cudaMemsetAsync(b.bright_key, 0, (size_t)b.nimg * (8 + 8 + 4), s));
+    CK(cudaMemsetAsync(b.bright_key, 0, (size_t)b.nimg * (8 + 8 + 4) + 4, s));      // + ovf_count
     CK(cudaMemsetAsync(b.mcu_map, 0, ctx->mcu_total * 4, s));
     CK(cudaMemsetAsync(b.blk_y, 0, ctx->blk_total * 2 * 3, s));
     if (ctx->opt.device_markers) launches += js_launch_marker_scan(b, ctx->max_scan_len, s);

@@ -23,14 +23,12 @@
 __global__ void __launch_bounds__(128) k_unstuff(DevBatch b)
 {
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (gw >= b.nseg_total) return;
-    uint32_t lo = 0, hi = b.nimg - 1;
-    while (lo < hi) { uint32_t mid = (lo + hi + 1) >> 1; if (b.img[mid].seg_first <= gw) lo = mid; else hi = mid - 1; }
-    const DevImage& im = b.img[lo];
-    if (!im.valid) return;
-    const uint32_t k = gw - im.seg_first;
-    if (k >= im.nseg) return;
+    for (uint32_t ii = blockIdx.y; ii < b.nimg; ii += gridDim.y) {            // grid.y = image (strided beyond 65535 images)
+    const DevImage& im = b.img[ii];
+    if (!im.valid) continue;
+    const uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (k >= im.nseg) continue;
+    const uint32_t gw = im.seg_first + k;
     const uint32_t s0 = b.seg_start[gw], len = b.seg_end[gw] - s0;
     const uint8_t* seg = b.bits + im.scan_off + s0;
     // destination: 16-byte aligned, never overlapping the neighbours
@@ -85,13 +83,18 @@ __global__ void __launch_bounds__(128) k_unstuff(DevBatch b)
     }
     // pad with 1-bits (the JPEG pad value; no valid code is all ones) so readers can over-fetch
     if (lane < 16) dst[wr + lane] = 0xFF;      // 16 bytes: the most a reader can over-fetch, and what the 32-byte slack allows
-    if (lane == 0) { b.seg_ulen[gw] = wr; b.seg_uoff[gw] = dst0; b.seg_nstuff[gw] = nstuff; }
+    if (lane == 0) {
+        b.seg_ulen[gw] = wr; b.seg_uoff[gw] = dst0; b.seg_nstuff[gw] = nstuff;
+        if (nstuff > JS_STUFF_LIST) b.ovf_list[atomicAdd(b.ovf_count, 1u)] = gw;     // rare: the MCU map of this interval needs the raw re-walk
+    }
+    }
 }
 
 int js_launch_unstuff(const DevBatch& b, cudaStream_t s)
 {
-    if (b.nseg_total == 0) return 0;
-    k_unstuff<<<(b.nseg_total + 3) / 4, 128, 0, s>>>(b);
+    if (b.nseg_total == 0 || b.max_nseg == 0) return 0;
+    const dim3 grid((b.max_nseg + 3) / 4, b.nimg < 65535u ? b.nimg : 65535u);
+    k_unstuff<<<grid, 128, 0, s>>>(b);
     return 1;
 }
 
@@ -467,8 +470,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 3) k_huff_lane(DevBatch b)
                         }
                     }
                     // ---- AC symbols: every lane advances its own interval by one symbol per step ----
-                    while (__any_sync(FULL, pos < 64)) {
-                        if (pos < 64) {
+                    auto ac_step = [&]() {
+
                             if (s.nb <= 32) s.refill();
                             uint32_t e = lut_ac[s.hi >> (32 - JS_LUT_BITS)];
                             if ((int)(short)e < 0) e = l2s ? l2_ac[(e & 0x7FFF) + ((s.hi >> 16) & ((1u << JS_LUT2_BITS) - 1))] : huff_level2(ts, gim.slot_ac[c], e, s.hi);
@@ -486,7 +489,10 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 3) k_huff_lane(DevBatch b)
                             if (want_ac) *reinterpret_cast<uint16_t*>(myrow + (q >> 16) * 2) = (uint16_t)(val * (int)(q & 0xFFFF));
                             pos = ((e & 0xFF) == 0) ? 128u : kk + 1;                     // EOB ends the block (its dummy store hit slot >= 64 or rewrote 0*q)
                             if (e == 0) { status |= 1; pos = 128; }
-                        }
+                    };
+                    while (__any_sync(FULL, pos < 64)) {       // two symbols per vote: the second step is simply predicated off where the block ended
+                        if (pos < 64) ac_step();
+                        if (pos < 64) ac_step();
                     }
                     if (pos > 64 && pos < 128) status |= 4;
                     const uint32_t v = bi / nh, h = bi - v * nh;

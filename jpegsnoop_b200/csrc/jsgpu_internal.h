@@ -100,6 +100,9 @@ struct DevBatch {
     uint32_t*          img_status;  // [nimg]
     // options
     int                decode_ac, want_histo, idct_mode;
+    uint32_t           max_nseg;             // most restart intervals in one image of the batch
+    uint32_t*          ovf_count;            // number of intervals with more stuffed bytes than JS_STUFF_LIST ...
+    uint32_t*          ovf_list;             // ... and their segment indices (appended by k_unstuff, walked by k_finalize_mcumap)
     uint32_t           lane_nlut;            // lane Huffman kernel: most distinct (class,Th) tables any image uses (<= 6)
     int                lane_l2_smem;         // ... and every used table's second level fits JS_LANE_L2S entries
     int                any_p12;              // some image has sample precision > 8 (ReadScanVal's divide, ID:1234-1238)

@@ -15,6 +15,7 @@
 // colour math uses __fmul_rn/__fadd_rn/__fsub_rn/__fdiv_rn so no FMA contraction can happen.
 #include "jsgpu_internal.h"
 #include <cstdio>
+#include <algorithm>
 
 #define FULL 0xffffffffu
 
@@ -264,15 +265,15 @@ __global__ void k_finalize_stats(DevBatch b)
 __global__ void __launch_bounds__(128) k_finalize_mcumap(DevBatch b)
 {
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (gw >= b.nseg_total) return;
-    if (b.seg_nstuff[gw] <= JS_STUFF_LIST) return;          // k_finalize_mcumap_fast did this interval
+    const uint32_t novf = *b.ovf_count;                     // intervals k_finalize_mcumap_fast could not do (list from k_unstuff)
+    for (uint32_t oi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; oi < novf; oi += (gridDim.x * blockDim.x) >> 5) {
+    const uint32_t gw = b.ovf_list[oi];
     uint32_t lo = 0, hi = b.nimg - 1;                       // image owning segment gw
     while (lo < hi) { uint32_t mid = (lo + hi + 1) >> 1; if (b.img[mid].seg_first <= gw) lo = mid; else hi = mid - 1; }
     const DevImage& im = b.img[lo];
-    if (!im.valid) return;
+    if (!im.valid) continue;
     const uint32_t k = gw - im.seg_first;
-    if (k >= im.nseg) return;
+    if (k >= im.nseg) continue;
     const uint32_t s0 = b.seg_start[gw], len = b.seg_end[gw] - s0;
     const uint8_t* seg = b.bits + im.scan_off + s0;
     const uint32_t m0 = k * im.ri, m1 = min(m0 + im.ri, im.nmcu);
@@ -309,6 +310,7 @@ __global__ void __launch_bounds__(128) k_finalize_mcumap(DevBatch b)
     while (tcur < nt) {
         if (lane == 0) b.mcu_map[im.mcu_off + tmcu(tcur)] = (len ? ((im.file_pos + s0 + last_kept) << 4) : 0u);
         tcur++;
+    }
     }
 }
 
@@ -350,7 +352,7 @@ int js_launch_finalize(const DevBatch& b, cudaStream_t s)
     if (b.mcu_map && b.nseg_total) {
         dim3 grid(32, b.nimg);
         k_finalize_mcumap_fast<<<grid, 256, 0, s>>>(b); n++;
-        if (b.stuff_overflow_possible) { k_finalize_mcumap<<<(b.nseg_total + 3) / 4, 128, 0, s>>>(b); n++; }
+        if (b.stuff_overflow_possible) { k_finalize_mcumap<<<std::min<uint32_t>((b.nseg_total + 3) / 4, 148 * 8), 128, 0, s>>>(b); n++; }
     }
     return n;
 }
