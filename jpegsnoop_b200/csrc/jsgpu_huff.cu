@@ -60,10 +60,10 @@ __global__ void __launch_bounds__(128) k_unstuff(DevBatch b)
         const uint32_t pre = __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
         const uint32_t tot = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
         uint32_t o = wr + pre;
-        if (keep == 0x80808080u && (o & 3) == 0) *reinterpret_cast<uint32_t*>(dst + o) = word;   // common case: one aligned word store
+        if (keep == 0x80808080u && (o & 3) == 0) *reinterpret_cast<uint32_t*>(dst + o) = __byte_perm(word, 0, 0x0123);   // common case: one aligned word store
         else {
             #pragma unroll
-            for (int j = 0; j < 4; j++) if (keep >> (8 * j + 7) & 1) { dst[o] = (uint8_t)(word >> (8 * j)); o++; }
+            for (int j = 0; j < 4; j++) if (keep >> (8 * j + 7) & 1) { dst[o ^ 3] = (uint8_t)(word >> (8 * j)); o++; }
         }
         // record where bytes were dropped (for the MCU file map): unstuffed index of the preceding FF
         if (__ballot_sync(FULL, drop != 0)) {
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(128) k_unstuff(DevBatch b)
         prev_ff = ((__shfl_sync(FULL, word, 31) >> 24) == 0xFF) ? 1u : 0u;
     }
     // pad with 1-bits (the JPEG pad value; no valid code is all ones) so readers can over-fetch
-    if (lane < 16) dst[wr + lane] = 0xFF;      // 16 bytes: the most a reader can over-fetch, and what the 32-byte slack allows
+    if (lane < 16) dst[(wr + lane) ^ 3] = 0xFF;      // 16 bytes: the most a reader can over-fetch, and what the 32-byte slack allows
     if (lane == 0) {
         b.seg_ulen[gw] = wr; b.seg_uoff[gw] = dst0; b.seg_nstuff[gw] = nstuff;
         if (nstuff > JS_STUFF_LIST) b.ovf_list[atomicAdd(b.ovf_count, 1u)] = gw;     // rare: the MCU map of this interval needs the raw re-walk
@@ -140,17 +140,18 @@ __device__ __forceinline__ uint32_t huff_level2(const DevTableSet* ts, uint32_t 
     return 0;     // no code has this prefix (the reference's search would fail too)
 }
 
-// Per-thread bit reader over an unstuffed, 4-byte aligned, 0xFF-padded interval.
+// Per-thread bit reader over an unstuffed, 4-byte aligned, 0xFF-padded interval (k_unstuff stores it as
+// big-endian 32-bit words, so a loaded word is already in bit order).
 struct Bits {
     unsigned long long w; int nb; const uint32_t* p; uint32_t words; uint32_t nx;
     __device__ __forceinline__ void init(const uint8_t* base) {
         p = reinterpret_cast<const uint32_t*>(base);
-        uint32_t a = __byte_perm(__ldg(p), 0, 0x0123), c = __byte_perm(__ldg(p + 1), 0, 0x0123);
+        uint32_t a = __ldg(p), c = __ldg(p + 1);
         nx = __ldg(p + 2);                                 // always one word ahead: the load latency hides behind ~6 symbols
         w = ((unsigned long long)a << 32) | c; nb = 64; p += 3; words = 2;
     }
     __device__ __forceinline__ void refill() {          // call when nb <= 32
-        uint32_t x = __byte_perm(nx, 0, 0x0123);
+        uint32_t x = nx;
         nx = __ldg(p);
         w |= (unsigned long long)x << (32 - nb);
         nb += 32; p++; words++;
@@ -313,7 +314,7 @@ int js_launch_huffman_warp(const DevBatch& b, int sm_count, cudaStream_t s)
 #define LN_WARPS   (JS_LANE_SEGS / 32)
 #define ROW_PITCH  144                      // bytes per lane row: 64 coefficients + 8 dummy slots; 16-byte aligned
 // Dynamic shared memory of the lane kernel:
-//   LaneHdr | coefficient rows [LN_WARPS][32][ROW_PITCH] | lut [nl][JS_LUT_SIZE] | lut2 [nl][JS_LANE_L2S] | (HISTO) hw [LN_WARPS][16][32]
+//   LaneHdr | coefficient rows [LN_WARPS][32][ROW_PITCH] | lut [nl][JS_LUT_SIZE] | lut2 [nl][JS_LANE_L2S] | (HISTO) hw [LN_WARPS][17][32]
 // nl = DevBatch::lane_nlut: the distinct (class,Th) tables an image selects are staged once each (Cb and Cr
 // normally share theirs).  hw: AC code-length counters, one 32-bit word per (length 1..16, lane); a lane only
 // touches its own column, so the result-less shared atomic is conflict-free and nothing waits on it; the
@@ -327,7 +328,7 @@ struct LaneHdr {
 };
 static inline size_t lane_smem_bytes(uint32_t nl, bool histo)
 {
-    return sizeof(LaneHdr) + (size_t)LN_WARPS * 32 * ROW_PITCH + (size_t)nl * (JS_LUT_SIZE + JS_LANE_L2S) * 2 + (histo ? (size_t)LN_WARPS * 16 * 32 * 4 : 0);
+    return sizeof(LaneHdr) + (size_t)LN_WARPS * 32 * ROW_PITCH + (size_t)nl * (JS_LUT_SIZE + JS_LANE_L2S) * 2 + (histo ? (size_t)LN_WARPS * 17 * 32 * 4 : 0);
 }
 
 // Bit window as two 32-bit registers (hi = next 32 bits, lo = the 32 after), funnel-shift consume.
@@ -335,11 +336,11 @@ struct Win {
     uint32_t hi, lo; int nb; uint32_t nx; uint32_t idx; const uint32_t* base;
     __device__ __forceinline__ void init(const uint8_t* b) {
         base = reinterpret_cast<const uint32_t*>(b);
-        hi = __byte_perm(__ldg(base), 0, 0x0123); lo = __byte_perm(__ldg(base + 1), 0, 0x0123);
+        hi = __ldg(base); lo = __ldg(base + 1);
         nx = __ldg(base + 2); idx = 3; nb = 64;
     }
     __device__ __forceinline__ void refill() {            // precondition: 6 <= nb <= 32
-        const uint32_t x = __byte_perm(nx, 0, 0x0123);
+        const uint32_t x = nx;
         nx = __ldg(base + idx); idx++;
         hi |= __funnelshift_rc(x, 0, nb);                  // x >> nb, 0 when nb == 32
         lo = x << (32 - nb);
@@ -362,13 +363,13 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 3) k_huff_lane(DevBatch b)
     uint8_t* const rows0 = smem_raw + sizeof(LaneHdr);
     uint16_t* const lutb = reinterpret_cast<uint16_t*>(rows0 + LN_WARPS * 32 * ROW_PITCH);
     uint16_t* const l2b = lutb + nlut * JS_LUT_SIZE;
-    uint32_t* const myhw = reinterpret_cast<uint32_t*>(l2b + nlut * JS_LANE_L2S) + (HISTO ? wid * 16 * 32 : 0);
+    uint32_t* const myhw = reinterpret_cast<uint32_t*>(l2b + nlut * JS_LANE_L2S) + (HISTO ? wid * 17 * 32 : 0);   // row 0 collects length 0 (= no code), never read
     uint8_t* const myrows = rows0 + wid * 32 * ROW_PITCH;
     uint8_t* const myrow = myrows + lane * ROW_PITCH;
     for (uint32_t i = lane; i < 32 * ROW_PITCH / 4; i += 32) reinterpret_cast<uint32_t*>(myrows)[i] = 0;
-    if (HISTO) for (uint32_t i = lane; i < 16 * 32; i += 32) myhw[i] = 0;
+    if (HISTO) for (uint32_t i = lane; i < 17 * 32; i += 32) myhw[i] = 0;
+    uint32_t* const hwl = myhw + lane;
     const bool want_ac = GENERIC ? (b.decode_ac != 0) : true;
-    const bool l2s = b.lane_l2_smem != 0;
     uint32_t cur_img = 0xffffffffu, cur_sig = 0xffffffffu, cur_set = 0xffffffffu;
     for (uint32_t it = blockIdx.x; it < b.nlitems; it += gridDim.x) {
         const uint2 item = b.litems[it];                      // (image, first interval); JS_LANE_SEGS intervals per item
@@ -397,12 +398,10 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 3) k_huff_lane(DevBatch b)
                     const uint4* s0 = reinterpret_cast<const uint4*>(ts->lut[slot]);
                     uint4* d0 = reinterpret_cast<uint4*>(lutb + j * JS_LUT_SIZE);
                     for (uint32_t i = threadIdx.x; i < JS_LUT_SIZE * 2 / 16; i += blockDim.x) d0[i] = __ldg(s0 + i);
-                    if (l2s) {
-                        const uint4* s1 = reinterpret_cast<const uint4*>(ts->lut2[slot]);
-                        uint4* d1 = reinterpret_cast<uint4*>(l2b + j * JS_LANE_L2S);
-                        const uint32_t used = ts->lut2_used[slot];          // <= JS_LANE_L2S (checked at batch_begin)
-                        for (uint32_t i = threadIdx.x; i < used * 2 / 16; i += blockDim.x) d1[i] = __ldg(s1 + i);
-                    }
+                    const uint4* s1 = reinterpret_cast<const uint4*>(ts->lut2[slot]);
+                    uint4* d1 = reinterpret_cast<uint4*>(l2b + j * JS_LANE_L2S);
+                    const uint32_t used = ts->lut2_used[slot];              // <= JS_LANE_L2S: the launcher refuses the batch otherwise
+                    for (uint32_t i = threadIdx.x; i < used * 2 / 16; i += blockDim.x) d1[i] = __ldg(s1 + i);
                 }
                 for (uint32_t c = 0; c < gim.ns; c++)
                     for (uint32_t i = threadIdx.x; i < 80; i += blockDim.x) sh.qz[c][i] = (i < 64) ? ts->qz[gim.dqt[c]][i] : ((64u + (i & 7)) << 16);
@@ -448,7 +447,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 3) k_huff_lane(DevBatch b)
                         // ---- DC symbol ----
                         if (s.nb <= 32) s.refill();
                         uint32_t e = lut_dc[s.hi >> (32 - JS_LUT_BITS)];
-                        if ((int)(short)e < 0) e = l2s ? l2_dc[(e & 0x7FFF) + ((s.hi >> 16) & ((1u << JS_LUT2_BITS) - 1))] : huff_level2(ts, gim.slot_dc[c], e, s.hi);
+                        if ((int)(short)e < 0) e = l2_dc[(e & 0x7FFF) + ((s.hi >> 16) & ((1u << JS_LUT2_BITS) - 1))];
                         if (e == 0) { status |= 1; active = false; }
                         else {
                             const uint32_t len = e >> 8, run = (e >> 4) & 15, size = e & 15;
@@ -470,13 +469,15 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 3) k_huff_lane(DevBatch b)
                         }
                     }
                     // ---- AC symbols: every lane advances its own interval by one symbol per step ----
+                    uint32_t emin = 0xffffffffu;                 // an entry of 0 (no code has this prefix) also ends the block like an EOB
                     auto ac_step = [&]() {
 
                             if (s.nb <= 32) s.refill();
                             uint32_t e = lut_ac[s.hi >> (32 - JS_LUT_BITS)];
-                            if ((int)(short)e < 0) e = l2s ? l2_ac[(e & 0x7FFF) + ((s.hi >> 16) & ((1u << JS_LUT2_BITS) - 1))] : huff_level2(ts, gim.slot_ac[c], e, s.hi);
+                            if ((int)(short)e < 0) e = l2_ac[(e & 0x7FFF) + ((s.hi >> 16) & ((1u << JS_LUT2_BITS) - 1))];
                             const uint32_t len = e >> 8, size = e & 15, run = (e >> 4) & 15;
-                            if (HISTO && e) atomicAdd(&myhw[(len - 1) * 32 + lane], 1u);
+                            if (HISTO) atomicAdd(hwl + len * 32, 1u);
+                            emin = min(emin, e);
                             // value bits follow the code: take them from the window before consuming both at once
                             const uint32_t t = __funnelshift_l(s.lo, s.hi, len);
                             uint32_t v; asm("shr.u32 %0, %1, %2;" : "=r"(v) : "r"(t), "r"(32u - size));   // 0 when size == 0 (shift clamps at 32)
@@ -488,12 +489,12 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 3) k_huff_lane(DevBatch b)
                             const uint32_t q = qz[kk];                                   // kk <= 78; entries >= 64 point at dummy slots
                             if (want_ac) *reinterpret_cast<uint16_t*>(myrow + (q >> 16) * 2) = (uint16_t)(val * (int)(q & 0xFFFF));
                             pos = ((e & 0xFF) == 0) ? 128u : kk + 1;                     // EOB ends the block (its dummy store hit slot >= 64 or rewrote 0*q)
-                            if (e == 0) { status |= 1; pos = 128; }
                     };
                     while (__any_sync(FULL, pos < 64)) {       // two symbols per vote: the second step is simply predicated off where the block ended
                         if (pos < 64) ac_step();
                         if (pos < 64) ac_step();
                     }
+                    if (emin == 0) status |= 1;
                     if (pos > 64 && pos < 128) status |= 4;
                     const uint32_t v = bi / nh, h = bi - v * nh;
                     if (active) {
@@ -521,7 +522,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 3) k_huff_lane(DevBatch b)
                 if (HISTO) {
                     // lane l sums AC length (l & 15) + 1 over lanes [16 * (l >> 4), +16); rotated so that the 32 lanes hit 32 banks
                     __syncwarp();
-                    uint32_t* hp = myhw + (lane & 15) * 32 + (lane >> 4) * 16;
+                    uint32_t* hp = myhw + 32 + (lane & 15) * 32 + (lane >> 4) * 16;
                     uint32_t tot = 0;
                     #pragma unroll
                     for (int k2 = 0; k2 < 16; k2++) { const uint32_t j = (k2 + lane) & 15; tot += hp[j]; hp[j] = 0; }
@@ -549,6 +550,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 3) k_huff_lane(DevBatch b)
 int js_launch_huffman_lane(const DevBatch& b, int sm_count, cudaStream_t s)
 {
     if (b.nlitems == 0) return 0;
+    if (!b.lane_l2_smem) return js_launch_huffman_warp(b, sm_count, s);   // a second level too large to stage (pathological DHT): the warp kernel reads it from global memory
     static bool attr_set = false;
     if (!attr_set) {
         const int mx = (int)lane_smem_bytes(6, true);
