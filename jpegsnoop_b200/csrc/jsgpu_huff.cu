@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 3) k_huff_lane(DevBatch b)
     uint32_t* const hwl = myhw + lane;
     const bool want_ac = GENERIC ? (b.decode_ac != 0) : true;
     uint32_t cur_img = 0xffffffffu, cur_sig = 0xffffffffu, cur_set = 0xffffffffu;
-    for (uint32_t it = blockIdx.x; it < b.nlitems; it += gridDim.x) {
+    for (uint32_t it = blockIdx.x; it < b.nlitems; it += gridDim.x) {      // strided: images of different entropy spread over all CTAs
         const uint2 item = b.litems[it];                      // (image, first interval); JS_LANE_SEGS intervals per item
         const DevImage& gim = b.img[item.x];
         const DevTableSet* ts = b.tables + gim.table_set;

@@ -50,6 +50,22 @@ __device__ __forceinline__ uint32_t ycc_to_bgra(int py, int pcb, int pcr, uint32
     return bl | (g << 8) | (r << 16);
 }
 
+// Coefficient row of block `idx` (0..nblk-1: all Y blocks of the tile row-major, then Cb, then Cr) of a tile.
+__device__ __forceinline__ bool tile_block_row(const DevBatch& b, const uint4& tile, uint32_t idx, size_t& row)
+{
+    const DevImage& im = b.img[tile.x];
+    const uint32_t ns = im.ns, U = im.tile_mcus;
+    const uint32_t hu0 = im.H[0] * U, hu1 = (ns == 3) ? im.H[1] * U : 0, hu2 = (ns == 3) ? im.H[2] * U : 0;
+    const uint32_t cnt0 = hu0 * im.V[0], cnt1 = hu1 * im.V[1], cnt2 = hu2 * im.V[2];
+    uint32_t i = idx, c = 0;
+    if (i >= cnt0) { i -= cnt0; c = 1; if (i >= cnt1) { i -= cnt1; c = 2; } }
+    if (c >= ns) c = 0;
+    const uint32_t Hc = im.H[c], huc = (c == 0) ? hu0 : (c == 1) ? hu1 : hu2;
+    const uint32_t v = i / huc, col = i - v * huc;
+    row = im.coef_row[c] + (size_t)(tile.y * im.V[c] + v) * im.cw[c] + (tile.z * Hc + col);
+    return (idx < cnt0 + cnt1 + cnt2) && (col < tile.w * Hc);
+}
+
 // TAB: where the quadrant table comes from — 0 = shared memory (broadcast LDS.128), 1 = constant bank (LDCU),
 // 2 = baked into the instruction stream as immediates (valid only when the host table equals the build-time copy)
 template <int TAB, int EHS>
@@ -61,14 +77,32 @@ __global__ void __launch_bounds__(IDCT_THREADS, IDCT_MIN_CTAS) k_idct_tile(DevBa
     uint8_t* const planes = smem + sizeof(Idct2Tables);
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     // stage the decomposed table once per CTA
-    for (uint32_t i = tid; i < 64 * 4; i += blockDim.x) T.s4[i] = reinterpret_cast<const int4*>(sym->s4)[i];
-    for (uint32_t i = tid; i < 64; i += blockDim.x) T.corrT[i] = make_int4(sym->corr[0][i], sym->corr[1][i], sym->corr[2][i], sym->corr[3][i]);
+    if (TAB == 0) for (uint32_t i = tid; i < 64 * 4; i += blockDim.x) T.s4[i] = reinterpret_cast<const int4*>(sym->s4)[i];
+    if (TAB != 2) for (uint32_t i = tid; i < 64; i += blockDim.x) T.corrT[i] = make_int4(sym->corr[0][i], sym->corr[1][i], sym->corr[2][i], sym->corr[3][i]);
     if (tid == 0) { T.ncorr = sym->ncorr; for (int j = 0; j < 4; j++) T.corr_pos[j] = sym->corr_pos[j]; T.rb_ok = ctab->rb_ok; }
     for (uint32_t i = tid; i < 256; i += blockDim.x) { T.tr[i] = (int16_t)(ctab->tr[i] - 128); T.tb[i] = (int16_t)(ctab->tb[i] - 128); }
     __syncthreads();
     const int ncorr = T.ncorr;
 
-    for (uint32_t ti = blockIdx.x; ti < tile_count; ti += gridDim.x) {
+    // Register double buffer: the coefficient rows this warp's first block group needs for the NEXT tile are
+    // requested before phase 2 of the current tile, so phase 1 never waits on HBM.
+    // Each CTA walks a contiguous run of tiles (same image for hundreds of tiles: descriptor loads hit L1,
+    // coefficient rows and output rows advance sequentially).
+    const uint32_t t_begin = (uint32_t)(((unsigned long long)tile_count * blockIdx.x) / gridDim.x);
+    const uint32_t t_end = (uint32_t)(((unsigned long long)tile_count * (blockIdx.x + 1)) / gridDim.x);
+    uint4 nx4[8];
+    #pragma unroll
+    for (int k = 0; k < 8; k++) nx4[k] = make_uint4(0, 0, 0, 0);
+    if (t_begin < t_end) {
+        size_t row;
+        if (tile_block_row(b, b.tiles[tile_first + t_begin], wid * 32 + lane, row)) {
+            const uint4* rp = reinterpret_cast<const uint4*>(b.coef + row * 64);
+            #pragma unroll
+            for (int k = 0; k < 8; k++) nx4[k] = __ldg(rp + k);
+        }
+    }
+
+    for (uint32_t ti = t_begin; ti < t_end; ti++) {
         const uint4 tile = b.tiles[tile_first + ti];       // (image, mcu row, first mcu col, mcus in tile)
         const DevImage& im = b.img[tile.x];
         const uint32_t ns = im.ns, U = im.tile_mcus;
@@ -93,16 +127,11 @@ __global__ void __launch_bounds__(IDCT_THREADS, IDCT_MIN_CTAS) k_idct_tile(DevBa
             const uint32_t v = i / huc, col = i - v * huc;
             const bool valid = (g * 32 + lane < nblk) && (col < nmt * Hc);
             const size_t row = im.coef_row[c] + (size_t)(trow * im.V[c] + v) * im.cw[c] + (mcol0 * Hc + col);
-            // pull this lane's row of the CTA's NEXT tile towards L2 while the current one is being computed
-            if (ti + gridDim.x < tile_count) {
-                const uint4 nt = b.tiles[tile_first + ti + gridDim.x];
-                if (nt.x == tile.x && col < nt.w * Hc) {
-                    const size_t nrow = im.coef_row[c] + (size_t)(nt.y * im.V[c] + v) * im.cw[c] + (nt.z * Hc + col);
-                    asm volatile("prefetch.global.L2 [%0];" :: "l"(b.coef + nrow * 64));
-                }
-            }
             uint4 cw4[8];
-            if (valid) {
+            if (g == wid) {                                        // prefetched while the previous tile was in phase 2
+                #pragma unroll
+                for (int k = 0; k < 8; k++) cw4[k] = nx4[k];
+            } else if (valid) {
                 const uint4* rp = reinterpret_cast<const uint4*>(b.coef + row * 64);
                 #pragma unroll
                 for (int k = 0; k < 8; k++) cw4[k] = __ldg(rp + k);
@@ -173,6 +202,16 @@ __global__ void __launch_bounds__(IDCT_THREADS, IDCT_MIN_CTAS) k_idct_tile(DevBa
         }
 #undef JS_COEF
         __syncthreads();
+        #pragma unroll
+        for (int k = 0; k < 8; k++) nx4[k] = make_uint4(0, 0, 0, 0);
+        if (ti + 1 < t_end) {                                      // request the next tile's rows; they land during phase 2
+            size_t nrow;
+            if (tile_block_row(b, b.tiles[tile_first + ti + 1], wid * 32 + lane, nrow)) {
+                const uint4* rp = reinterpret_cast<const uint4*>(b.coef + nrow * 64);
+                #pragma unroll
+                for (int k = 0; k < 8; k++) nx4[k] = __ldg(rp + k);
+            }
+        }
         // ---------------- phase 2: 8 pixels x (chroma row group) per thread, vector stores ----------------
         {
             P2x a;

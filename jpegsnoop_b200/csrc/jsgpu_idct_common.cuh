@@ -33,7 +33,7 @@ static __device__ __noinline__ uint32_t ycc_exact(int py, int pcb, int pcr)
 
 __device__ __forceinline__ uint32_t fin2(int s, int dc)
 {
-    int r = (s + ((s >> 31) & 3)) >> 12;          // trunc(s/4) then floor(>>10)
+    int r = (s - 3 * (s >> 31)) >> 12;            // trunc(s/4) then floor(>>10): +3 before the shift when s < 0 (one IMAD)
     return (uint32_t)(r * 8 + dc) & 0xFFFFu;      // low 16 bits of (short)r*8 + dc
 }
 
