@@ -269,8 +269,14 @@ def main():
         idct_ms = float(stage_ms[2]); huff_ms = float(stage_ms[1])
         ach = bd.npadded_pixels * bpp / (idct_ms / 1e3) / 1e9
         huff_gbs = (bits.size + bd.npadded_pixels * (bpp - 10.0)) / (huff_ms / 1e3) / 1e9      # bitstream read + coefficient rows written
+        traffic = None        # DRAM bytes of one K2 launch from the committed ncu capture of this workload (GB), if there is one
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.config)
+            if tj and nimg == CONFIGS[args.config][0]: traffic = round(tj["dram_read_gb"] + tj["dram_write_gb"], 3)
+        except Exception:
+            pass
         roof = {"bound": "hbm", "kernel": "k_idct_tile (dequant+IDCT+upsample+YCC->BGRA, stage B)", "achieved": round(ach, 1), "peak": peak,
-                "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": traffic, "traffic_unit": "GB per launch (algorithmic: %.3f)" % (bd.npadded_pixels * bpp / 1e9), "peak_source": peak_src,
                 "algorithmic_bytes_per_padded_px": bpp, "ms_per_launch": round(idct_ms, 3),
                 "stage_ms": {"marker_scan+unstuff": round(float(stage_ms[0]), 3), "huffman": round(huff_ms, 3),
                              "idct+colour": round(idct_ms, 3), "finalize": round(float(stage_ms[3]), 3), "step_total": round(float(stage_ms[4]), 3)},
