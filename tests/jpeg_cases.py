@@ -37,6 +37,22 @@ def small_cases():
     ]
 
 
+def mini_cases():
+    """(name, jpeg bytes) from tests/mini_jpeg.py: what Pillow cannot produce — unusual Huffman code-length
+    distributions (large second-level look-up; the lane Huffman kernel must hand these to the warp kernel when
+    the second level does not fit its shared-memory copy) and sampling layouts 4:1:1 / 4:4:0."""
+    import mini_jpeg as MJ
+    ac_big = MJ.long_code_table(MJ.all_ac_symbols(), n11=24)     # ~15 ten-bit prefixes with longer codes: second level > 512 entries
+    ac_fit = MJ.long_code_table(MJ.all_ac_symbols(), n11=8)      # fits the staged second level
+    return [
+        ("mini_longcodes_big_420_dri4", MJ.encode(synth_rgb(320, 176, 21), quality=90, samp=((2, 2), (1, 1), (1, 1)), dri=4, ac_tabs=[ac_big, ac_big])),
+        ("mini_longcodes_fit_420_dri2", MJ.encode(synth_rgb(320, 176, 22), quality=90, samp=((2, 2), (1, 1), (1, 1)), dri=2, ac_tabs=[ac_fit, ac_big])),
+        ("mini_411_dri3", MJ.encode(synth_rgb(200, 72, 23), quality=75, samp=((4, 1), (1, 1), (1, 1)), dri=3)),
+        ("mini_440_nodri", MJ.encode(synth_rgb(120, 88, 24), quality=80, samp=((1, 2), (1, 1), (1, 1)))),
+        ("mini_gray_longcodes_nodri", MJ.encode(synth_rgb(136, 64, 25)[:, :, 1], quality=95, ac_tabs=[ac_big, ac_big])),
+    ]
+
+
 def compare(a, b, what=("geom", "pix_y", "pix_cb", "pix_cr", "dib", "mcu_map", "blk_dc", "dht_histo", "stats")):
     """Bit-exact comparison of two Decoded-like objects; returns list of mismatching field names."""
     bad = []

@@ -44,7 +44,7 @@ def test_port_matches_golden(built, path, fixed):
 @pytest.mark.parametrize("fixed", [True, False], ids=["fixed", "float"])
 def test_port_matches_compiled_reference(built, fixed):
     ref = Oracle("ref_fixed" if fixed else "ref_float"); port = Oracle("port", idct_fixed=fixed)
-    for name, j in JC.small_cases()[:7]:
+    for name, j in JC.small_cases()[:7] + JC.mini_cases():
         a, b = ref.decode(j), port.decode(j)
         assert a.nerr == 0 and b.nerr == 0
         assert JC.compare(a, b) == [], name
