@@ -290,7 +290,7 @@ def main():
             bad = JC.compare(orc.decode(bytes(jpegs[i])), bd.fetch(i), what=("geom", "pix_y", "pix_cb", "pix_cr", "dib", "mcu_map", "blk_dc", "dht_histo"))
             checked.append(i); parity_ok = parity_ok and not bad
         cb = None
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:          # the CPU leg is reported at N=1 only (the reference arm covers N>1)
             cb, _, _ = cpu_baseline(jpegs, w * h)
         line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": round(ms_max / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
