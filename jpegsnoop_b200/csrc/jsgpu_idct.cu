@@ -50,10 +50,17 @@ __device__ __forceinline__ uint32_t ycc_to_bgra(int py, int pcb, int pcr, uint32
     return bl | (g << 8) | (r << 16);
 }
 
+// Per-CTA copy of what the tile loop needs from the current image's descriptor (a CTA walks a contiguous run of
+// tiles, i.e. stays on one image for hundreds of tiles: one global read per image instead of per tile).
+struct TileGeo {
+    uint32_t ns, tile_mcus, H[3], V[3], cw[3], mcu_w, mcu_h, wp, hp, evc, pad;
+    unsigned long long coef_row[3], pix_off, dib_off;
+};
+
 // Coefficient row of block `idx` (0..nblk-1: all Y blocks of the tile row-major, then Cb, then Cr) of a tile.
-__device__ __forceinline__ bool tile_block_row(const DevBatch& b, const uint4& tile, uint32_t idx, size_t& row)
+template <typename Geo>
+__device__ __forceinline__ bool tile_block_row(const Geo& im, const uint4& tile, uint32_t idx, size_t& row)
 {
-    const DevImage& im = b.img[tile.x];
     const uint32_t ns = im.ns, U = im.tile_mcus;
     const uint32_t hu0 = im.H[0] * U, hu1 = (ns == 3) ? im.H[1] * U : 0, hu2 = (ns == 3) ? im.H[2] * U : 0;
     const uint32_t cnt0 = hu0 * im.V[0], cnt1 = hu1 * im.V[1], cnt2 = hu2 * im.V[2];
@@ -74,7 +81,7 @@ __global__ void __launch_bounds__(IDCT_THREADS, IDCT_MIN_CTAS) k_idct_tile(DevBa
 {
     extern __shared__ __align__(16) uint8_t smem[];
     Idct2Tables& T = *reinterpret_cast<Idct2Tables*>(smem);
-    uint8_t* const planes = smem + sizeof(Idct2Tables);
+    uint8_t* const planes = smem + sizeof(Idct2Tables) + sizeof(TileGeo);
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     // stage the decomposed table once per CTA
     if (TAB == 0) for (uint32_t i = tid; i < 64 * 4; i += blockDim.x) T.s4[i] = reinterpret_cast<const int4*>(sym->s4)[i];
@@ -86,6 +93,8 @@ __global__ void __launch_bounds__(IDCT_THREADS, IDCT_MIN_CTAS) k_idct_tile(DevBa
 
     // Register double buffer: the coefficient rows this warp's first block group needs for the NEXT tile are
     // requested before phase 2 of the current tile, so phase 1 never waits on HBM.
+    TileGeo& G = *reinterpret_cast<TileGeo*>(smem + sizeof(Idct2Tables));
+    uint32_t cur_img = 0xffffffffu;
     // Each CTA walks a contiguous run of tiles (same image for hundreds of tiles: descriptor loads hit L1,
     // coefficient rows and output rows advance sequentially).
     const uint32_t t_begin = (uint32_t)(((unsigned long long)tile_count * blockIdx.x) / gridDim.x);
@@ -95,7 +104,8 @@ __global__ void __launch_bounds__(IDCT_THREADS, IDCT_MIN_CTAS) k_idct_tile(DevBa
     for (int k = 0; k < 8; k++) nx4[k] = make_uint4(0, 0, 0, 0);
     if (t_begin < t_end) {
         size_t row;
-        if (tile_block_row(b, b.tiles[tile_first + t_begin], wid * 32 + lane, row)) {
+        const uint4 t0 = b.tiles[tile_first + t_begin];
+        if (tile_block_row(b.img[t0.x], t0, wid * 32 + lane, row)) {
             const uint4* rp = reinterpret_cast<const uint4*>(b.coef + row * 64);
             #pragma unroll
             for (int k = 0; k < 8; k++) nx4[k] = __ldg(rp + k);
@@ -104,7 +114,18 @@ __global__ void __launch_bounds__(IDCT_THREADS, IDCT_MIN_CTAS) k_idct_tile(DevBa
 
     for (uint32_t ti = t_begin; ti < t_end; ti++) {
         const uint4 tile = b.tiles[tile_first + ti];       // (image, mcu row, first mcu col, mcus in tile)
-        const DevImage& im = b.img[tile.x];
+        if (tile.x != cur_img) {                           // block-uniform; once or twice per CTA
+            __syncthreads();
+            if (tid == 0) {
+                const DevImage& gi = b.img[tile.x];
+                G.ns = gi.ns; G.tile_mcus = gi.tile_mcus; G.mcu_w = gi.mcu_w; G.mcu_h = gi.mcu_h; G.wp = gi.wp; G.hp = gi.hp;
+                G.evc = (gi.ns == 3) ? gi.ev[1] : 1; G.pix_off = gi.pix_off; G.dib_off = gi.dib_off;
+                for (int c = 0; c < 3; c++) { G.H[c] = gi.H[c]; G.V[c] = gi.V[c]; G.cw[c] = gi.cw[c]; G.coef_row[c] = gi.coef_row[c]; }
+            }
+            __syncthreads();
+            cur_img = tile.x;
+        }
+        const TileGeo& im = G;
         const uint32_t ns = im.ns, U = im.tile_mcus;
         const uint32_t trow = tile.y, mcol0 = tile.z, nmt = tile.w;
         // per-component tile geometry
@@ -206,7 +227,8 @@ __global__ void __launch_bounds__(IDCT_THREADS, IDCT_MIN_CTAS) k_idct_tile(DevBa
         for (int k = 0; k < 8; k++) nx4[k] = make_uint4(0, 0, 0, 0);
         if (ti + 1 < t_end) {                                      // request the next tile's rows; they land during phase 2
             size_t nrow;
-            if (tile_block_row(b, b.tiles[tile_first + ti + 1], wid * 32 + lane, nrow)) {
+            const uint4 nt = b.tiles[tile_first + ti + 1];
+            if ((nt.x == tile.x) ? tile_block_row(G, nt, wid * 32 + lane, nrow) : tile_block_row(b.img[nt.x], nt, wid * 32 + lane, nrow)) {
                 const uint4* rp = reinterpret_cast<const uint4*>(b.coef + nrow * 64);
                 #pragma unroll
                 for (int k = 0; k < 8; k++) nx4[k] = __ldg(rp + k);
@@ -218,7 +240,7 @@ __global__ void __launch_bounds__(IDCT_THREADS, IDCT_MIN_CTAS) k_idct_tile(DevBa
             a.planes = planes; a.pbase1 = pbase1; a.pbase2 = pbase2; a.ppitch0 = ppitch0; a.ppitch1 = ppitch1; a.ppitch2 = ppitch2;
             a.opr = (nmt * im.mcu_w) >> 3; a.px0 = mcol0 * im.mcu_w; a.py0 = trow * im.mcu_h; a.wp = im.wp; a.hp = im.hp; a.mcu_h = im.mcu_h;
             a.mapy = b.pix_y + im.pix_off; a.mapcb = b.pix_cb + im.pix_off; a.mapcr = b.pix_cr + im.pix_off; a.dib = b.dib + im.dib_off;
-            a.ns = ns; a.evc = (ns == 3) ? im.ev[1] : 1; a.gflag = ctab->gflag;
+            a.ns = ns; a.evc = im.evc; a.gflag = ctab->gflag;
             unsigned long long best = 0; uint32_t sum = 0;
             phase2x<EHS>(a, T, lane, wid, best, sum);
             sum = (sum & 0xFFFF) + (sum >> 16);
@@ -285,7 +307,7 @@ template <int TAB>
 static int launch_tab(const DevBatch& b, const IdctSym* sym, const ColorTabs* ctab, int sm_count, cudaStream_t s)
 {
     static bool attr_set = false;
-    const int mx = (int)(sizeof(Idct2Tables) + 48 * 1024);
+    const int mx = (int)(sizeof(Idct2Tables) + sizeof(TileGeo) + 48 * 1024);
     if (!attr_set) {
         cudaFuncSetAttribute(k_idct_tile<TAB, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         cudaFuncSetAttribute(k_idct_tile<TAB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
@@ -295,7 +317,7 @@ static int launch_tab(const DevBatch& b, const IdctSym* sym, const ColorTabs* ct
     // one warp per 32-block group of a tile, at most 4 warps (larger tiles loop)
     uint32_t groups = (b.tile_plane_bytes / 128 + 31) / 32;
     uint32_t threads = 32 * (groups < 1 ? 1 : groups > IDCT_THREADS / 32 ? IDCT_THREADS / 32 : groups);
-    const size_t smem = sizeof(Idct2Tables) + (size_t)b.tile_plane_bytes;
+    const size_t smem = sizeof(Idct2Tables) + sizeof(TileGeo) + (size_t)b.tile_plane_bytes;
     int n = 0;
     for (int cls = 0; cls < 3; cls++) {
         const uint32_t cnt = b.tcls_count[cls];

@@ -87,13 +87,14 @@ __device__ __forceinline__ void phase2x(const P2x& a, const Idct2Tables& T, uint
             cbw[0] = cbw[1] = cbw[2] = cbw[3] = 0; crw[0] = crw[1] = crw[2] = crw[3] = 0;
         }
         int tRs[NC], tGs[NC], tBs[NC];
+        uint32_t gw[NC], gs[NC];                  // exact-path bitmap words: requested here, looked at after the first row's arithmetic
         #pragma unroll
         for (int j = 0; j < NC; j++) {
             const int cbc = max(-128, min(127, cs[j] >> 3)), crc = max(-128, min(127, rs[j] >> 3));
             const uint32_t gi = (uint32_t)(((cbc + 128) << 8) | (crc + 128));
             tRs[j] = T.tr[crc + 128]; tBs[j] = T.tb[cbc + 128];
             tGs[j] = (-(JS_GA * cbc + JS_GB * crc)) >> 23;                         // verified arithmetic form of the G chroma term
-            if ((__ldg(&a.gflag[gi >> 5]) >> (gi & 31)) & 1) unsafe |= ((1u << (1 << EHS)) - 1) << (j << EHS);
+            gw[j] = __ldg(&a.gflag[gi >> 5]); gs[j] = gi & 31;
         }
         #pragma unroll
         for (int p = 0; p < 4; p++) {
@@ -101,7 +102,6 @@ __device__ __forceinline__ void phase2x(const P2x& a, const Idct2Tables& T, uint
             else if (EHS == 1) { dR[p] = dup16(tRs[p]); dG[p] = dup16(tGs[p]); dB[p] = dup16(tBs[p]); }
             else               { dR[p] = dup16(tRs[p >> 1]); dG[p] = dup16(tGs[p >> 1]); dB[p] = dup16(tBs[p >> 1]); }
         }
-        if (!T.rb_ok) unsafe = 0xFF;
         for (uint32_t r2 = 0; r2 < a.evc; r2++) {
             const uint32_t oy = rg * a.evc + r2;
             const uint4 yv = *reinterpret_cast<const uint4*>(a.planes + oy * a.ppitch0 + px * 2);
@@ -123,6 +123,11 @@ __device__ __forceinline__ void phase2x(const P2x& a, const Idct2Tables& T, uint
                 sum2 += y8;                                                                   // halves stay < 2^16 within a tile
                 bgra[2 * p]     = __byte_perm(__byte_perm(bp, gp, 0x0040), rp, 0x5410);
                 bgra[2 * p + 1] = __byte_perm(__byte_perm(bp, gp, 0x0062), rp, 0x7610);
+            }
+            if (r2 == 0) {
+                #pragma unroll
+                for (int j = 0; j < NC; j++) if ((gw[j] >> gs[j]) & 1) unsafe |= ((1u << (1 << EHS)) - 1) << (j << EHS);
+                if (!T.rb_ok) unsafe = 0xFF;
             }
             if (unsafe) {              // rare (a handful of (cb,cr) pairs): the exact float routine, out of line
                 #pragma unroll
