@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(IDCT_THREADS, IDCT_MIN_CTAS) k_idct_tile(DevBa
 {
     extern __shared__ __align__(16) uint8_t smem[];
     Idct2Tables& T = *reinterpret_cast<Idct2Tables*>(smem);
-    uint8_t* const planes = smem + sizeof(Idct2Tables) + sizeof(TileGeo);
+    uint8_t* const planes0 = smem + sizeof(Idct2Tables) + sizeof(TileGeo);    // two plane buffers: one barrier per tile (see the loop)
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     // stage the decomposed table once per CTA
     if (TAB == 0) for (uint32_t i = tid; i < 64 * 4; i += blockDim.x) T.s4[i] = reinterpret_cast<const int4*>(sym->s4)[i];
@@ -126,6 +126,10 @@ __global__ void __launch_bounds__(IDCT_THREADS, IDCT_MIN_CTAS) k_idct_tile(DevBa
             cur_img = tile.x;
         }
         const TileGeo& im = G;
+        // Sample planes are double-buffered: phase 1 of tile t+1 may start while slower warps still read tile t's
+        // planes in phase 2; it cannot run further ahead than the barrier of tile t+1, which every warp reaches
+        // only after finishing phase 2 of tile t, so the buffer written for tile t+2 is free by then.
+        uint8_t* const planes = planes0 + ((ti - t_begin) & 1) * b.tile_plane_bytes;
         const uint32_t ns = im.ns, U = im.tile_mcus;
         const uint32_t trow = tile.y, mcol0 = tile.z, nmt = tile.w;
         // per-component tile geometry
@@ -249,7 +253,6 @@ __global__ void __launch_bounds__(IDCT_THREADS, IDCT_MIN_CTAS) k_idct_tile(DevBa
             for (int d = 16; d; d >>= 1) { best = max(best, __shfl_xor_sync(FULL, best, d)); sum64 += __shfl_xor_sync(FULL, sum64, d); }
             if (lane == 0 && best) { atomicMax(&b.bright_key[tile.x], best); atomicAdd(&b.sum_y[tile.x], sum64); }
         }
-        __syncthreads();
     }
 }
 
@@ -317,7 +320,7 @@ static int launch_tab(const DevBatch& b, const IdctSym* sym, const ColorTabs* ct
     // one warp per 32-block group of a tile, at most 4 warps (larger tiles loop)
     uint32_t groups = (b.tile_plane_bytes / 128 + 31) / 32;
     uint32_t threads = 32 * (groups < 1 ? 1 : groups > IDCT_THREADS / 32 ? IDCT_THREADS / 32 : groups);
-    const size_t smem = sizeof(Idct2Tables) + sizeof(TileGeo) + (size_t)b.tile_plane_bytes;
+    const size_t smem = sizeof(Idct2Tables) + sizeof(TileGeo) + 2 * (size_t)b.tile_plane_bytes;
     int n = 0;
     for (int cls = 0; cls < 3; cls++) {
         const uint32_t cnt = b.tcls_count[cls];
