@@ -312,13 +312,16 @@ int js_launch_huffman_warp(const DevBatch& b, int sm_count, cudaStream_t s)
 // lane per restart interval
 // ------------------------------------------------------------------------------------------------
 #define LN_WARPS   (JS_LANE_SEGS / 32)
-#define ROW_PITCH  144                      // bytes per lane row: 64 coefficients + 8 dummy slots; 16-byte aligned
+#define ROW_PITCH  208                      // bytes per lane row: 64 coefficients, 8 dummy slots, 16 code-length counters; 16-byte aligned
+#define ROW_HIST   144                      // byte offset of the counter for length 1 (length 0 = "no code" lands in the dummy slots)
+#define LN_TAB     (JS_LUT_SIZE + JS_LANE_L2S)   // entries per staged table: first level, then its second level
 // Dynamic shared memory of the lane kernel:
-//   LaneHdr | coefficient rows [LN_WARPS][32][ROW_PITCH] | lut [nl][JS_LUT_SIZE] | lut2 [nl][JS_LANE_L2S] | (HISTO) hw [LN_WARPS][17][32]
+//   LaneHdr | lane rows [LN_WARPS][32][ROW_PITCH] | tables [nl][LN_TAB]
 // nl = DevBatch::lane_nlut: the distinct (class,Th) tables an image selects are staged once each (Cb and Cr
-// normally share theirs).  hw: AC code-length counters, one 32-bit word per (length 1..16, lane); a lane only
-// touches its own column, so the result-less shared atomic is conflict-free and nothing waits on it; the
-// columns are summed into LaneHdr::histo once per (MCU, component).
+// normally share theirs), second level right behind its first level (one base register per table).
+// A lane row = its block's 64 coefficients + dummy slots + its AC code-length counters (one 32-bit word per
+// length): a lane only touches its own row, so the result-less shared atomic is conflict-free and nothing
+// waits on it; the counters are summed into LaneHdr::histo once per (MCU, component).
 struct LaneHdr {
     uint32_t histo[6][17];
     uint32_t qz[3][80];                     // quantiser | natural index<<16 ; entries 64..79 -> dummy slots past the row
@@ -328,7 +331,8 @@ struct LaneHdr {
 };
 static inline size_t lane_smem_bytes(uint32_t nl, bool histo)
 {
-    return sizeof(LaneHdr) + (size_t)LN_WARPS * 32 * ROW_PITCH + (size_t)nl * (JS_LUT_SIZE + JS_LANE_L2S) * 2 + (histo ? (size_t)LN_WARPS * 17 * 32 * 4 : 0);
+    (void)histo;
+    return sizeof(LaneHdr) + (size_t)LN_WARPS * 32 * ROW_PITCH + (size_t)nl * LN_TAB * 2;
 }
 
 // Bit window as two 32-bit registers (hi = next 32 bits, lo = the 32 after), funnel-shift consume.
@@ -343,7 +347,7 @@ struct Win {
         const uint32_t x = nx;
         nx = __ldg(base + idx); idx++;
         hi |= __funnelshift_rc(x, 0, nb);                  // x >> nb, 0 when nb == 32
-        lo = x << (32 - nb);
+        lo = __funnelshift_rc(0, x, nb);                   // x << (32 - nb), x when nb == 32
         nb += 32;
     }
     __device__ __forceinline__ void consume(uint32_t n) { hi = __funnelshift_l(lo, hi, n); lo <<= n; nb -= (int)n; }
@@ -359,16 +363,11 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 3) k_huff_lane(DevBatch b)
     extern __shared__ __align__(16) uint8_t smem_raw[];
     LaneHdr& sh = *reinterpret_cast<LaneHdr*>(smem_raw);
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const uint32_t nlut = b.lane_nlut;
     uint8_t* const rows0 = smem_raw + sizeof(LaneHdr);
     uint16_t* const lutb = reinterpret_cast<uint16_t*>(rows0 + LN_WARPS * 32 * ROW_PITCH);
-    uint16_t* const l2b = lutb + nlut * JS_LUT_SIZE;
-    uint32_t* const myhw = reinterpret_cast<uint32_t*>(l2b + nlut * JS_LANE_L2S) + (HISTO ? wid * 17 * 32 : 0);   // row 0 collects length 0 (= no code), never read
     uint8_t* const myrows = rows0 + wid * 32 * ROW_PITCH;
     uint8_t* const myrow = myrows + lane * ROW_PITCH;
     for (uint32_t i = lane; i < 32 * ROW_PITCH / 4; i += 32) reinterpret_cast<uint32_t*>(myrows)[i] = 0;
-    if (HISTO) for (uint32_t i = lane; i < 17 * 32; i += 32) myhw[i] = 0;
-    uint32_t* const hwl = myhw + lane;
     const bool want_ac = GENERIC ? (b.decode_ac != 0) : true;
     uint32_t cur_img = 0xffffffffu, cur_sig = 0xffffffffu, cur_set = 0xffffffffu;
     for (uint32_t it = blockIdx.x; it < b.nlitems; it += gridDim.x) {      // strided: images of different entropy spread over all CTAs
@@ -396,10 +395,10 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 3) k_huff_lane(DevBatch b)
                 for (uint32_t j = 0; j < nl; j++) {
                     const uint32_t slot = sh.lslot[j];
                     const uint4* s0 = reinterpret_cast<const uint4*>(ts->lut[slot]);
-                    uint4* d0 = reinterpret_cast<uint4*>(lutb + j * JS_LUT_SIZE);
+                    uint4* d0 = reinterpret_cast<uint4*>(lutb + j * LN_TAB);
                     for (uint32_t i = threadIdx.x; i < JS_LUT_SIZE * 2 / 16; i += blockDim.x) d0[i] = __ldg(s0 + i);
                     const uint4* s1 = reinterpret_cast<const uint4*>(ts->lut2[slot]);
-                    uint4* d1 = reinterpret_cast<uint4*>(l2b + j * JS_LANE_L2S);
+                    uint4* d1 = reinterpret_cast<uint4*>(lutb + j * LN_TAB + JS_LUT_SIZE);
                     const uint32_t used = ts->lut2_used[slot];              // <= JS_LANE_L2S: the launcher refuses the batch otherwise
                     for (uint32_t i = threadIdx.x; i < used * 2 / 16; i += blockDim.x) d1[i] = __ldg(s1 + i);
                 }
@@ -430,16 +429,15 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 3) k_huff_lane(DevBatch b)
             if (mlive) b.mcu_bitpos[gim.mcu_off + m0 + mi] = s.consumed();
             #pragma unroll 1
             for (uint32_t c = 0; c < ns; c++) {
-                const uint16_t* lut_dc = lutb + sh.li[c * 2] * JS_LUT_SIZE;
-                const uint16_t* lut_ac = lutb + sh.li[c * 2 + 1] * JS_LUT_SIZE;
-                const uint16_t* l2_dc = l2b + sh.li[c * 2] * JS_LANE_L2S;
-                const uint16_t* l2_ac = l2b + sh.li[c * 2 + 1] * JS_LANE_L2S;
+                const uint16_t* lut_dc = lutb + sh.li[c * 2] * LN_TAB;
+                const uint16_t* lut_ac = lutb + sh.li[c * 2 + 1] * LN_TAB;
                 const uint32_t* qz = sh.qz[c];
                 const uint32_t nh = gim.H[c], nv = gim.V[c], cw = gim.cw[c];
                 const uint32_t ehc = gim.eh[c], evc = gim.ev[c], blk_xmax = gim.blk_xmax, mcu_ymax = gim.mcu_ymax;
                 int16_t* const blkmap = ((c == 0) ? b.blk_y : (c == 1) ? b.blk_cb : b.blk_cr) + gim.blk_off;
                 int dc = (c == 0) ? dc0 : (c == 1) ? dc1 : dc2;
                 #pragma unroll 1
+                uint32_t bh = 0, bv = 0;
                 for (uint32_t bi = 0; bi < nh * nv; bi++) {
                     bool active = mlive && !(status & 7);
                     uint32_t pos = 64;
@@ -447,7 +445,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 3) k_huff_lane(DevBatch b)
                         // ---- DC symbol ----
                         if (s.nb <= 32) s.refill();
                         uint32_t e = lut_dc[s.hi >> (32 - JS_LUT_BITS)];
-                        if ((int)(short)e < 0) e = l2_dc[(e & 0x7FFF) + ((s.hi >> 16) & ((1u << JS_LUT2_BITS) - 1))];
+                        if (e & 0x8000) e = lut_dc[JS_LUT_SIZE + (e & 0x7FFF) + ((s.hi >> 16) & ((1u << JS_LUT2_BITS) - 1))];
                         if (e == 0) { status |= 1; active = false; }
                         else {
                             const uint32_t len = e >> 8, run = (e >> 4) & 15, size = e & 15;
@@ -474,9 +472,9 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 3) k_huff_lane(DevBatch b)
 
                             if (s.nb <= 32) s.refill();
                             uint32_t e = lut_ac[s.hi >> (32 - JS_LUT_BITS)];
-                            if ((int)(short)e < 0) e = l2_ac[(e & 0x7FFF) + ((s.hi >> 16) & ((1u << JS_LUT2_BITS) - 1))];
+                            if (e & 0x8000) e = lut_ac[JS_LUT_SIZE + (e & 0x7FFF) + ((s.hi >> 16) & ((1u << JS_LUT2_BITS) - 1))];
                             const uint32_t len = e >> 8, size = e & 15, run = (e >> 4) & 15;
-                            if (HISTO) atomicAdd(hwl + len * 32, 1u);
+                            if (HISTO) atomicAdd(reinterpret_cast<uint32_t*>(myrow + (ROW_HIST - 4)) + len, 1u);
                             emin = min(emin, e);
                             // value bits follow the code: take them from the window before consuming both at once
                             const uint32_t t = __funnelshift_l(s.lo, s.hi, len);
@@ -496,7 +494,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 3) k_huff_lane(DevBatch b)
                     }
                     if (emin == 0) status |= 1;
                     if (pos > 64 && pos < 128) status |= 4;
-                    const uint32_t v = bi / nh, h = bi - v * nh;
+                    const uint32_t v = bv, h = bh;                        // block (h, v) inside the MCU, kept incrementally (no division)
+                    if (++bh == nh) { bh = 0; bv++; }
                     if (active) {
                         *reinterpret_cast<uint16_t*>(myrow) = (uint16_t)dc;
                         // block-DC map (ImgDecode.cpp:3524-3608 in gather form): cell (mx*eh+h, my*ev+v) keeps this
@@ -522,10 +521,10 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 3) k_huff_lane(DevBatch b)
                 if (HISTO) {
                     // lane l sums AC length (l & 15) + 1 over lanes [16 * (l >> 4), +16); rotated so that the 32 lanes hit 32 banks
                     __syncwarp();
-                    uint32_t* hp = myhw + 32 + (lane & 15) * 32 + (lane >> 4) * 16;
+                    uint8_t* hp = myrows + (lane >> 4) * 16 * ROW_PITCH + ROW_HIST + (lane & 15) * 4;
                     uint32_t tot = 0;
                     #pragma unroll
-                    for (int k2 = 0; k2 < 16; k2++) { const uint32_t j = (k2 + lane) & 15; tot += hp[j]; hp[j] = 0; }
+                    for (int k2 = 0; k2 < 16; k2++) { uint32_t* q = reinterpret_cast<uint32_t*>(hp + ((k2 + lane) & 15) * ROW_PITCH); tot += *q; *q = 0; }
                     tot += __shfl_xor_sync(FULL, tot, 16);
                     if (lane < 16 && tot) atomicAdd(&sh.histo[c * 2 + 1][lane + 1], tot);
                     __syncwarp();
