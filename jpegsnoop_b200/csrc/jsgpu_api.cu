@@ -377,7 +377,7 @@ int jsgpu_batch_begin(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, 
         for (uint32_t k = 0; k < im.nseg; k += JS_HUFF_WARPS) items.push_back(make_uint2(i, k));
         im.nitems = (uint32_t)items.size() - im.item_first;
         for (uint32_t k = 0; k < im.nseg; k += JS_LANE_SEGS) litems.push_back(make_uint2(i, k));
-        im.ubits_off = ub; ub += align_up(im.scan_len + 32ull * im.nseg + 64, 256);
+        im.ubits_off = ub; ub += align_up(im.scan_len + (uint64_t)JS_USLACK * im.nseg + 128, 256);
         if (im.std_layout) {
             n_std++;
             const uint32_t ehc = (im.ns == 3) ? im.eh[1] : 1, cls = (ehc == 1) ? 0 : (ehc == 2) ? 1 : 2;

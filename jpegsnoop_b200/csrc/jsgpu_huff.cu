@@ -1,9 +1,11 @@
 // jsgpu_huff.cu — entropy decode (stage A): FF00 unstuffing pre-pass + two Huffman kernels.
 //
-//   k_unstuff      one warp per restart interval: 128 raw bytes per step, stuffed zeros found with
-//                  one shuffle, kept-byte ranks from three __ballot_sync (the per-lane count is
-//                  0..4, so three ballots give its exclusive prefix), compaction straight into an
-//                  aligned, 0xFF-padded copy of the interval.  (BuffAddByte, ImgDecode.cpp:1386-1573.)
+//   k_unstuff      a warp walks restart intervals of one image: 128 raw bytes per step, stuffed zeros
+//                  found with one shuffle, kept-byte ranks from three __ballot_sync (the per-lane
+//                  count is 0..4, so three ballots give its exclusive prefix); each lane's kept
+//                  bytes are packed by a PRMT (selector from a 16-entry table) and OR-ed into a
+//                  zeroed shared-memory ring, which leaves as 16-byte stores of big-endian words into
+//                  an aligned, 0xFF-padded copy of the interval.  (BuffAddByte, ImgDecode.cpp:1386-1573.)
 //   k_huff_warp    ONE WARP PER RESTART INTERVAL, warp-uniform symbol loop; lane i owns coefficients
 //                  2i,2i+1 so a block leaves as one coalesced 128-byte row.  Right when there are few,
 //                  long intervals (BASELINE config 5: no DRI) — a serial chain per interval.
@@ -14,78 +16,123 @@
 // dequantised int16 coefficient rows in natural order (DecodeIdctSet, :2270-2303) whose slot 0
 // holds the running DC predictor sum (m_nDcLum += m_anDctBlock[0], :3280).
 #include "jsgpu_internal.h"
+#include <cstdlib>
 
 #define FULL 0xffffffffu
 
 // ------------------------------------------------------------------------------------------------
 // unstuff
 // ------------------------------------------------------------------------------------------------
+#define US_RING 1024                        // bytes of staging ring per warp (two 512-byte halves)
 __global__ void __launch_bounds__(128) k_unstuff(DevBatch b)
 {
-    const uint32_t lane = threadIdx.x & 31;
+    __shared__ __align__(16) uint32_t s_ring[4][US_RING / 4];
+    __shared__ uint32_t s_sel[16];          // PRMT selector that packs the kept bytes of a word to the low end, by removal mask
+    __shared__ uint32_t s_cnt[4];           // stuffed bytes seen in the current interval, per warp
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t* const ring = s_ring[wid];
+    if (threadIdx.x < 16) {
+        uint32_t sel = 0, n = 0;
+        for (uint32_t j = 0; j < 4; j++) if (!(threadIdx.x >> j & 1)) sel |= j << (4 * n++);
+        for (; n < 4; n++) sel |= 4u << (4 * n);                                  // 4 = a byte of the zero operand
+        s_sel[threadIdx.x] = sel;
+    }
+    for (uint32_t i = lane; i < US_RING / 4; i += 32) ring[i] = 0;
+    __syncthreads();
+    // place the (<= 4) low bytes of `kk` at byte offset o of the ring: two result-less shared ORs into the zeroed ring
+    auto place = [&](uint32_t kk, uint32_t o) {
+        const uint32_t sh = (o & 3) * 8, A = (o >> 2) & (US_RING / 4 - 1);
+        atomicOr(&ring[A], kk << sh);
+        atomicOr(&ring[(A + 1) & (US_RING / 4 - 1)], __funnelshift_l(kk, 0, sh));
+    };
     for (uint32_t ii = blockIdx.y; ii < b.nimg; ii += gridDim.y) {            // grid.y = image (strided beyond 65535 images)
     const DevImage& im = b.img[ii];
     if (!im.valid) continue;
-    const uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (k >= im.nseg) continue;
-    const uint32_t gw = im.seg_first + k;
-    const uint32_t s0 = b.seg_start[gw], len = b.seg_end[gw] - s0;
-    const uint8_t* seg = b.bits + im.scan_off + s0;
+    const uint32_t nseg = im.nseg, seg_first = im.seg_first, kstep = (gridDim.x * blockDim.x) >> 5;
+    const uint8_t* const scan = b.bits + im.scan_off;
+    const uint64_t ubase = im.ubits_off;
+    uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    // a warp walks intervals k, k + kstep, ...; the bounds of the next one are requested while this one is processed
+    uint32_t ns0 = 0, ne0 = 0;
+    if (k < nseg) { ns0 = b.seg_start[seg_first + k]; ne0 = b.seg_end[seg_first + k]; }
+    for (; k < nseg; k += kstep) {
+    const uint32_t gw = seg_first + k;
+    const uint32_t s0 = ns0, len = ne0 - ns0;
+    if (k + kstep < nseg) { ns0 = b.seg_start[gw + kstep]; ne0 = b.seg_end[gw + kstep]; }
+    const uint8_t* seg = scan + s0;
     // destination: 16-byte aligned, never overlapping the neighbours
-    const uint64_t dst0 = im.ubits_off + (uint64_t)(s0 & ~15u) + 32ull * k;
+    const uint64_t dst0 = ubase + (uint64_t)(s0 & ~15u) + (unsigned long long)JS_USLACK * k;
     uint8_t* dst = b.ubits + dst0;
     const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(seg) & 3);
-    const uint8_t* abase = seg - mis;
-    uint32_t wr = 0, prev_ff = 0, nstuff = 0;
+    const uint32_t* abase = reinterpret_cast<const uint32_t*>(seg - mis);
+    uint32_t wr = 0, fl = 0, carry = 0;
     const uint32_t lt = (1u << lane) - 1;
+    if (lane == 0) s_cnt[wid] = 0;
+    __syncwarp();
+    // rows are requested one ahead of their use
+    auto load_row = [&](uint32_t rp) -> uint32_t {
+        const int r0 = (int)(rp + 4 * lane) - (int)mis;
+        return (r0 + 3 >= 0 && r0 < (int)len) ? __ldg(abase + (rp >> 2) + lane) : 0u;
+    };
+    uint32_t nword = load_row(0);
     for (uint32_t rpos = 0; rpos < len + mis; rpos += 128) {
-        const int rel0 = (int)(rpos + 4 * lane) - (int)mis;         // segment offset of this lane's byte 0
-        uint32_t word = 0;
-        if (rel0 + 3 >= 0 && rel0 < (int)len) word = __ldg(reinterpret_cast<const uint32_t*>(abase + rpos + 4 * lane));
-        // byte flags live in bit 7 of each byte.  valid bytes: 0 <= rel0+j < len
-        const int lo = max(0, -rel0), hi = min(4, (int)len - rel0);
-        uint32_t vmask = 0;
-        if (hi > lo) vmask = (0x80808080u >> (32 - 8 * hi)) & ~((lo > 0) ? (0x80808080u >> (32 - 8 * lo)) : 0u);
+        const int rel0 = (int)(rpos + 4 * lane) - (int)mis;                       // interval offset of this lane's byte 0
+        const uint32_t word = nword;
+        if (rpos + 128 < len + mis) nword = load_row(rpos + 128);
         uint32_t up = __shfl_up_sync(FULL, word, 1);
-        if (lane == 0) up = prev_ff ? 0xFF000000u : 0u;
-        const uint32_t pw = __byte_perm(up, word, 0x6543);           // byte j = the byte before word's byte j
+        if (lane == 0) up = carry;
+        carry = __shfl_sync(FULL, word, 31);
+        // nibble masks over this lane's 4 bytes: inside the interval; allowed to be a stuffed zero (not the first byte)
+        const int vlo = max(0, -rel0), vhi = min(4, (int)len - rel0);
+        const uint32_t vn = (vhi > vlo) ? (((1u << vhi) - 1u) & ~((1u << vlo) - 1u)) : 0u;
+        const uint32_t an = (rel0 <= 0 && rel0 > -4) ? (vn & ~(1u << (-rel0))) : vn;
+        const uint32_t pw = __byte_perm(up, word, 0x6543);                       // byte j = the byte before word's byte j
         const uint32_t npw = ~pw;
-        const uint32_t z = ~(((word & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | word | 0x7F7F7F7Fu);   // byte == 0x00
+        const uint32_t z = ~(((word & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | word | 0x7F7F7F7Fu);   // byte == 0x00 (flag in bit 7)
         const uint32_t f = ~(((npw & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | npw | 0x7F7F7F7Fu);     // previous byte == 0xFF
-        uint32_t drop = z & f & vmask;
-        if (rel0 <= 0 && rel0 > -4) drop &= ~(0x80u << (8 * (-rel0)));                     // the first byte has no predecessor in the interval
-        const uint32_t keep = vmask & ~drop;
-        const uint32_t cnt = __popc(keep);
+        const uint32_t dn = ((((z & f) >> 7) * 0x00204081u) >> 21) & an;                    // stuffed zeros, as a nibble
+        const uint32_t rm = dn | (vn ^ 15u);                                                // bytes that do not reach the output
+        const uint32_t kk = __byte_perm(word, 0, s_sel[rm]);
+        const uint32_t cnt = 4 - __popc(rm);                                                // 0..4 kept bytes
         const uint32_t b0 = __ballot_sync(FULL, cnt & 1), b1 = __ballot_sync(FULL, cnt & 2), b2 = __ballot_sync(FULL, cnt & 4);
-        const uint32_t pre = __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
-        const uint32_t tot = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
-        uint32_t o = wr + pre;
-        if (keep == 0x80808080u && (o & 3) == 0) *reinterpret_cast<uint32_t*>(dst + o) = __byte_perm(word, 0, 0x0123);   // common case: one aligned word store
-        else {
-            #pragma unroll
-            for (int j = 0; j < 4; j++) if (keep >> (8 * j + 7) & 1) { dst[o ^ 3] = (uint8_t)(word >> (8 * j)); o++; }
-        }
-        // record where bytes were dropped (for the MCU file map): unstuffed index of the preceding FF
-        if (__ballot_sync(FULL, drop != 0)) {
-            const uint32_t dc = __popc(drop);                               // 0..2 per lane
-            const uint32_t d0 = __ballot_sync(FULL, dc & 1), d1 = __ballot_sync(FULL, dc & 2);
-            uint32_t dr = nstuff + __popc(d0 & lt) + 2 * __popc(d1 & lt);
-            uint32_t oo = wr + pre;
-            #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                if (drop >> (8 * j + 7) & 1) { if (dr < JS_STUFF_LIST) b.seg_stuff[(size_t)gw * JS_STUFF_LIST + dr] = oo - 1; dr++; }
-                else if (keep >> (8 * j + 7) & 1) oo++;
+        const uint32_t o = wr + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
+        if (__any_sync(FULL, dn != 0)) {              // remember where bytes were dropped (MCU file map): unstuffed index of the preceding FF
+            uint32_t d = dn;
+            while (d) {
+                const uint32_t j = __ffs(d) - 1; d &= d - 1;
+                const uint32_t idx = atomicAdd(&s_cnt[wid], 1u);
+                if (idx < JS_STUFF_LIST) b.seg_stuff[(size_t)gw * JS_STUFF_LIST + idx] = o + __popc(~rm & ((1u << j) - 1u)) - 1;
             }
-            nstuff += __popc(d0) + 2 * __popc(d1);
         }
-        wr += tot;
-        prev_ff = ((__shfl_sync(FULL, word, 31) >> 24) == 0xFF) ? 1u : 0u;
+        place(kk, o);
+        wr += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+        __syncwarp();
+        if (wr - fl >= 512) {                          // a 512-byte half is complete: big-endian words out, half re-zeroed
+            uint4* rp = reinterpret_cast<uint4*>(ring + ((fl & (US_RING - 1)) >> 2)) + lane;
+            const uint4 v = *rp;
+            *rp = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(dst + fl + 16 * lane) = make_uint4(__byte_perm(v.x, 0, 0x0123), __byte_perm(v.y, 0, 0x0123), __byte_perm(v.z, 0, 0x0123), __byte_perm(v.w, 0, 0x0123));
+            fl += 512;
+            __syncwarp();
+        }
     }
-    // pad with 1-bits (the JPEG pad value; no valid code is all ones) so readers can over-fetch
-    if (lane < 16) dst[(wr + lane) ^ 3] = 0xFF;      // 16 bytes: the most a reader can over-fetch, and what the 32-byte slack allows
+    // pad with 16 bytes of 1-bits (the JPEG pad value; no valid code is all ones) so readers can over-fetch
+    if (lane < 4) place(0xFFFFFFFFu, wr + 4 * lane);
+    __syncwarp();
+    #pragma unroll 1
+    for (uint32_t off = 16 * lane; off < wr + 16 - fl; off += 512) {
+        uint4* rp = reinterpret_cast<uint4*>(ring + (((fl + off) & (US_RING - 1)) >> 2));
+        const uint4 v = *rp;
+        *rp = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(dst + fl + off) = make_uint4(__byte_perm(v.x, 0, 0x0123), __byte_perm(v.y, 0, 0x0123), __byte_perm(v.z, 0, 0x0123), __byte_perm(v.w, 0, 0x0123));
+    }
+    __syncwarp();
     if (lane == 0) {
+        const uint32_t nstuff = s_cnt[wid];
         b.seg_ulen[gw] = wr; b.seg_uoff[gw] = dst0; b.seg_nstuff[gw] = nstuff;
         if (nstuff > JS_STUFF_LIST) b.ovf_list[atomicAdd(b.ovf_count, 1u)] = gw;     // rare: the MCU map of this interval needs the raw re-walk
+    }
+    __syncwarp();
     }
     }
 }
@@ -93,7 +140,10 @@ __global__ void __launch_bounds__(128) k_unstuff(DevBatch b)
 int js_launch_unstuff(const DevBatch& b, cudaStream_t s)
 {
     if (b.nseg_total == 0 || b.max_nseg == 0) return 0;
-    const dim3 grid((b.max_nseg + 3) / 4, b.nimg < 65535u ? b.nimg : 65535u);
+    dim3 grid((b.max_nseg + 3) / 4, b.nimg < 65535u ? b.nimg : 65535u);
+    // persistent over an image's intervals: enough CTAs to fill the GPU ~8x, at most one warp per interval
+    const uint32_t want = (148u * 16u * 8u + grid.y - 1) / grid.y;
+    if (grid.x > want) grid.x = want < 1 ? 1 : want;
     k_unstuff<<<grid, 128, 0, s>>>(b);
     return 1;
 }

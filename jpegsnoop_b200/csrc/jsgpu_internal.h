@@ -9,6 +9,7 @@
 #define JS_LUT2_BITS  (16 - JS_LUT_BITS)
 #define JS_LUT2_SIZE  8192               // second-level entries per slot (256 sub-tables of 32)
 #define JS_MAX_CODES  260
+#define JS_USLACK     48                 // bytes of slack per restart interval in the unstuffed pool (16 pad + flush rounding + alignment)
 #define JS_STUFF_LIST 6                  // stuffed-byte positions recorded per restart interval
 #define JS_NSLOT      8                  // (class,Th) pairs: slot = class*4 + Th
 
