@@ -95,6 +95,15 @@ __global__ void __launch_bounds__(IDCT_THREADS, IDCT_MIN_CTAS) k_idct_tile(DevBa
     // requested before phase 2 of the current tile, so phase 1 never waits on HBM.
     TileGeo& G = *reinterpret_cast<TileGeo*>(smem + sizeof(Idct2Tables));
     uint32_t cur_img = 0xffffffffu;
+    // per-thread statistics of the current image, kept across its tiles: brightest pixel (key + value) and the luma sum
+    unsigned long long best = 0; int bestm = -0x7fffffff - 1; uint32_t acc_y = 0;
+    auto flush_stats = [&](uint32_t img) {
+        unsigned long long s64 = acc_y;
+        #pragma unroll
+        for (int d = 16; d; d >>= 1) { best = max(best, __shfl_xor_sync(FULL, best, d)); s64 += __shfl_xor_sync(FULL, s64, d); }
+        if (lane == 0 && best) { atomicMax(&b.bright_key[img], best); atomicAdd(&b.sum_y[img], s64); }
+        best = 0; bestm = -0x7fffffff - 1; acc_y = 0;
+    };
     // Each CTA walks a contiguous run of tiles (same image for hundreds of tiles: descriptor loads hit L1,
     // coefficient rows and output rows advance sequentially).
     const uint32_t t_begin = (uint32_t)(((unsigned long long)tile_count * blockIdx.x) / gridDim.x);
@@ -115,6 +124,7 @@ __global__ void __launch_bounds__(IDCT_THREADS, IDCT_MIN_CTAS) k_idct_tile(DevBa
     for (uint32_t ti = t_begin; ti < t_end; ti++) {
         const uint4 tile = b.tiles[tile_first + ti];       // (image, mcu row, first mcu col, mcus in tile)
         if (tile.x != cur_img) {                           // block-uniform; once or twice per CTA
+            if (cur_img != 0xffffffffu) flush_stats(cur_img);
             __syncthreads();
             if (tid == 0) {
                 const DevImage& gi = b.img[tile.x];
@@ -245,15 +255,12 @@ __global__ void __launch_bounds__(IDCT_THREADS, IDCT_MIN_CTAS) k_idct_tile(DevBa
             a.opr = (nmt * im.mcu_w) >> 3; a.px0 = mcol0 * im.mcu_w; a.py0 = trow * im.mcu_h; a.wp = im.wp; a.hp = im.hp; a.mcu_h = im.mcu_h;
             a.mapy = b.pix_y + im.pix_off; a.mapcb = b.pix_cb + im.pix_off; a.mapcr = b.pix_cr + im.pix_off; a.dib = b.dib + im.dib_off;
             a.ns = ns; a.evc = im.evc; a.gflag = ctab->gflag;
-            unsigned long long best = 0; uint32_t sum = 0;
-            phase2x<EHS>(a, T, lane, wid, best, sum);
-            sum = (sum & 0xFFFF) + (sum >> 16);
-            unsigned long long sum64 = sum;
-            #pragma unroll
-            for (int d = 16; d; d >>= 1) { best = max(best, __shfl_xor_sync(FULL, best, d)); sum64 += __shfl_xor_sync(FULL, sum64, d); }
-            if (lane == 0 && best) { atomicMax(&b.bright_key[tile.x], best); atomicAdd(&b.sum_y[tile.x], sum64); }
+            uint32_t sum = 0;                               // packed halves, < 2^16 each within one tile
+            phase2x<EHS>(a, T, lane, wid, best, bestm, sum);
+            acc_y += (sum & 0xFFFF) + (sum >> 16);
         }
     }
+    if (cur_img != 0xffffffffu) flush_stats(cur_img);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -184,8 +184,8 @@ __global__ void __launch_bounds__(T2_MAXWARPS * 32, 4) k_idct_tma(DevBatch b, co
             a.opr = (nmt * im.mcu_w) >> 3; a.px0 = mcol0 * im.mcu_w; a.py0 = trow * im.mcu_h; a.wp = im.wp; a.hp = im.hp; a.mcu_h = im.mcu_h;
             a.mapy = b.pix_y + im.pix_off; a.mapcb = b.pix_cb + im.pix_off; a.mapcr = b.pix_cr + im.pix_off; a.dib = b.dib + im.dib_off;
             a.ns = ns; a.evc = (ns == 3) ? im.ev[1] : 1; a.gflag = ctab->gflag;
-            unsigned long long best = 0; uint32_t sum2 = 0;
-            phase2x<EHS>(a, T, lane, wid, best, sum2);
+            unsigned long long best = 0; uint32_t sum2 = 0; int bestm = -0x7fffffff - 1;
+            phase2x<EHS>(a, T, lane, wid, best, bestm, sum2);
             unsigned long long sum64 = (sum2 & 0xFFFF) + (sum2 >> 16);
             #pragma unroll
             for (int d = 16; d; d >>= 1) { best = max(best, __shfl_xor_sync(FULL, best, d)); sum64 += __shfl_xor_sync(FULL, sum64, d); }

@@ -49,12 +49,13 @@ __device__ __forceinline__ uint32_t dup16(int v) { return __byte_perm((uint32_t)
 __device__ __forceinline__ uint32_t pack16(int lo, int hi) { return __byte_perm((uint32_t)lo, (uint32_t)hi, 0x5410); }
 
 template <int EHS>
-__device__ __forceinline__ void phase2x(const P2x& a, const Idct2Tables& T, uint32_t lane, uint32_t wid, unsigned long long& best, uint32_t& sum2)
+// best/bestm: this thread's brightest-pixel candidate so far, as (value, earliest raster position) key and as plain value;
+// the caller may keep them across tiles of one image (ties are resolved on the full key, so processing order does not matter).
+__device__ __forceinline__ void phase2x(const P2x& a, const Idct2Tables& T, uint32_t lane, uint32_t wid, unsigned long long& best, int& bestm, uint32_t& sum2)
 {
     constexpr int NC = 8 >> EHS;
     const uint32_t nwarps = blockDim.x >> 5;
     const uint32_t px = lane * 8;
-    int bestm = -0x7fffffff - 1;
     for (uint32_t rg = wid; rg * a.evc < a.mcu_h; rg += nwarps) {
         if (lane >= a.opr) continue;
         uint32_t cbw[4], crw[4];                  // replicated chroma, packed for the map stores (= per-pair chroma)
@@ -141,12 +142,12 @@ __device__ __forceinline__ void phase2x(const P2x& a, const Idct2Tables& T, uint
             // brightest pixel: first strict maximum of raw Y in raster order
             const uint32_t m2 = __vmaxs2(__vmaxs2(yw[0], yw[1]), __vmaxs2(yw[2], yw[3]));
             const int m = max((int)(short)(m2 & 0xFFFF), (int)m2 >> 16);
-            if (m > bestm) {            // strict: an equal value later in raster order does not replace the first one
-                bestm = m;
+            if (m >= bestm) {           // rare once the running maximum is high
                 int kf = 7;
                 #pragma unroll
                 for (int k = 7; k >= 0; k--) { const int yraw = (k & 1) ? ((int)yw[k >> 1] >> 16) : (int)(short)(yw[k >> 1] & 0xFFFF); if (yraw == m) kf = k; }
-                best = ((unsigned long long)(uint32_t)(m + 32768) << 32) | (0xffffffffu - (uint32_t)(mi + kf));
+                const unsigned long long key = ((unsigned long long)(uint32_t)(m + 32768) << 32) | (0xffffffffu - (uint32_t)(mi + kf));
+                if (key > best) { best = key; bestm = m; }      // equal value: the earlier raster position wins
             }
             uint4* dp = reinterpret_cast<uint4*>(a.dib + ((size_t)(a.hp - 1 - ay) * a.wp + ax) * 4);
             dp[0] = make_uint4(bgra[0], bgra[1], bgra[2], bgra[3]);
