@@ -37,62 +37,70 @@ __global__ void __launch_bounds__(MS_THREADS) k_marker_scan(DevBatch b)
     if (t == 0) seg_start[0] = 0;
     uint32_t found = 0;            // RST markers accepted so far (uniform after each iteration)
     uint32_t term = 0xffffffffu;
-    for (uint64_t base = 0; base < n; base += MS_THREADS * 16) {
-        __syncthreads();
+    // 64 bytes per thread and iteration (32 KB per CTA pass): three barriers per pass, so few of them per image
+    for (uint64_t base = 0; base < n; base += MS_THREADS * 64) {
         if (t == 0) s_term = 0xffffffffu;
         __syncthreads();
-        uint64_t off = base + (uint64_t)t * 16;
-        // 16 bytes per thread as four words (scan_off is 16-byte aligned); FF bytes are rare (~1/200), so
-        // test a whole word for "any byte == FF" first and only then look at its bytes.
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (off + 16 <= n) v = __ldg(reinterpret_cast<const uint4*>(p + off));
-        else { uint32_t w[4] = {0, 0, 0, 0}; for (int i = 0; i < 16; i++) if (off + i < n) w[i >> 2] |= (uint32_t)p[off + i] << (8 * (i & 3)); v = make_uint4(w[0], w[1], w[2], w[3]); }
-        uint32_t nextb = __shfl_down_sync(FULL, v.x, 1) & 0xFF;           // first byte of the next thread's chunk
-        if (lane == 31) nextb = (off + 16 < n) ? p[off + 16] : 0;
-        uint32_t mask = 0;         // bit i: RST marker starts at off+i
-        uint32_t myterm = 0xffffffffu;
-        const uint32_t ws[5] = {v.x, v.y, v.z, v.w, nextb};
+        const uint64_t off0 = base + (uint64_t)t * 64;
+        uint4 v[4];
         #pragma unroll
-        for (int wi = 0; wi < 4; wi++) {
-            const uint32_t w = ws[wi];
-            if (((~w - 0x01010101u) & w & 0x80808080u) == 0) continue;     // no byte of w is 0xFF
+        for (int c = 0; c < 4; c++) {
+            const uint64_t off = off0 + 16 * c;
+            v[c] = make_uint4(0, 0, 0, 0);
+            if (off + 16 <= n) v[c] = __ldg(reinterpret_cast<const uint4*>(p + off));        // scan_off is 16-byte aligned
+            else if (off < n) { uint32_t w[4] = {0, 0, 0, 0}; for (int i = 0; i < 16; i++) if (off + i < n) w[i >> 2] |= (uint32_t)p[off + i] << (8 * (i & 3)); v[c] = make_uint4(w[0], w[1], w[2], w[3]); }
+        }
+        uint32_t nextb = __shfl_down_sync(FULL, v[0].x, 1) & 0xFF;        // first byte of the next thread's chunk
+        if (lane == 31) nextb = (off0 + 64 < n) ? p[off0 + 64] : 0;
+        unsigned long long mask = 0;        // bit i: RST marker starts at off0+i
+        uint32_t myterm = 0xffffffffu;
+        #pragma unroll
+        for (int c = 0; c < 4; c++) {
+            // FF bytes are rare (~1/200): test a whole word for "any byte == FF" first and only then look at its bytes
+            const uint32_t ws[5] = {v[c].x, v[c].y, v[c].z, v[c].w, (c < 3) ? v[c < 3 ? c + 1 : 3].x : nextb};
             #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                if (((w >> (8 * j)) & 0xFF) != 0xFF) continue;
-                const int i = wi * 4 + j;
-                if (off + i + 1 >= n) continue;
-                const uint32_t m = (j < 3) ? ((w >> (8 * j + 8)) & 0xFF) : (ws[wi + 1] & 0xFF);
-                if (m >= 0xD0 && m <= 0xD7) mask |= 1u << i;
-                else if (m != 0x00 && m != 0xFF && myterm == 0xffffffffu) myterm = (uint32_t)(off + i);
+            for (int wi = 0; wi < 4; wi++) {
+                const uint32_t w = ws[wi];
+                if (((~w - 0x01010101u) & w & 0x80808080u) == 0) continue;     // no byte of w is 0xFF
+                #pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (((w >> (8 * j)) & 0xFF) != 0xFF) continue;
+                    const int i = c * 16 + wi * 4 + j;
+                    if (off0 + i + 1 >= n) continue;
+                    const uint32_t m = (j < 3) ? ((w >> (8 * j + 8)) & 0xFF) : (ws[wi + 1] & 0xFF);
+                    if (m >= 0xD0 && m <= 0xD7) mask |= 1ull << i;
+                    else if (m != 0x00 && m != 0xFF && myterm == 0xffffffffu) myterm = (uint32_t)(off0 + i);
+                }
             }
         }
         if (myterm != 0xffffffffu) atomicMin(&s_term, myterm);
         __syncthreads();
         term = s_term;
         if (term != 0xffffffffu) {          // drop markers at/after the terminating marker
-            #pragma unroll
-            for (int i = 0; i < 16; i++) if ((mask >> i & 1) && off + i >= term) mask &= ~(1u << i);
+            if (off0 >= term) mask = 0;
+            else if (term - off0 < 64) mask &= (1ull << (uint32_t)(term - off0)) - 1ull;
         }
-        uint32_t cnt = __popc(mask);
+        uint32_t cnt = __popcll(mask);
         // block exclusive scan of cnt
         uint32_t inc = cnt;
         #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { uint32_t v = __shfl_up_sync(FULL, inc, d); if (lane >= d) inc += v; }
+        for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(FULL, inc, d); if (lane >= d) inc += y; }
         if (lane == 31) s_warp[wid] = inc;
         __syncthreads();
         uint32_t wbase = 0, total = 0;
         #pragma unroll
-        for (int w = 0; w < MS_THREADS / 32; w++) { uint32_t v = s_warp[w]; if (w < wid) wbase += v; total += v; }
+        for (int w = 0; w < MS_THREADS / 32; w++) { uint32_t y = s_warp[w]; if (w < wid) wbase += y; total += y; }
         uint32_t rank = found + wbase + inc - cnt;
         while (mask) {
-            int i = __ffs(mask) - 1; mask &= mask - 1;
-            uint32_t pos = (uint32_t)(off + i);
+            int i = __ffsll((long long)mask) - 1; mask &= mask - 1;
+            uint32_t pos = (uint32_t)(off0 + i);
             if (rank < im.nseg) seg_end[rank] = pos;
             if (rank + 1 < im.nseg) seg_start[rank + 1] = pos + 2;
             rank++;
         }
         found += total;
         if (term != 0xffffffffu) break;
+        __syncthreads();                    // s_warp / s_term are rewritten by the next pass
     }
     __syncthreads();
     if (t == 0) {

@@ -73,6 +73,18 @@ def test_unusual_tables_and_layouts_match_oracle(built, huff):
         assert not JC.compare(orc.decode(j), got, what=("geom", "pix_y", "pix_cb", "pix_cr", "dib", "mcu_map", "blk_dc", "dht_histo")), name
 
 
+@pytest.mark.parametrize("huff", [1, 2], ids=["warp", "lane"])
+def test_dc_only_mode_matches_oracle(built, cases, huff):
+    """CSnoopConfig::bDecodeScanImgAc = false: AC symbols are parsed but not stored (ImgDecode.cpp:1759-1766)."""
+    from jpegsnoop_b200 import CimgDecode
+    orc = Oracle("ref_fixed", decode_ac=False) if ref_available("fixed") else Oracle("port", idct_fixed=True, decode_ac=False)
+    dec = CimgDecode(decode_ac=False, idct_fixedpt=True, huff_kernel=huff, idct_kernel=0)
+    for name, j in cases[:6] + JC.mini_cases()[:2]:
+        want = orc.decode(j); got = dec.decode(j)
+        assert got.nerr == 0 and want.nerr == 0, (name, dec.log_lines(3))
+        assert not JC.compare(want, got), name
+
+
 def test_host_marker_walk_equals_device_marker_scan(built, cases):
     from jpegsnoop_b200 import BatchDecoder
     jpegs = [j for _, j in cases]
