@@ -393,12 +393,19 @@ struct Win {
         hi = __ldg(base); lo = __ldg(base + 1);
         nx = __ldg(base + 2); idx = 3; nb = 64;
     }
-    __device__ __forceinline__ void refill() {            // precondition: 6 <= nb <= 32
-        const uint32_t x = nx;
-        nx = __ldg(base + idx); idx++;
-        hi |= __funnelshift_rc(x, 0, nb);                  // x >> nb, 0 when nb == 32
-        lo = __funnelshift_rc(0, x, nb);                   // x << (32 - nb), x when nb == 32
-        nb += 32;
+    // Top up when 32 bits or fewer are left (6 <= nb then).  The look-ahead word is reloaded IN PLACE by a
+    // predicated load: written as a C++ conditional, the compiler loads into a temporary and copies it into
+    // `nx` at the end of the same step, i.e. waits for the global load it was supposed to hide (22 % of the
+    // kernel's stall samples in the round-1 profile).
+    __device__ __forceinline__ void refill_if_low() {
+        const uint32_t need = (nb <= 32) ? 1u : 0u;
+        if (need) {
+            hi |= __funnelshift_rc(nx, 0, nb);             // nx >> nb, 0 when nb == 32
+            lo = __funnelshift_rc(0, nx, nb);              // nx << (32 - nb), nx when nb == 32
+            nb += 32;
+        }
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.global.nc.u32 %0, [%1];\n\t}" : "+r"(nx) : "l"(base + idx), "r"(need));
+        idx += need;
     }
     __device__ __forceinline__ void consume(uint32_t n) { hi = __funnelshift_l(lo, hi, n); lo <<= n; nb -= (int)n; }
     __device__ __forceinline__ uint32_t consumed() const { return 32u * (idx - 1) - (uint32_t)nb; }
@@ -493,7 +500,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 3) k_huff_lane(DevBatch b)
                     uint32_t pos = 64;
                     if (active) {
                         // ---- DC symbol ----
-                        if (s.nb <= 32) s.refill();
+                        s.refill_if_low();
                         uint32_t e = lut_dc[s.hi >> (32 - JS_LUT_BITS)];
                         if (e & 0x8000) e = lut_dc[JS_LUT_SIZE + (e & 0x7FFF) + ((s.hi >> 16) & ((1u << JS_LUT2_BITS) - 1))];
                         if (e == 0) { status |= 1; active = false; }
@@ -501,7 +508,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 3) k_huff_lane(DevBatch b)
                             const uint32_t len = e >> 8, run = (e >> 4) & 15, size = e & 15;
                             if (HISTO) atomicAdd(&sh.histo[c * 2][len], 1u);
                             s.consume(len);
-                            if (s.nb <= 32) s.refill();          // a 16-bit code + 16 value bits can exceed what is left
+                            s.refill_if_low();          // a 16-bit code + 16 value bits can exceed what is left
                             const uint32_t t = s.hi;
                             const uint32_t v = (size == 0) ? 0u : (t >> (32 - size));
                             int val = (int)v - (((int)~t >> 31) & (int)((1u << size) - 1));
@@ -520,7 +527,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 3) k_huff_lane(DevBatch b)
                     uint32_t emin = 0xffffffffu;                 // an entry of 0 (no code has this prefix) also ends the block like an EOB
                     auto ac_step = [&]() {
 
-                            if (s.nb <= 32) s.refill();
+                            s.refill_if_low();
                             uint32_t e = lut_ac[s.hi >> (32 - JS_LUT_BITS)];
                             if (e & 0x8000) e = lut_ac[JS_LUT_SIZE + (e & 0x7FFF) + ((s.hi >> 16) & ((1u << JS_LUT2_BITS) - 1))];
                             const uint32_t len = e >> 8, size = e & 15, run = (e >> 4) & 15;
