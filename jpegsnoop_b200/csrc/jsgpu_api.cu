@@ -401,7 +401,7 @@ int jsgpu_batch_begin(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, 
     CK(ctx->d_img.reserve(sizeof(DevImage) * (size_t)n));
     CK(ctx->d_items.reserve(sizeof(uint2) * std::max<size_t>(items.size(), 1)));
     CK(ctx->d_bits.reserve(bitstream_bytes + 64));
-    CK(ctx->d_ubits.reserve(ub + 256));
+    CK(ctx->d_ubits.reserve(ub + 16384));          // + slack: a reader of corrupt data stops at the next MCU boundary, at most one MCU (<= 12 KB of bits) past the end
     CK(ctx->d_litems.reserve(sizeof(uint2) * std::max<size_t>(litems.size(), 1)));
     CK(ctx->d_tiles.reserve(sizeof(uint4) * std::max<size_t>(tiles.size(), 1)));
     CK(ctx->d_seg64.reserve(8 * (size_t)seg + 16));

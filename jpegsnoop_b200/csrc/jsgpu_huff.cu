@@ -268,6 +268,7 @@ __global__ void __launch_bounds__(JS_HUFF_WARPS * 32) k_huff_warp(DevBatch b)
         uint32_t* const coef32 = reinterpret_cast<uint32_t*>(b.coef);
         const bool want_ac = b.decode_ac != 0;
         for (uint32_t m = m0; m < m1 && !(status & 7); m++) {
+            if (s.consumed() > ulen * 8) { status |= 2; break; }       // ran off the end of the interval (corrupt or truncated data): stop reading
             if (lane == 0) b.mcu_bitpos[gim.mcu_off + m] = s.consumed();
             #pragma unroll 1
             for (uint32_t c = 0; c < ns; c++) {
@@ -480,9 +481,11 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 3) k_huff_lane(DevBatch b)
         int dc0 = 0, dc1 = 0, dc2 = 0;
         uint32_t status = 0;
         const uint32_t nm_max = min(ri, nmcu - kbase * ri);         // longest interval in this warp (the first lane's)
+        const uint32_t avail = b.seg_ulen[sidx] * 8;
         #pragma unroll 1
         for (uint32_t mi = 0; mi < nm_max; mi++) {
-            const bool mlive = (mi < nm) && !(status & 7);
+            bool mlive = (mi < nm) && !(status & 7);
+            if (mlive && s.consumed() > avail) { status |= 2; mlive = false; }     // ran off the end of the interval (corrupt or truncated data): stop reading
             if (mlive) b.mcu_bitpos[gim.mcu_off + m0 + mi] = s.consumed();
             #pragma unroll 1
             for (uint32_t c = 0; c < ns; c++) {
@@ -590,8 +593,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 3) k_huff_lane(DevBatch b)
             if (++mx == mcu_xmax) { mx = 0; my++; }
         }
         if (live) {
-            const uint32_t ulen = b.seg_ulen[sidx];
-            uint32_t consumed = s.consumed(), avail = ulen * 8;
+            const uint32_t consumed = s.consumed();
             if (consumed > avail) status |= 2;
             else if (!(status & 5) && avail - consumed >= 8) status |= 16;
             b.seg_endbits[sidx] = consumed;

@@ -85,6 +85,36 @@ def test_dc_only_mode_matches_oracle(built, cases, huff):
         assert not JC.compare(want, got), name
 
 
+@pytest.mark.parametrize("huff", [1, 2], ids=["warp", "lane"])
+def test_corrupt_streams_are_reported_not_fatal(built, cases, huff):
+    """Truncated / bit-flipped / zero-filled scans: every kernel terminates, the damaged images carry a non-zero
+    status (m_bScanBad), and a healthy image in the same batch is still bit-exact (the
+    reference's bit-by-bit resynchronisation itself is not reproduced)."""
+    from jpegsnoop_b200 import BatchDecoder, CimgDecode
+    rng = np.random.default_rng(5)
+    good_name, good = cases[2]                               # 1080p 4:2:0 DRI=4
+    nodri = cases[3][1]                                      # no restart markers: one long interval
+    sos = good.index(b"\xff\xda"); body0 = sos + 14
+    def flipped(j, n):
+        a = bytearray(j); lo = j.index(b"\xff\xda") + 14
+        for p in rng.integers(lo, len(j) - 2, n): a[p] ^= 1 << int(rng.integers(0, 8))
+        return bytes(a)
+    bad = [good[: body0 + (len(good) - body0) // 2] + b"\xff\xd9",                 # truncated in the middle of the scan
+           flipped(good, 200), flipped(nodri, 40),
+           good[: body0 + 5000] + bytes(len(good) - body0 - 5002) + b"\xff\xd9",    # tail zero-filled
+           nodri[: len(nodri) // 2]]                                                # cut, no EOI
+    bd = BatchDecoder(huff_kernel=huff, idct_kernel=0)
+    bd.set_batch(bad + [good]); bd.decode(); bd.sync()
+    st = [bd.fetch(i).status for i in range(len(bad) + 1)]
+    assert all(x != 0 for x in st[:-1]), st
+    assert st[-1] == 0, st
+    orc = _oracle(True)
+    assert not JC.compare(orc.decode(good), bd.fetch(len(bad)), what=("pix_y", "pix_cb", "pix_cr", "dib", "mcu_map", "blk_dc", "dht_histo")), good_name
+    dec = CimgDecode(idct_fixedpt=True, huff_kernel=huff, idct_kernel=0)
+    assert dec.decode(bad[0]).nerr > 0
+    assert not JC.compare(orc.decode(good), dec.decode(good)), "decode after a damaged image"
+
+
 def test_host_marker_walk_equals_device_marker_scan(built, cases):
     from jpegsnoop_b200 import BatchDecoder
     jpegs = [j for _, j in cases]
