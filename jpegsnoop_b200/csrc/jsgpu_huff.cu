@@ -496,8 +496,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 3) k_huff_lane(DevBatch b)
                 const uint32_t ehc = gim.eh[c], evc = gim.ev[c], blk_xmax = gim.blk_xmax, mcu_ymax = gim.mcu_ymax;
                 int16_t* const blkmap = ((c == 0) ? b.blk_y : (c == 1) ? b.blk_cb : b.blk_cr) + gim.blk_off;
                 int dc = (c == 0) ? dc0 : (c == 1) ? dc1 : dc2;
-                #pragma unroll 1
                 uint32_t bh = 0, bv = 0;
+                #pragma unroll 1
                 for (uint32_t bi = 0; bi < nh * nv; bi++) {
                     bool active = mlive && !(status & 7);
                     uint32_t pos = 64;
