@@ -217,6 +217,17 @@ def main():
     ms_max = float(t.item()); total_px = float(npx.item())
     value = total_px * args.steps / (ms_max / 1e3) / 1e6
 
+    # ---- bit-exactness spot check against the CPU oracle on images spread over the batch (rank 0) -----------
+    checked = []; parity_ok = True; orc = None
+    if rank == 0:
+        from oracle_util import Oracle, ref_available
+        import jpeg_cases as JC
+        orc = Oracle("ref_fixed") if ref_available("fixed") else Oracle("port", idct_fixed=True)
+        WHAT = ("geom", "pix_y", "pix_cb", "pix_cr", "dib", "mcu_map", "blk_dc", "dht_histo")
+        for i in sorted(set([0, nimg // 3, (2 * nimg) // 3, nimg - 1])):
+            bad = JC.compare(orc.decode(bytes(jpegs[i])), bd.fetch(i), what=WHAT)
+            checked.append(i); parity_ok = parity_ok and not bad
+
     # ---- end-to-end: host buffers in/out through the one-call C-ABI --------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -251,7 +262,13 @@ def main():
                 dist.all_reduce(te, op=dist.ReduceOp.MAX)
             e2e = {"value": round(total_px * args.e2e_steps / float(te.item()) / 1e6, 1), "unit": UNIT,
                    "h2d_bytes_per_step": int(bits.size), "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps,
-                   "what": "jsgpu_decode_batch_host: pinned bitstream -> all reference outputs in pinned host memory"}
+                   "what": "jsgpu_decode_batch_host: pinned bitstream -> all reference outputs in pinned host memory "
+                           "(4 image ranges, D2H of one overlapping upload+decode of the next)"}
+            if rank == 0:                                 # the host buffers themselves against the oracle
+                ok = True
+                for i in checked:
+                    ok = ok and not JC.compare(orc.decode(bytes(jpegs[i])), bd.fetch_host(i, outs), what=WHAT)
+                e2e["host_buffers_bit_exact_vs_oracle"] = bool(ok)
         else:
             e2e = {"value": None, "unit": UNIT, "error": "pinned host allocation failed"}
 
@@ -281,14 +298,6 @@ def main():
                 "stage_ms": {"marker_scan+unstuff": round(float(stage_ms[0]), 3), "huffman": round(huff_ms, 3),
                              "idct+colour": round(idct_ms, 3), "finalize": round(float(stage_ms[3]), 3), "step_total": round(float(stage_ms[4]), 3)},
                 "huffman_achieved_gbs": round(huff_gbs, 1)}
-        # bit-exactness spot check against the CPU oracle on images spread over the batch
-        from oracle_util import Oracle, ref_available
-        import jpeg_cases as JC
-        orc = Oracle("ref_fixed") if ref_available("fixed") else Oracle("port", idct_fixed=True)
-        checked = []; parity_ok = True
-        for i in sorted(set([0, nimg // 3, (2 * nimg) // 3, nimg - 1])):
-            bad = JC.compare(orc.decode(bytes(jpegs[i])), bd.fetch(i), what=("geom", "pix_y", "pix_cb", "pix_cr", "dib", "mcu_map", "blk_dc", "dht_histo"))
-            checked.append(i); parity_ok = parity_ok and not bad
         cb = None
         if not args.no_cpu and world == 1:          # the CPU leg is reported at N=1 only (the reference arm covers N>1)
             cb, _, _ = cpu_baseline(jpegs, w * h)

@@ -54,6 +54,11 @@ struct jsgpu_ctx {
     alignas(64) unsigned char tmap[128]; bool tmap_ok = false;
     uint32_t n_nonstd = 0, n_std = 0;
     int launches = 0;
+    // host copies of the configuration, replayed into the chunk contexts of jsgpu_decode_batch_host
+    std::vector<jsgpu_tables> h_sets; std::vector<int32_t> h_li; std::vector<float> h_lf;
+    std::vector<jsgpu_ctx*> kids;            // chunk contexts (own stream and pools), created on first use
+    bool plan_only = false;                  // batch_begin computes the layout only (the chunk contexts own the device pools)
+    bool host_delivered = false;             // the last decode went straight to host buffers: nothing to download from this context
     float ms[5] = {0, 0, 0, 0, 0};
 };
 
@@ -112,6 +117,8 @@ int jsgpu_init(int device, jsgpu_ctx** out)
 void jsgpu_free(jsgpu_ctx* ctx)
 {
     if (!ctx) return;
+    for (jsgpu_ctx* k : ctx->kids) jsgpu_free(k);
+    ctx->kids.clear();
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = { &ctx->d_ctab, &ctx->d_li, &ctx->d_lf, &ctx->d_sym, &ctx->d_tables, &ctx->d_img, &ctx->d_items, &ctx->d_litems, &ctx->d_tiles, &ctx->d_ubits, &ctx->d_seg64, &ctx->d_bits, &ctx->d_seg,
@@ -172,6 +179,7 @@ int jsgpu_set_idct_tables(jsgpu_ctx* ctx, const int32_t* li, const float* lf)
     IdctSym* sym = new IdctSym;
     ctx->sym_ok = build_idct_sym(li, *sym);
     ctx->baked_ok = js_idct_baked_matches(li) != 0;
+    ctx->h_li.assign(li, li + 64 * 64); ctx->h_lf.assign(lf, lf + 64 * 64);
     {   // table source of the LDG tile kernel: env override for experiments, else immediates when the baked copy matches
         const char* e = getenv("JSGPU_IDCT_TABLE");
         ctx->tab_mode = e ? atoi(e) : (ctx->baked_ok ? 2 : 0);
@@ -279,6 +287,7 @@ int jsgpu_upload_tables(jsgpu_ctx* ctx, const jsgpu_tables* sets, uint32_t nsets
     cudaSetDevice(ctx->device);
     std::vector<DevTableSet> h(nsets);
     for (uint32_t i = 0; i < nsets; i++) build_table_set(sets[i], h[i]);
+    ctx->h_sets.assign(sets, sets + nsets);
     CK(ctx->d_tables.reserve(sizeof(DevTableSet) * (size_t)nsets));
     CK(cudaMemcpyAsync(ctx->d_tables.p, h.data(), sizeof(DevTableSet) * (size_t)nsets, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -397,6 +406,8 @@ int jsgpu_batch_begin(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, 
     for (int k = 0; k < 3; k++) { tcls_first[k] = (uint32_t)tiles.size(); tcls_count[k] = (uint32_t)tcls[k].size(); tiles.insert(tiles.end(), tcls[k].begin(), tcls[k].end()); }
     ctx->bits_len = bitstream_bytes; ctx->pix_total = pix; ctx->dib_total = dib; ctx->blk_total = blk; ctx->mcu_total = mcu;
     ctx->coef_rows = rows; ctx->max_scan_len = max_scan; ctx->ubits_total = ub; ctx->n_std = n_std; ctx->n_nonstd = n_nonstd;
+    ctx->host_delivered = false;
+    if (ctx->plan_only) { ctx->planned = true; return JSGPU_OK; }
     // allocate
     CK(ctx->d_img.reserve(sizeof(DevImage) * (size_t)n));
     CK(ctx->d_items.reserve(sizeof(uint2) * std::max<size_t>(items.size(), 1)));
@@ -451,7 +462,7 @@ int jsgpu_batch_layout(jsgpu_ctx* ctx, jsgpu_image_layout* out, uint32_t n)
     if (!ctx || !out) return JSGPU_EINVAL;
     if (!ctx->planned) return fail(ctx, JSGPU_ESTATE, "no batch planned");
     if (n > ctx->layout.size()) n = (uint32_t)ctx->layout.size();
-    if (ctx->decoded) {
+    if (ctx->decoded && !ctx->host_delivered) {
         cudaSetDevice(ctx->device);
         std::vector<uint32_t> st(ctx->layout.size());
         CK(cudaMemcpyAsync(st.data(), ctx->batch.img_status, st.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -466,6 +477,7 @@ int jsgpu_batch_pools(jsgpu_ctx* ctx, jsgpu_pools* out)
 {
     if (!ctx || !out) return JSGPU_EINVAL;
     if (!ctx->planned) return fail(ctx, JSGPU_ESTATE, "no batch planned");
+    if (ctx->host_delivered) return fail(ctx, JSGPU_ESTATE, "the last batch was delivered to host buffers by jsgpu_decode_batch_host");
     const DevBatch& b = ctx->batch;
     out->pix_y = b.pix_y; out->pix_cb = b.pix_cb; out->pix_cr = b.pix_cr; out->dib = b.dib;
     out->blk_y = b.blk_y; out->blk_cb = b.blk_cb; out->blk_cr = b.blk_cr; out->mcu_map = b.mcu_map;
@@ -626,6 +638,7 @@ int jsgpu_batch_download(jsgpu_ctx* ctx, int which, uint32_t image, void* dst, u
 {
     if (!ctx || !dst) return JSGPU_EINVAL;
     if (!ctx->decoded) return fail(ctx, JSGPU_ESTATE, "nothing decoded yet");
+    if (ctx->host_delivered) return fail(ctx, JSGPU_ESTATE, "the last batch was delivered to host buffers by jsgpu_decode_batch_host");
     if (image >= ctx->himg.size()) return fail(ctx, JSGPU_EINVAL, "image index out of range");
     cudaSetDevice(ctx->device);
     const DevImage& im = ctx->himg[image]; const DevBatch& b = ctx->batch;
@@ -652,15 +665,14 @@ int jsgpu_batch_download(jsgpu_ctx* ctx, int which, uint32_t image, void* dst, u
     return JSGPU_OK;
 }
 
-int jsgpu_decode_batch_host(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, const uint8_t* bits, uint64_t bytes,
-                            const jsgpu_host_outputs* out)
+// One context, one stream: upload, decode, pooled D2H (each pool is one contiguous copy in batch order).
+static int decode_host_single(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, const uint8_t* bits, uint64_t bytes,
+                              const jsgpu_host_outputs* out, bool wait)
 {
-    if (!ctx || !imgs || !bits || !out) return JSGPU_EINVAL;
     int r = jsgpu_batch_begin(ctx, imgs, n, bytes); if (r) return r;
     r = jsgpu_batch_upload(ctx, bits, bytes); if (r) return r;
     r = jsgpu_batch_decode(ctx); if (r) return r;
     const DevBatch& b = ctx->batch; cudaStream_t s = ctx->stream;
-    // pooled D2H: each pool is one contiguous copy in batch order
     if (out->pix_y)  CK(cudaMemcpyAsync(out->pix_y,  b.pix_y,  ctx->pix_total * 2, cudaMemcpyDeviceToHost, s));
     if (out->pix_cb) CK(cudaMemcpyAsync(out->pix_cb, b.pix_cb, ctx->pix_total * 2, cudaMemcpyDeviceToHost, s));
     if (out->pix_cr) CK(cudaMemcpyAsync(out->pix_cr, b.pix_cr, ctx->pix_total * 2, cudaMemcpyDeviceToHost, s));
@@ -671,7 +683,76 @@ int jsgpu_decode_batch_host(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32
     if (out->mcu_map) CK(cudaMemcpyAsync(out->mcu_map, b.mcu_map, ctx->mcu_total * 4, cudaMemcpyDeviceToHost, s));
     if (out->dht_histo) CK(cudaMemcpyAsync(out->dht_histo, b.histo, (size_t)n * 2 * 4 * 17 * 4, cudaMemcpyDeviceToHost, s));
     if (out->stats)  CK(cudaMemcpyAsync(out->stats, b.stats, (size_t)n * 16 * 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    if (wait) CK(cudaStreamSynchronize(s));
+    return JSGPU_OK;
+}
+
+// Host bitstream in, every reference output in host buffers out.  A large batch is cut into JS_HOST_CHUNKS image
+// ranges, each on its own stream with its own pools: the device-to-host copy of one range (PCIe-bound, ~97 % of the
+// call) overlaps upload and decode of the next ones.  Afterwards this context holds the batch LAYOUT (and statuses)
+// only; the device pools belong to the chunk contexts, so jsgpu_batch_download()/pools() report JSGPU_ESTATE.
+#define JS_HOST_CHUNKS 4
+int jsgpu_decode_batch_host(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, const uint8_t* bits, uint64_t bytes,
+                            const jsgpu_host_outputs* out)
+{
+    if (!ctx || !imgs || !bits || !out) return JSGPU_EINVAL;
+    static const uint64_t min_bytes = getenv("JSGPU_HOST_CHUNK_MIN_BYTES") ? strtoull(getenv("JSGPU_HOST_CHUNK_MIN_BYTES"), nullptr, 10) : (64ull << 20);
+    bool chunked = n >= 4 * JS_HOST_CHUNKS && bytes >= min_bytes && !ctx->h_sets.empty() && !ctx->h_li.empty();
+    for (uint32_t i = 1; chunked && i < n; i++)             // chunk bitstreams must be contiguous, 16-byte aligned ranges
+        if (imgs[i].scan_offset < imgs[i - 1].scan_offset + imgs[i - 1].scan_length || (imgs[i].scan_offset & 15)) chunked = false;
+    if (chunked && ((imgs[0].scan_offset & 15) || imgs[n - 1].scan_offset + imgs[n - 1].scan_length > bytes)) chunked = false;
+    if (!chunked) return decode_host_single(ctx, imgs, n, bits, bytes, out, true);
+
+    // global layout (offsets of every image in the host pools) without device allocations
+    ctx->plan_only = true;
+    int r = jsgpu_batch_begin(ctx, imgs, n, bytes);
+    ctx->plan_only = false;
+    if (r) return r;
+    while (ctx->kids.size() < JS_HOST_CHUNKS) {
+        jsgpu_ctx* k = nullptr;
+        r = jsgpu_init(ctx->device, &k); if (r) return fail(ctx, r, "chunk context: %s", jsgpu_strerror(r));
+        ctx->kids.push_back(k);
+    }
+    std::vector<jsgpu_image_desc> d;
+    for (uint32_t c = 0; c < JS_HOST_CHUNKS; c++) {
+        jsgpu_ctx* k = ctx->kids[c];
+        const uint32_t i0 = (uint32_t)((uint64_t)n * c / JS_HOST_CHUNKS), i1 = (uint32_t)((uint64_t)n * (c + 1) / JS_HOST_CHUNKS);
+        // (re)configure the chunk context like this one
+        jsgpu_options o = ctx->opt;
+        r = jsgpu_set_options(k, &o); if (r) return fail(ctx, r, "%s", k->err.c_str());
+        if (!k->have_idct || k->h_li != ctx->h_li) { r = jsgpu_set_idct_tables(k, ctx->h_li.data(), ctx->h_lf.data()); if (r) return fail(ctx, r, "%s", k->err.c_str()); }
+        if (k->h_sets.size() != ctx->h_sets.size() || memcmp(k->h_sets.data(), ctx->h_sets.data(), sizeof(jsgpu_tables) * ctx->h_sets.size()) != 0) {
+            r = jsgpu_upload_tables(k, ctx->h_sets.data(), (uint32_t)ctx->h_sets.size()); if (r) return fail(ctx, r, "%s", k->err.c_str());
+        }
+        const uint64_t base = imgs[i0].scan_offset, end = imgs[i1 - 1].scan_offset + imgs[i1 - 1].scan_length;
+        d.assign(imgs + i0, imgs + i1);
+        for (auto& x : d) x.scan_offset -= base;
+        const DevImage& f = ctx->himg[i0];                   // first image of the chunk: its offsets in the global pools
+        jsgpu_host_outputs o2 = {};
+        o2.pix_y  = out->pix_y  ? (int16_t*)out->pix_y  + f.pix_off : nullptr;
+        o2.pix_cb = out->pix_cb ? (int16_t*)out->pix_cb + f.pix_off : nullptr;
+        o2.pix_cr = out->pix_cr ? (int16_t*)out->pix_cr + f.pix_off : nullptr;
+        o2.dib    = out->dib    ? (uint8_t*)out->dib    + f.dib_off : nullptr;
+        o2.blk_y  = out->blk_y  ? (int16_t*)out->blk_y  + f.blk_off : nullptr;
+        o2.blk_cb = out->blk_cb ? (int16_t*)out->blk_cb + f.blk_off : nullptr;
+        o2.blk_cr = out->blk_cr ? (int16_t*)out->blk_cr + f.blk_off : nullptr;
+        o2.mcu_map   = out->mcu_map   ? (uint32_t*)out->mcu_map + f.mcu_off : nullptr;
+        o2.dht_histo = out->dht_histo ? (uint32_t*)out->dht_histo + (size_t)i0 * 2 * 4 * 17 : nullptr;
+        o2.stats     = out->stats     ? (int32_t*)out->stats + (size_t)i0 * 16 : nullptr;
+        r = decode_host_single(k, d.data(), i1 - i0, bits + base, end - base, &o2, false);
+        if (r) return fail(ctx, r, "chunk %u: %s", c, k->err.c_str());
+    }
+    ctx->launches = 0;
+    for (uint32_t c = 0; c < JS_HOST_CHUNKS; c++) {
+        jsgpu_ctx* k = ctx->kids[c];
+        CK(cudaStreamSynchronize(k->stream));
+        const uint32_t i0 = (uint32_t)((uint64_t)n * c / JS_HOST_CHUNKS), i1 = (uint32_t)((uint64_t)n * (c + 1) / JS_HOST_CHUNKS);
+        std::vector<jsgpu_image_layout> lo(i1 - i0);
+        r = jsgpu_batch_layout(k, lo.data(), i1 - i0); if (r) return fail(ctx, r, "%s", k->err.c_str());
+        for (uint32_t i = i0; i < i1; i++) ctx->layout[i].status = lo[i - i0].status;
+        ctx->launches += k->launches;
+    }
+    ctx->decoded = true; ctx->host_delivered = true;
     return JSGPU_OK;
 }
 

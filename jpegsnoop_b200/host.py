@@ -262,6 +262,28 @@ class BatchDecoder:
         a = np.zeros(shape, dtype)
         self._ck(self.L.jsgpu_batch_download(self.ctx, which, i, a.ctypes.data, a.nbytes)); return a
 
+    def fetch_host(self, i, outs):
+        """The same DecodedImage as fetch(), cut out of the host buffers a decode_host() call filled."""
+        self.refresh_layout()
+        lo = self.layout[i]; d = DecodedImage()
+        d.geom = np.array([lo.mcu_w, lo.mcu_h, lo.mcu_xmax, lo.mcu_ymax, lo.blk_xmax, lo.blk_ymax, lo.img_x, lo.img_y], np.uint32)
+        Wp, Hp = int(lo.img_x), int(lo.img_y); nblk = int(lo.blk_xmax) * int(lo.blk_ymax); nmcu = int(lo.mcu_xmax) * int(lo.mcu_ymax)
+        ns = self.descs[i].num_sos_comps
+        po, do, bo, mo = int(lo.pix_off), int(lo.dib_off), int(lo.blk_off), int(lo.mcu_off)
+        cut = lambda a, off, n, shape: np.array(a[off:off + n]).reshape(shape)
+        d.pix_y = cut(outs["pix_y"], po, Wp * Hp, (Hp, Wp))
+        d.pix_cb = cut(outs["pix_cb"], po, Wp * Hp, (Hp, Wp)) if ns == 3 else None
+        d.pix_cr = cut(outs["pix_cr"], po, Wp * Hp, (Hp, Wp)) if ns == 3 else None
+        d.dib = cut(outs["dib"], do, Wp * Hp * 4, (Hp, Wp, 4))
+        d.mcu_map = cut(outs["mcu_map"], mo, nmcu, (nmcu,))
+        d.blk_dc = (cut(outs["blk_y"], bo, nblk, (nblk,)),
+                    cut(outs["blk_cb"], bo, nblk, (nblk,)) if ns == 3 else None,
+                    cut(outs["blk_cr"], bo, nblk, (nblk,)) if ns == 3 else None)
+        d.dht_histo = cut(outs["dht_histo"], i * 136, 136, (2, 4, 17))
+        d.stats = cut(outs["stats"], i * 16, 16, (16,))
+        d.status = int(lo.status)
+        return d
+
     def fetch(self, i):
         self.refresh_layout()
         lo = self.layout[i]; d = DecodedImage()

@@ -1,6 +1,10 @@
 import os
 import sys
+import os
 import pytest
+
+# let small test batches take the chunked (overlapped) path of jsgpu_decode_batch_host too
+os.environ.setdefault("JSGPU_HOST_CHUNK_MIN_BYTES", "0")
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

@@ -115,6 +115,33 @@ def test_corrupt_streams_are_reported_not_fatal(built, cases, huff):
     assert not JC.compare(orc.decode(good), dec.decode(good)), "decode after a damaged image"
 
 
+@pytest.mark.parametrize("nrep", [1, 2], ids=["single_stream_15", "chunked_30"])
+def test_decode_batch_host_matches_oracle(built, cases, nrep):
+    """jsgpu_decode_batch_host (the end-to-end entry point): host bitstream in, host buffers out; with >= 16 images
+    it runs as 4 overlapped image ranges on separate streams (tests/conftest.py drops the size threshold)."""
+    from jpegsnoop_b200 import BatchDecoder
+    allc = (list(cases) + JC.mini_cases()) * nrep
+    jpegs = [j for _, j in allc]
+    bd = BatchDecoder(huff_kernel=0, idct_kernel=0)
+    tarr, darr, bits = bd.prepare(jpegs)
+    bd.set_tables(tarr); bd.plan(darr, bits.size)
+    lay = bd.layout
+    pix_n = sum((int(l.img_x) * int(l.img_y) + 63) // 64 * 64 for l in lay)
+    dib_n = sum((int(l.img_x) * int(l.img_y) * 4 + 255) // 256 * 256 for l in lay)
+    blk_n = sum((int(l.blk_xmax) * int(l.blk_ymax) + 63) // 64 * 64 for l in lay)
+    mcu_n = sum((int(l.mcu_xmax) * int(l.mcu_ymax) + 31) // 32 * 32 for l in lay)
+    outs = {"pix_y": np.zeros(pix_n, np.int16), "pix_cb": np.zeros(pix_n, np.int16), "pix_cr": np.zeros(pix_n, np.int16),
+            "dib": np.zeros(dib_n, np.uint8), "blk_y": np.zeros(blk_n, np.int16), "blk_cb": np.zeros(blk_n, np.int16),
+            "blk_cr": np.zeros(blk_n, np.int16), "mcu_map": np.zeros(mcu_n, np.uint32),
+            "dht_histo": np.zeros(len(jpegs) * 136, np.uint32), "stats": np.zeros(len(jpegs) * 16, np.int32)}
+    bd.decode_host(darr, bits, outs)
+    orc = _oracle(True)
+    for i, (name, j) in enumerate(allc):
+        got = bd.fetch_host(i, outs)
+        assert got.status == 0, (name, got.status)
+        assert not JC.compare(orc.decode(j), got, what=("geom", "pix_y", "pix_cb", "pix_cr", "dib", "mcu_map", "blk_dc", "dht_histo")), (i, name)
+
+
 def test_host_marker_walk_equals_device_marker_scan(built, cases):
     from jpegsnoop_b200 import BatchDecoder
     jpegs = [j for _, j in cases]
