@@ -596,6 +596,7 @@ int jsgpu_batch_decode(jsgpu_ctx* ctx)
         bf.blkdc_by_gather = 0; bf.stuff_overflow_possible = 1;     // block-DC maps are written by the Huffman kernels
         (void)fused_all;
         launches += js_launch_finalize(bf, s);
+        if (ctx->opt.want_mcu_map) launches += js_launch_finalize_emptied(bf, s);
     }
     CK(cudaEventRecord(ctx->ev[4], s));
     CK(cudaGetLastError());

@@ -16,6 +16,7 @@
 // dequantised int16 coefficient rows in natural order (DecodeIdctSet, :2270-2303) whose slot 0
 // holds the running DC predictor sum (m_nDcLum += m_anDctBlock[0], :3280).
 #include "jsgpu_internal.h"
+#include <algorithm>
 #include <cstdlib>
 
 #define FULL 0xffffffffu
@@ -220,6 +221,105 @@ __device__ __forceinline__ int take_value(Bits& s, uint32_t size, uint32_t preci
     s.w <<= size; s.nb -= (int)size;
     if (precision > 8) val /= (1 << (precision - 8));
     return val;
+}
+
+// ------------------------------------------------------------------------------------------------
+// MCU file map, intervals consumed to their very last bit.  The entry of the first MCU after an RSTn is the
+// reader state at the END of the previous interval (lazy restart, ImgDecode.cpp:1644-1680).  When that
+// interval was used up exactly, the reference's byte-position array is drained and reports what is left in
+// its LAST slot (ScanBuffConsume shifts pos[1..3] down and never clears pos[3], :934-953): the file position
+// of the last byte that entered the 4-byte accumulator while it held three others.  The accumulator is
+// topped up before every code and every value read (BuffTopup, :1292-1323), so that byte is unstuffed byte
+// c*+3, where c* is the largest whole-byte count consumed at any of those moments that still left >= 4
+// bytes (c* <= D-4).  Usually c* = D-4 and the answer is the interval's last byte; when a single read
+// stepped over two byte boundaries near the end it is an earlier one.  One thread per interval re-reads the
+// code lengths of the last MCU(s) to find c*.  (Verified against the CPU oracle on every boundary of the
+// test corpus; tests/jpeg_cases.py compares the map exactly.)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t peek32(const uint32_t* w, uint32_t bp)
+{
+    const uint32_t i = bp >> 5;
+    return __funnelshift_l(__ldg(w + i + 1), __ldg(w + i), bp & 31);
+}
+__device__ __forceinline__ uint32_t lookup_code(const DevTableSet* ts, uint32_t slot, uint32_t top)
+{
+    uint32_t e = ts->lut[slot][top >> (32 - JS_LUT_BITS)];
+    if (e & 0x8000) e = huff_level2(ts, slot, e, top);
+    return e;
+}
+#define EM_SPAN 1024                        // intervals examined per CTA pass (about one in eight is drained exactly)
+__global__ void __launch_bounds__(128) k_finalize_mcumap_emptied(DevBatch b)
+{
+    __shared__ uint32_t s_list[EM_SPAN];
+    __shared__ uint32_t s_n;
+    for (uint32_t ii = blockIdx.y; ii < b.nimg; ii += gridDim.y) {            // grid.y = image (strided beyond 65535 images)
+    const DevImage& im = b.img[ii];
+    if (!im.valid || !im.restart_en || im.nseg < 2) continue;
+    const DevTableSet* ts = b.tables + im.table_set;
+    for (uint32_t base = blockIdx.x * EM_SPAN; base + 1 < im.nseg; base += gridDim.x * EM_SPAN) {
+        // pass 1: which intervals of this span were drained exactly?  (compacted, so that pass 2 runs with full warps)
+        if (threadIdx.x == 0) s_n = 0;
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < EM_SPAN; i += blockDim.x) {
+            const uint32_t k = base + i;
+            if (k + 1 >= im.nseg) break;
+            const uint32_t gw = im.seg_first + k;
+            const uint32_t D = b.seg_ulen[gw];
+            if (D >= 4 && b.seg_endbits[gw] == 8 * D && !b.seg_status[gw] && min(k * im.ri + im.ri, im.nmcu) < im.nmcu)
+                s_list[atomicAdd(&s_n, 1u)] = k;                         // (D < 4 reports 0: k_finalize_mcumap_fast did that)
+        }
+        __syncthreads();
+        const uint32_t n = s_n;
+        for (uint32_t li = threadIdx.x; li < n; li += blockDim.x) {
+        const uint32_t k = s_list[li];
+        const uint32_t gw = im.seg_first + k;
+        const uint32_t D = b.seg_ulen[gw];
+        const uint32_t m0 = k * im.ri, m1 = min(m0 + im.ri, im.nmcu);
+        const uint32_t lim = 8 * (D - 3);                                // top-ups at bit positions below this still see >= 4 bytes
+        uint32_t mm = m1 - 1;
+        while (mm > m0 && b.mcu_bitpos[im.mcu_off + mm] >= lim) mm--;
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(b.ubits + b.seg_uoff[gw]);
+        uint32_t bp = (mm == m0) ? 0u : b.mcu_bitpos[im.mcu_off + mm], last = bp;
+        bool ok = true;
+        for (uint32_t m = mm; m < m1 && ok && bp < lim; m++)
+            for (uint32_t c = 0; c < im.ns && ok && bp < lim; c++)
+                for (uint32_t bi = 0; bi < im.H[c] * im.V[c] && ok && bp < lim; bi++) {
+                    uint32_t pos = 0;
+                    while (pos < 64 && bp < lim) {
+                        last = bp;                                        // top-up before the code
+                        const uint32_t e = lookup_code(ts, pos ? im.slot_ac[c] : im.slot_dc[c], peek32(w, bp));
+                        if (e == 0) { ok = false; break; }
+                        bp += e >> 8;
+                        if (bp < lim) last = bp;                          // top-up before the value bits
+                        if (pos && (e & 0xFF) == 0) break;                // EOB
+                        bp += e & 15;
+                        pos += pos ? ((e >> 4) & 15) + 1 : 1;
+                    }
+                }
+        if (!ok) continue;
+        const uint32_t j = (last >> 3) + 3;                              // unstuffed index of the reported byte (<= D-1)
+        // its raw offset: walk back from the end of the raw interval, skipping stuffed zeros
+        const uint32_t s0 = b.seg_start[gw], len = b.seg_end[gw] - s0;
+        const uint8_t* seg = b.bits + im.scan_off + s0;
+        uint32_t r = len - 1, t = D - 1 - j;
+        for (;;) {
+            if (r > 0 && seg[r] == 0 && seg[r - 1] == 0xFF) r--;         // a stuffed zero: its FF is the data byte
+            if (t == 0 || r == 0) break;
+            t--; r--;
+        }
+        b.mcu_map[im.mcu_off + m1] = (im.file_pos + s0 + r) << 4;
+        }
+        __syncthreads();
+    }
+    }
+}
+
+int js_launch_finalize_emptied(const DevBatch& b, cudaStream_t s)
+{
+    if (!b.mcu_map || b.nimg == 0 || b.max_nseg < 2) return 0;
+    const dim3 grid(std::min<uint32_t>((b.max_nseg + EM_SPAN - 1) / EM_SPAN, 64u), b.nimg < 65535u ? b.nimg : 65535u);
+    k_finalize_mcumap_emptied<<<grid, 128, 0, s>>>(b);
+    return 1;
 }
 
 // ------------------------------------------------------------------------------------------------

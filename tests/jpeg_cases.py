@@ -79,19 +79,8 @@ def compare(a, b, what=("geom", "pix_y", "pix_cb", "pix_cr", "dib", "mcu_map", "
 
 
 def mcu_map_ok(want, got):
-    """MCU file map comparison.  Exact, except for ONE documented deviation (known
-    deviation D1): when a restart interval is consumed exactly to its last bit AND the last symbol
-    stepped over two byte boundaries at once, the reference's emptied accumulator reports a stale
-    position (the second-to-last byte, ImgDecode.cpp:934-953) where we report the last byte.  Such
-    entries are byte-aligned in both maps and at most 3 bytes apart; anything else is a failure."""
+    """MCU file map comparison: exact.  (Round 1 accepted one documented deviation here — the stale byte position the
+    reference reports after an interval was consumed to its last bit by a read that stepped over two byte boundaries;
+    k_finalize_mcumap_emptied now reproduces it.)"""
     want = np.asarray(want); got = np.asarray(got)
-    if want.shape != got.shape:
-        return False
-    idx = np.nonzero(want != got)[0]
-    if idx.size == 0:
-        return True
-    if idx.size > max(1, want.size // 20):
-        return False
-    w, g = want[idx].astype(np.int64), got[idx].astype(np.int64)
-    ok = ((w & 15) == 0) & ((g & 15) == 0) & ((g >> 4) - (w >> 4) >= 1) & ((g >> 4) - (w >> 4) <= 3)
-    return bool(ok.all())
+    return want.shape == got.shape and bool(np.array_equal(want, got))
