@@ -252,10 +252,23 @@ __global__ void __launch_bounds__(128) k_finalize_mcumap_emptied(DevBatch b)
 {
     __shared__ uint32_t s_list[EM_SPAN];
     __shared__ uint32_t s_n;
+    __shared__ __align__(16) uint16_t s_lut[6][JS_LUT_SIZE];      // first-level tables of the current image, [comp*2 + class]
     for (uint32_t ii = blockIdx.y; ii < b.nimg; ii += gridDim.y) {            // grid.y = image (strided beyond 65535 images)
     const DevImage& im = b.img[ii];
     if (!im.valid || !im.restart_en || im.nseg < 2) continue;
+    if (blockIdx.x * EM_SPAN + 1 >= im.nseg) continue;
     const DevTableSet* ts = b.tables + im.table_set;
+    const uint32_t ns = im.ns, ri = im.ri, nmcu = im.nmcu;
+    const uint32_t nb0 = im.H[0] * im.V[0], nb1 = (ns == 3) ? im.H[1] * im.V[1] : 0, nb2 = (ns == 3) ? im.H[2] * im.V[2] : 0;
+    __syncthreads();
+    for (uint32_t c = 0; c < ns; c++) {
+        const uint4* s0 = reinterpret_cast<const uint4*>(ts->lut[im.slot_dc[c]]);
+        const uint4* s1 = reinterpret_cast<const uint4*>(ts->lut[im.slot_ac[c]]);
+        for (uint32_t i = threadIdx.x; i < JS_LUT_SIZE * 2 / 16; i += blockDim.x) {
+            reinterpret_cast<uint4*>(s_lut[c * 2])[i] = __ldg(s0 + i); reinterpret_cast<uint4*>(s_lut[c * 2 + 1])[i] = __ldg(s1 + i);
+        }
+    }
+    const uint32_t sdc0 = im.slot_dc[0], sac0 = im.slot_ac[0], sdc1 = im.slot_dc[1], sac1 = im.slot_ac[1], sdc2 = im.slot_dc[2], sac2 = im.slot_ac[2];
     for (uint32_t base = blockIdx.x * EM_SPAN; base + 1 < im.nseg; base += gridDim.x * EM_SPAN) {
         // pass 1: which intervals of this span were drained exactly?  (compacted, so that pass 2 runs with full warps)
         if (threadIdx.x == 0) s_n = 0;
@@ -265,7 +278,7 @@ __global__ void __launch_bounds__(128) k_finalize_mcumap_emptied(DevBatch b)
             if (k + 1 >= im.nseg) break;
             const uint32_t gw = im.seg_first + k;
             const uint32_t D = b.seg_ulen[gw];
-            if (D >= 4 && b.seg_endbits[gw] == 8 * D && !b.seg_status[gw] && min(k * im.ri + im.ri, im.nmcu) < im.nmcu)
+            if (D >= 4 && b.seg_endbits[gw] == 8 * D && !b.seg_status[gw] && min(k * ri + ri, nmcu) < nmcu)
                 s_list[atomicAdd(&s_n, 1u)] = k;                         // (D < 4 reports 0: k_finalize_mcumap_fast did that)
         }
         __syncthreads();
@@ -274,20 +287,28 @@ __global__ void __launch_bounds__(128) k_finalize_mcumap_emptied(DevBatch b)
         const uint32_t k = s_list[li];
         const uint32_t gw = im.seg_first + k;
         const uint32_t D = b.seg_ulen[gw];
-        const uint32_t m0 = k * im.ri, m1 = min(m0 + im.ri, im.nmcu);
+        const uint32_t m0 = k * ri, m1 = min(m0 + ri, nmcu);
         const uint32_t lim = 8 * (D - 3);                                // top-ups at bit positions below this still see >= 4 bytes
         uint32_t mm = m1 - 1;
         while (mm > m0 && b.mcu_bitpos[im.mcu_off + mm] >= lim) mm--;
         const uint32_t* w = reinterpret_cast<const uint32_t*>(b.ubits + b.seg_uoff[gw]);
         uint32_t bp = (mm == m0) ? 0u : b.mcu_bitpos[im.mcu_off + mm], last = bp;
+        uint32_t cw = bp >> 5, w0 = __ldg(w + cw), w1 = __ldg(w + cw + 1);   // bit window: two words, reloaded when bp leaves the first
         bool ok = true;
         for (uint32_t m = mm; m < m1 && ok && bp < lim; m++)
-            for (uint32_t c = 0; c < im.ns && ok && bp < lim; c++)
-                for (uint32_t bi = 0; bi < im.H[c] * im.V[c] && ok && bp < lim; bi++) {
+            #pragma unroll 1
+            for (uint32_t c = 0; c < ns && ok && bp < lim; c++) {
+                const uint32_t nb = (c == 0) ? nb0 : (c == 1) ? nb1 : nb2;
+                const uint32_t sdc = (c == 0) ? sdc0 : (c == 1) ? sdc1 : sdc2, sac = (c == 0) ? sac0 : (c == 1) ? sac1 : sac2;
+                const uint16_t* ldc = s_lut[c * 2]; const uint16_t* lac = s_lut[c * 2 + 1];
+                for (uint32_t bi = 0; bi < nb && ok && bp < lim; bi++) {
                     uint32_t pos = 0;
                     while (pos < 64 && bp < lim) {
                         last = bp;                                        // top-up before the code
-                        const uint32_t e = lookup_code(ts, pos ? im.slot_ac[c] : im.slot_dc[c], peek32(w, bp));
+                        if ((bp >> 5) != cw) { cw = bp >> 5; w0 = __ldg(w + cw); w1 = __ldg(w + cw + 1); }
+                        const uint32_t top = __funnelshift_l(w1, w0, bp & 31);
+                        uint32_t e = (pos ? lac : ldc)[top >> (32 - JS_LUT_BITS)];
+                        if (e & 0x8000) e = huff_level2(ts, pos ? sac : sdc, e, top);
                         if (e == 0) { ok = false; break; }
                         bp += e >> 8;
                         if (bp < lim) last = bp;                          // top-up before the value bits
@@ -296,6 +317,7 @@ __global__ void __launch_bounds__(128) k_finalize_mcumap_emptied(DevBatch b)
                         pos += pos ? ((e >> 4) & 15) + 1 : 1;
                     }
                 }
+            }
         if (!ok) continue;
         const uint32_t j = (last >> 3) + 3;                              // unstuffed index of the reported byte (<= D-1)
         // its raw offset: walk back from the end of the raw interval, skipping stuffed zeros
