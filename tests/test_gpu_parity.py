@@ -142,6 +142,44 @@ def test_decode_batch_host_matches_oracle(built, cases, nrep):
         assert not JC.compare(orc.decode(j), got, what=("geom", "pix_y", "pix_cb", "pix_cr", "dib", "mcu_map", "blk_dc", "dht_histo")), (i, name)
 
 
+def test_random_corpus_matches_oracle(built):
+    """A seeded corpus of 48 small images — random size, sampling layout, quality, restart interval, optimised or
+    standard Huffman tables (Pillow) plus 4:1:1 / 4:4:0 / long-code tables (tests/mini_jpeg.py) — decoded as ONE batch
+    (many table sets, many geometries) and compared with the oracle on every output, MCU file map included."""
+    import mini_jpeg as MJ
+    from jpegsnoop_b200 import BatchDecoder
+    rng = np.random.default_rng(20260923)
+    named = []
+    for i in range(36):
+        W, H = int(rng.integers(8, 420)), int(rng.integers(8, 300))
+        ss = int(rng.integers(0, 3)); q = int(rng.integers(25, 99)); kw = {}
+        mode = int(rng.integers(0, 4))
+        if mode == 1: kw["restart_marker_blocks"] = int(rng.integers(1, 9))
+        if mode == 2: kw["restart_marker_rows"] = int(rng.integers(1, 3))
+        if mode == 3: kw["restart_marker_blocks"] = 1
+        img = JC.synth_rgb(W, H, 1000 + i)
+        if rng.integers(0, 6) == 0: img = img[:, :, 0]; ss = None
+        args = dict(quality=q, optimize=bool(rng.integers(0, 2)), **kw)
+        if ss is not None: args["subsampling"] = ss
+        named.append((f"pil_{i}_{W}x{H}_ss{ss}_q{q}_{mode}", JC.enc(img, **args)))
+    for i in range(12):
+        W, H = int(rng.integers(16, 260)), int(rng.integers(16, 200))
+        samp = [((2, 2), (1, 1), (1, 1)), ((4, 1), (1, 1), (1, 1)), ((1, 2), (1, 1), (1, 1)), ((2, 1), (1, 1), (1, 1)), ((1, 1), (1, 1), (1, 1))][int(rng.integers(0, 5))]
+        n11 = int(rng.integers(0, 28))
+        ac = MJ.long_code_table(MJ.all_ac_symbols(), n11=n11)
+        named.append((f"mini_{i}_{W}x{H}_{samp[0]}_n11={n11}", MJ.encode(JC.synth_rgb(W, H, 2000 + i), quality=int(rng.integers(40, 97)), samp=samp,
+                                                                       dri=int(rng.integers(0, 7)), ac_tabs=[ac, ac])))
+    orc = _oracle(True)
+    for huff in (0, 2):
+        bd = BatchDecoder(huff_kernel=huff, idct_kernel=0)
+        bd.set_batch([j for _, j in named]); bd.decode(); bd.sync()
+        for i, (name, j) in enumerate(named):
+            want = orc.decode(j); got = bd.fetch(i)
+            assert want.nerr == 0 and got.status == 0, (name, want.nerr, got.status)
+            bad = JC.compare(want, got, what=("geom", "pix_y", "pix_cb", "pix_cr", "dib", "mcu_map", "blk_dc", "dht_histo"))
+            assert not bad, f"{name} (huff_kernel={huff}): mismatch in {bad}"
+
+
 def test_host_marker_walk_equals_device_marker_scan(built, cases):
     from jpegsnoop_b200 import BatchDecoder
     jpegs = [j for _, j in cases]
