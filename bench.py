@@ -232,6 +232,21 @@ def main():
     e2e = None
     if not args.no_e2e:
         L = B.load()
+        # host buffers should live on the NUMA node the GPU hangs off: run the e2e leg on that node's cores
+        # (pinned pages are first-touch local) and give the process its full CPU set back afterwards
+        old_aff = None; numa = None
+        try:
+            bus = torch.cuda.get_device_properties(local)
+            busid = "%04x:%02x:%02x.0" % (getattr(bus, "pci_domain_id", 0), bus.pci_bus_id, bus.pci_device_id)
+            cl = open(f"/sys/bus/pci/devices/{busid}/local_cpulist").read().strip()
+            numa = int(open(f"/sys/bus/pci/devices/{busid}/numa_node").read())
+            cpus = set()
+            for part in cl.split(","):
+                a, _, b2 = part.partition("-"); cpus.update(range(int(a), int(b2 or a) + 1))
+            if cpus and numa >= 0:
+                old_aff = os.sched_getaffinity(0); os.sched_setaffinity(0, cpus & old_aff or old_aff)
+        except Exception:
+            old_aff = None
         def pinned(nbytes, dtype):
             p = L.jsgpu_host_alloc(int(nbytes))
             if not p:
@@ -271,6 +286,9 @@ def main():
                 e2e["host_buffers_bit_exact_vs_oracle"] = bool(ok)
         else:
             e2e = {"value": None, "unit": UNIT, "error": "pinned host allocation failed"}
+        if old_aff is not None:
+            os.sched_setaffinity(0, old_aff)
+            if e2e is not None: e2e["host_numa_node"] = numa
 
     # ---- roofline of the dominant kernel + CPU baseline (rank 0) ---------------------------------------
     if rank == 0:
