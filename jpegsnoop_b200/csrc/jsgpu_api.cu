@@ -575,12 +575,10 @@ int jsgpu_batch_decode(jsgpu_ctx* ctx)
         else launches += js_launch_huffman_warp(b, ctx->sm_count, s);
     }
     CK(cudaEventRecord(ctx->ev[2], s));
-    bool fused_all = false;
     {
         // fused tile kernel: integer IDCT, standard sampling layouts, decomposable table; everything
         // else (float IDCT, exotic sampling, a libm whose table does not decompose) takes the simple kernels
         const bool fused = (ctx->opt.idct_kernel != 1) && ctx->opt.idct_mode == 0 && ctx->sym_ok && b.ntiles > 0;
-        fused_all = fused && ctx->n_nonstd == 0;
         // idct_kernel: 2 = TMA-staged tile kernel, 0/3 = tile kernel with per-lane vector loads (measured faster, profiles/r1_idct.md)
         if (fused && ctx->opt.idct_kernel == 2 && ctx->tmap_ok) launches += js_launch_idct_tma(b, (const IdctSym*)ctx->d_sym.p, (const ColorTabs*)ctx->d_ctab.p, ctx->tmap, ctx->sm_count, s);
         else if (fused) launches += js_launch_idct_fused(b, (const IdctSym*)ctx->d_sym.p, (const ColorTabs*)ctx->d_ctab.p, ctx->sm_count, ctx->tab_mode, s);
@@ -593,8 +591,6 @@ int jsgpu_batch_decode(jsgpu_ctx* ctx)
     {
         DevBatch bf = b;
         if (!ctx->opt.want_mcu_map) bf.mcu_map = nullptr;
-        bf.blkdc_by_gather = 0; bf.stuff_overflow_possible = 1;     // block-DC maps are written by the Huffman kernels
-        (void)fused_all;
         launches += js_launch_finalize(bf, s);
         if (ctx->opt.want_mcu_map) launches += js_launch_finalize_emptied(bf, s);
     }

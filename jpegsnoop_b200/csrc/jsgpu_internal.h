@@ -107,8 +107,6 @@ struct DevBatch {
     uint32_t           lane_nlut;            // lane Huffman kernel: most distinct (class,Th) tables any image uses (<= 6)
     int                lane_l2_smem;         // ... and every used table's second level fits JS_LANE_L2S entries
     int                any_p12;              // some image has sample precision > 8 (ReadScanVal's divide, ID:1234-1238)
-    int                blkdc_by_gather;      // 1: block-DC maps by the gather kernel (simple IDCT path), 0: written by k_idct_tile
-    int                stuff_overflow_possible;
     int                simple_only_nonstd;   // simple IDCT kernels skip images the fused kernel handled
     uint32_t           tile_plane_bytes;     // shared-memory plane bytes the largest tile needs
 };

@@ -218,29 +218,9 @@ int js_launch_idct_simple(const DevBatch& b, const int32_t* li, const float* lf,
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3: finalisation — block-DC maps (ImgDecode.cpp:3524-3608), scalar statistics (:4802-4819)
+// K3: finalisation — scalar statistics (ImgDecode.cpp:4802-4819) and the MCU file map.  (The block-DC maps,
+// :3524-3608, are written by the Huffman kernels.)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_finalize_blkdc(DevBatch b)
-{
-    const DevImage& im = b.img[blockIdx.y];
-    if (!im.valid) return;
-    const uint32_t ncell = im.blk_xmax * im.blk_ymax;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < ncell * im.ns; i += gridDim.x * blockDim.x) {
-        uint32_t c = i / ncell, cell = i % ncell, bx = cell % im.blk_xmax, by = cell / im.blk_xmax;
-        // last MCU (raster order) that writes this cell: cell = (mx*eh + h, my*ev + v), h<H, v<V
-        int val = 0;
-        uint32_t eh = im.eh[c], ev = im.ev[c], H = im.H[c], V = im.V[c];
-        uint32_t my = min(by / ev, im.mcu_ymax - 1), mx = min(bx / eh, im.mcu_xmax - 1);
-        uint32_t v = by - my * ev, h = bx - mx * eh;
-        if (v < V && h < H) {
-            size_t row = im.coef_row[c] + (size_t)(my * V + v) * im.cw[c] + (mx * H + h);
-            val = b.coef[row * 64];
-        }
-        int16_t* map = ((c == 0) ? b.blk_y : (c == 1) ? b.blk_cb : b.blk_cr) + im.blk_off;
-        map[cell] = (int16_t)val;
-    }
-}
-
 __global__ void k_finalize_stats(DevBatch b)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -355,12 +335,11 @@ int js_launch_finalize(const DevBatch& b, cudaStream_t s)
 {
     if (b.nimg == 0) return 0;
     int n = 0;
-    if (b.blkdc_by_gather) { dim3 grid(64, b.nimg); k_finalize_blkdc<<<grid, 256, 0, s>>>(b); n++; }
     k_finalize_stats<<<(b.nimg + 127) / 128, 128, 0, s>>>(b); n++;
     if (b.mcu_map && b.nseg_total) {
         dim3 grid(32, b.nimg);
         k_finalize_mcumap_fast<<<grid, 256, 0, s>>>(b); n++;
-        if (b.stuff_overflow_possible) { k_finalize_mcumap<<<std::min<uint32_t>((b.nseg_total + 3) / 4, 148 * 8), 128, 0, s>>>(b); n++; }
+        k_finalize_mcumap<<<std::min<uint32_t>((b.nseg_total + 3) / 4, 148 * 8), 128, 0, s>>>(b); n++;      // walks the overflow list only
     }
     return n;
 }
