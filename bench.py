@@ -278,7 +278,7 @@ def main():
             e2e = {"value": round(total_px * args.e2e_steps / float(te.item()) / 1e6, 1), "unit": UNIT,
                    "h2d_bytes_per_step": int(bits.size), "d2h_bytes_per_step": int(d2h), "steps": args.e2e_steps,
                    "what": "jsgpu_decode_batch_host: pinned bitstream -> all reference outputs in pinned host memory "
-                           "(4 image ranges, D2H of one overlapping upload+decode of the next)"}
+                           "(8 image ranges, D2H of one overlapping upload+decode of the next)"}
             if rank == 0:                                 # the host buffers themselves against the oracle
                 ok = True
                 for i in checked:

@@ -197,7 +197,7 @@ int jsgpu_batch_launches(jsgpu_ctx* ctx);
  * skip that output).  Output buffers hold the images back to back in batch order using the
  * element offsets of jsgpu_batch_layout.  Small batches run H2D, decode and D2H on the context
  * stream.  Large ones (>= 16 images and >= 64 MB of bitstream, images laid out in increasing,
- * 16-byte aligned scan offsets) are cut into 4 image ranges, each with its own stream and device
+ * 16-byte aligned scan offsets) are cut into 8 image ranges, each with its own stream and device
  * pools, so the device-to-host copy of one range overlaps upload and decode of the next; afterwards
  * this context holds the batch layout and statuses only (jsgpu_batch_layout works,
  * jsgpu_batch_download / jsgpu_batch_pools return JSGPU_ESTATE: the data already is in `out`). */

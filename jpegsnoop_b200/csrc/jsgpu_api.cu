@@ -684,17 +684,18 @@ static int decode_host_single(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint
     return JSGPU_OK;
 }
 
-// Host bitstream in, every reference output in host buffers out.  A large batch is cut into JS_HOST_CHUNKS image
-// ranges, each on its own stream with its own pools: the device-to-host copy of one range (PCIe-bound, ~97 % of the
+// Host bitstream in, every reference output in host buffers out.  A large batch is cut into JS_HOST_CHUNKS (8; 4 and 16
+// measured within 1.5 %) image ranges, each on its own stream with its own pools: the device-to-host copy of one range (PCIe-bound, ~97 % of the
 // call) overlaps upload and decode of the next ones.  Afterwards this context holds the batch LAYOUT (and statuses)
 // only; the device pools belong to the chunk contexts, so jsgpu_batch_download()/pools() report JSGPU_ESTATE.
-#define JS_HOST_CHUNKS 4
+#define JS_HOST_CHUNKS_MAX 16
 int jsgpu_decode_batch_host(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, const uint8_t* bits, uint64_t bytes,
                             const jsgpu_host_outputs* out)
 {
     if (!ctx || !imgs || !bits || !out) return JSGPU_EINVAL;
+    static const uint32_t JS_HOST_CHUNKS = [] { const char* e = getenv("JSGPU_HOST_CHUNKS"); int v = e ? atoi(e) : 8; return (uint32_t)(v < 2 ? 2 : v > JS_HOST_CHUNKS_MAX ? JS_HOST_CHUNKS_MAX : v); }();
     static const uint64_t min_bytes = getenv("JSGPU_HOST_CHUNK_MIN_BYTES") ? strtoull(getenv("JSGPU_HOST_CHUNK_MIN_BYTES"), nullptr, 10) : (64ull << 20);
-    bool chunked = n >= 4 * JS_HOST_CHUNKS && bytes >= min_bytes && !ctx->h_sets.empty() && !ctx->h_li.empty();
+    bool chunked = n >= 2 * JS_HOST_CHUNKS && bytes >= min_bytes && !ctx->h_sets.empty() && !ctx->h_li.empty();
     for (uint32_t i = 1; chunked && i < n; i++)             // chunk bitstreams must be contiguous, 16-byte aligned ranges
         if (imgs[i].scan_offset < imgs[i - 1].scan_offset + imgs[i - 1].scan_length || (imgs[i].scan_offset & 15)) chunked = false;
     if (chunked && ((imgs[0].scan_offset & 15) || imgs[n - 1].scan_offset + imgs[n - 1].scan_length > bytes)) chunked = false;
