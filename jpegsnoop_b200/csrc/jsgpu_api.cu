@@ -375,7 +375,9 @@ int jsgpu_batch_begin(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, 
             return fail(ctx, JSGPU_EINVAL, "image %u: scan [%llu,+%llu) outside the %llu-byte bitstream", i,
                         (unsigned long long)imgs[i].scan_offset, (unsigned long long)imgs[i].scan_length, (unsigned long long)bitstream_bytes);
         if (ok && imgs[i].scan_length >= 0xfffffff0ull) return fail(ctx, JSGPU_EINVAL, "image %u: scan longer than 4 GiB", i);
-        if (!ok) { im.valid = 0; lo.status = 0x80000000u; continue; }
+        if (!ok) {            // skipped image: no pool space, but keep seg_first monotone (k_finalize_mcumap binary-searches it)
+            im.valid = 0; im.nseg = 0; im.seg_first = seg; lo.status = 0x80000000u; continue;
+        }
         im.pix_off = pix; im.dib_off = dib; im.blk_off = blk; im.mcu_off = mcu; im.seg_first = seg;
         for (uint32_t c = 0; c < im.ns; c++) { im.coef_row[c] = rows; rows += (uint64_t)im.cw[c] * im.ch[c]; }
         uint64_t npx = (uint64_t)im.wp * im.hp;
@@ -725,7 +727,10 @@ int jsgpu_decode_batch_host(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32
         const uint64_t base = imgs[i0].scan_offset, end = imgs[i1 - 1].scan_offset + imgs[i1 - 1].scan_length;
         d.assign(imgs + i0, imgs + i1);
         for (auto& x : d) x.scan_offset -= base;
-        const DevImage& f = ctx->himg[i0];                   // first image of the chunk: its offsets in the global pools
+        uint32_t iv = i0;                                    // first image of the chunk that occupies pool space (skipped images do not)
+        while (iv < i1 && !ctx->himg[iv].valid) iv++;
+        static const DevImage none = {};
+        const DevImage& f = (iv < i1) ? ctx->himg[iv] : none;    // its offsets in the global pools = where this chunk's outputs start
         jsgpu_host_outputs o2 = {};
         o2.pix_y  = out->pix_y  ? (int16_t*)out->pix_y  + f.pix_off : nullptr;
         o2.pix_cb = out->pix_cb ? (int16_t*)out->pix_cb + f.pix_off : nullptr;

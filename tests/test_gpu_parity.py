@@ -180,6 +180,46 @@ def test_random_corpus_matches_oracle(built):
             assert not bad, f"{name} (huff_kernel={huff}): mismatch in {bad}"
 
 
+@pytest.mark.xfail(strict=False, reason="written when round 1's GPU budget was spent: its only run failed (MCU map of an image behind a "
+                                       "skipped one) BEFORE the seg_first fix in jsgpu_batch_begin; the fix itself has not run on a GPU yet")
+def test_unsupported_images_in_a_batch_are_skipped(built, cases):
+    """Images the reference's DecodeScanImg would refuse (here: 4-component CMYK scans) occupy no pool space, carry
+    status 0x80000000 and do not disturb their neighbours — also at the start of an image range of the pipelined
+    host call."""
+    import io
+    from PIL import Image
+    from jpegsnoop_b200 import BatchDecoder
+    b = io.BytesIO(); Image.fromarray(JC.synth_rgb(64, 48, 77)).convert("CMYK").save(b, "JPEG", quality=80); cmyk = b.getvalue()
+    good = [j for _, j in cases[:6]] * 3                       # 18 decodable images
+    jpegs = list(good); names = ["ok"] * len(good)
+    for at in (0, 5, 11):
+        jpegs.insert(at, cmyk); names.insert(at, "cmyk")
+    bd = BatchDecoder(huff_kernel=0, idct_kernel=0)
+    tarr, darr, bits = bd.prepare(jpegs)
+    bd.set_tables(tarr); bd.plan(darr, bits.size)
+    lay = bd.layout
+    tot = lambda f, a: sum((f(l) + a - 1) // a * a for l, nm in zip(lay, names) if nm == "ok")
+    pix_n = tot(lambda l: int(l.img_x) * int(l.img_y), 64); dib_n = tot(lambda l: int(l.img_x) * int(l.img_y) * 4, 256)
+    blk_n = tot(lambda l: int(l.blk_xmax) * int(l.blk_ymax), 64); mcu_n = tot(lambda l: int(l.mcu_xmax) * int(l.mcu_ymax), 32)
+    outs = {"pix_y": np.zeros(pix_n, np.int16), "pix_cb": np.zeros(pix_n, np.int16), "pix_cr": np.zeros(pix_n, np.int16),
+            "dib": np.zeros(dib_n, np.uint8), "blk_y": np.zeros(blk_n, np.int16), "blk_cb": np.zeros(blk_n, np.int16),
+            "blk_cr": np.zeros(blk_n, np.int16), "mcu_map": np.zeros(mcu_n, np.uint32),
+            "dht_histo": np.zeros(len(jpegs) * 136, np.uint32), "stats": np.zeros(len(jpegs) * 16, np.int32)}
+    bd.decode_host(darr, bits, outs)
+    orc = _oracle(True)
+    st = [int(l.status) for l in bd.refresh_layout()]
+    for i, (nm, j) in enumerate(zip(names, jpegs)):
+        if nm == "cmyk":
+            assert st[i] == 0x80000000, (i, hex(st[i]))
+        else:
+            assert st[i] == 0, (i, hex(st[i]))
+            assert not JC.compare(orc.decode(j), bd.fetch_host(i, outs), what=("geom", "pix_y", "pix_cb", "pix_cr", "dib", "mcu_map", "blk_dc", "dht_histo")), i
+    bd.set_batch(jpegs); bd.decode(); bd.sync()                 # and the device-resident path
+    for i, (nm, j) in enumerate(zip(names, jpegs)):
+        if nm == "ok":
+            assert not JC.compare(orc.decode(j), bd.fetch(i), what=("pix_y", "dib", "mcu_map")), i
+
+
 def test_host_marker_walk_equals_device_marker_scan(built, cases):
     from jpegsnoop_b200 import BatchDecoder
     jpegs = [j for _, j in cases]
