@@ -58,6 +58,7 @@ struct jsgpu_ctx {
     std::vector<jsgpu_tables> h_sets; std::vector<int32_t> h_li; std::vector<float> h_lf;
     std::vector<jsgpu_ctx*> kids;            // chunk contexts (own stream and pools), created on first use
     bool plan_only = false;                  // batch_begin computes the layout only (the chunk contexts own the device pools)
+    bool layout_only = false;                // ... and that is all this context currently holds: upload/decode need a new batch_begin
     bool host_delivered = false;             // the last decode went straight to host buffers: nothing to download from this context
     float ms[5] = {0, 0, 0, 0, 0};
 };
@@ -408,7 +409,7 @@ int jsgpu_batch_begin(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, 
     for (int k = 0; k < 3; k++) { tcls_first[k] = (uint32_t)tiles.size(); tcls_count[k] = (uint32_t)tcls[k].size(); tiles.insert(tiles.end(), tcls[k].begin(), tcls[k].end()); }
     ctx->bits_len = bitstream_bytes; ctx->pix_total = pix; ctx->dib_total = dib; ctx->blk_total = blk; ctx->mcu_total = mcu;
     ctx->coef_rows = rows; ctx->max_scan_len = max_scan; ctx->ubits_total = ub; ctx->n_std = n_std; ctx->n_nonstd = n_nonstd;
-    ctx->host_delivered = false;
+    ctx->host_delivered = false; ctx->layout_only = ctx->plan_only;
     if (ctx->plan_only) { ctx->planned = true; return JSGPU_OK; }
     // allocate
     CK(ctx->d_img.reserve(sizeof(DevImage) * (size_t)n));
@@ -490,7 +491,7 @@ int jsgpu_batch_pools(jsgpu_ctx* ctx, jsgpu_pools* out)
 int jsgpu_batch_upload(jsgpu_ctx* ctx, const uint8_t* host, uint64_t bytes)
 {
     if (!ctx || !host) return JSGPU_EINVAL;
-    if (!ctx->planned) return fail(ctx, JSGPU_ESTATE, "no batch planned");
+    if (!ctx->planned || ctx->layout_only) return fail(ctx, JSGPU_ESTATE, "no batch planned");
     if (bytes > ctx->bits_len) return fail(ctx, JSGPU_EINVAL, "upload larger than the planned bitstream");
     cudaSetDevice(ctx->device);
     CK(cudaMemcpyAsync(ctx->d_bits.p, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -537,7 +538,7 @@ static int host_marker_walk(jsgpu_ctx* ctx, const uint8_t* bits_host)
 int jsgpu_batch_decode(jsgpu_ctx* ctx)
 {
     if (!ctx) return JSGPU_EINVAL;
-    if (!ctx->planned) return fail(ctx, JSGPU_ESTATE, "no batch planned");
+    if (!ctx->planned || ctx->layout_only) return fail(ctx, JSGPU_ESTATE, "no batch planned (the last jsgpu_decode_batch_host left only its layout here)");
     cudaSetDevice(ctx->device);
     DevBatch& b = ctx->batch;
     b.decode_ac = ctx->opt.decode_ac; b.want_histo = ctx->opt.want_histo; b.idct_mode = ctx->opt.idct_mode;
