@@ -85,7 +85,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_baseline(jpegs, npix_per_img, budget_s=15.0, threads=None):
+def cpu_baseline(jpegs, npix_per_img, budget_s=15.0, threads=None, extras=True):
     """The reference's own CPU DecodeScanImg (oracle/_ref, -DIDCT_FIXEDPT build) on the host cores,
     on a bounded sample of the same batch.  Falls back to the C port when _ref is absent."""
     from oracle_util import Oracle, ref_available
@@ -99,9 +99,22 @@ def cpu_baseline(jpegs, npix_per_img, budget_s=15.0, threads=None):
     n = int(max(cores, min(len(jpegs), budget_s * cores / per_img)))
     sample = [bytes(j) for j in jpegs[:n]]
     t, errs = orc.bench(sample, threads=cores, reps=1)
-    return {"value": round(len(sample) * npix_per_img / t / 1e6, 2), "unit": UNIT, "cores": cores, "kind": kind,
-            "sample": f"first {len(sample)} images of the batch, {cores} threads, one CimgDecode per thread, "
-                      f"integer-IDCT build, {t:.2f} s wall", "err_lines": errs}, t, len(sample)
+    out = {"value": round(len(sample) * npix_per_img / t / 1e6, 2), "unit": UNIT, "cores": cores, "kind": kind,
+           "sample": f"first {len(sample)} images of the batch, {cores} threads, one CimgDecode per thread, "
+                     f"integer-IDCT build, {t:.2f} s wall", "err_lines": errs}
+    if extras:      # also one thread, and the float-IDCT build (the reference's shipping default)
+        try:
+            k1 = [bytes(j) for j in jpegs[:max(1, min(len(jpegs), int(2.0 / per_img) or 1))]]
+            t1, _ = orc.bench(k1, threads=1, reps=1)
+            out["one_thread_value"] = round(len(k1) * npix_per_img / t1 / 1e6, 2)
+            if kind == "reference" and ref_available("float"):
+                of = Oracle("ref_float")
+                kf = sample[:max(cores, len(sample) // 3)]
+                tf, _ = of.bench(kf, threads=cores, reps=1)
+                out["float_idct_build_value"] = round(len(kf) * npix_per_img / tf / 1e6, 2)
+        except Exception as e:                      # the headline CPU figure above does not depend on these
+            out["extras_error"] = str(e)[:200]
+    return out, t, len(sample)
 
 
 def run_reference(args):
