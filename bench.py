@@ -317,10 +317,12 @@ def main():
         idct_ms = float(stage_ms[2]); huff_ms = float(stage_ms[1])
         ach = bd.npadded_pixels * bpp / (idct_ms / 1e3) / 1e9
         huff_gbs = (bits.size + bd.npadded_pixels * (bpp - 10.0)) / (huff_ms / 1e3) / 1e9      # bitstream read + coefficient rows written
+        traffic_rw = None
         traffic = None        # DRAM bytes of one K2 launch from the committed ncu capture of this workload (GB), if there is one
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.config)
-            if tj and nimg == CONFIGS[args.config][0]: traffic = round(tj["dram_read_gb"] + tj["dram_write_gb"], 3)
+            if tj and nimg == CONFIGS[args.config][0]:
+                traffic = round(tj["dram_read_gb"] + tj["dram_write_gb"], 3); traffic_rw = (tj["dram_read_gb"], tj["dram_write_gb"])
         except Exception:
             pass
         roof = {"bound": "hbm", "kernel": "k_idct_tile (dequant+IDCT+upsample+YCC->BGRA, stage B)", "achieved": round(ach, 1), "peak": peak,
@@ -329,6 +331,8 @@ def main():
                 "stage_ms": {"marker_scan+unstuff": round(float(stage_ms[0]), 3), "huffman": round(huff_ms, 3),
                              "idct+colour": round(idct_ms, 3), "finalize": round(float(stage_ms[3]), 3), "step_total": round(float(stage_ms[4]), 3)},
                 "huffman_achieved_gbs": round(huff_gbs, 1)}
+        if traffic_rw:        # read-only and write-only rates of the same launch
+            roof["dram_read_gbs"] = round(traffic_rw[0] / (idct_ms / 1e3), 1); roof["dram_write_gbs"] = round(traffic_rw[1] / (idct_ms / 1e3), 1)
         cb = None
         if not args.no_cpu and world == 1:          # the CPU leg is reported at N=1 only (the reference arm covers N>1)
             cb, _, _ = cpu_baseline(jpegs, w * h)
