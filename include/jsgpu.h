@@ -92,8 +92,9 @@ typedef struct {
     int32_t idct_mode;      /* 0 = integer IDCT (the -DIDCT_FIXEDPT build, ImgDecode.cpp:2402-2423,
                                2512-2515; default), 1 = float IDCT (:2372-2392, 2517-2519)       */
     int32_t decode_ac;      /* m_bDecodeScanAc (ImgDecode.cpp:1723-1725,1818); default 1          */
-    int32_t huff_kernel;    /* 0 = auto, 1 = one warp per restart interval, 2 = one lane per
-                               restart interval                                                   */
+    int32_t huff_kernel;    /* 0 = auto (3 for images with long restart intervals, else 2 or 1 by the
+                               number of intervals), 1 = one warp per restart interval, 2 = one lane
+                               per restart interval, 3 = self-synchronising passes for long intervals */
     int32_t idct_kernel;    /* 0 = auto, 1 = simple reference kernels, 2 = fused tile kernel with
                                TMA-staged coefficients, 3 = fused tile kernel with plain loads    */
     int32_t want_histo;     /* accumulate m_anDhtHisto (ImgDecode.cpp:1190-1191); default 1      */
@@ -192,6 +193,12 @@ int jsgpu_timer_start(jsgpu_ctx* ctx);
 int jsgpu_timer_stop(jsgpu_ctx* ctx, float* ms);
 /* Number of kernels launched by the last jsgpu_batch_decode. */
 int jsgpu_batch_launches(jsgpu_ctx* ctx);
+/* Diagnostics of the self-synchronising Huffman passes of the last jsgpu_batch_decode (images with long restart
+ * intervals — no DRI, or a DRI of an MCU row and more — whose single serial walk, ImgDecode.cpp:3164-3630, is cut into
+ * 4096-bit slots): info[0] = images on that path, info[1] = slots reserved, info[2] = fix rounds enqueued (R),
+ * info[3..3+R] = slots whose state changed in fix round 1..R+... (0 from the round in which everything had settled).
+ * n = capacity of info in words (16 is enough).  Forces a sync. */
+int jsgpu_batch_selfsync_info(jsgpu_ctx* ctx, uint32_t* info, uint32_t n);
 
 /* One-call end-to-end form: host bitstream in, host outputs out (any pointer may be NULL to
  * skip that output).  Output buffers hold the images back to back in batch order using the

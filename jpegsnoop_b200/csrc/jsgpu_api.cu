@@ -4,6 +4,8 @@
 // decode goes to the device or fails.
 #include "../../include/jsgpu.h"
 #include "jsgpu_internal.h"
+#include "jsgpu_tables_host.h"
+#include "jsgpu_phuff_core.cuh"
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -39,7 +41,7 @@ struct jsgpu_ctx {
     bool have_idct = false;
     // device state
     DevBuf d_ctab; bool have_ctab = false;
-    DevBuf d_li, d_lf, d_sym, d_tables, d_img, d_items, d_litems, d_tiles, d_ubits, d_seg64;
+    DevBuf d_li, d_lf, d_sym, d_tables, d_img, d_items, d_litems, d_tiles, d_ubits, d_seg64, d_ph, d_rowtab;
     bool sym_ok = false, baked_ok = false; int tab_mode = 0;
     DevBuf d_bits, d_seg, d_coef, d_mcubits, d_pix, d_dib, d_blk, d_mcumap, d_histo, d_stats, d_misc;
     uint32_t nsets = 0;
@@ -50,7 +52,8 @@ struct jsgpu_ctx {
     std::vector<jsgpu_image_layout> layout;
     DevBatch batch;
     uint64_t bits_len = 0, pix_total = 0, dib_total = 0, blk_total = 0, mcu_total = 0, coef_rows = 0;
-    uint64_t max_scan_len = 0, ubits_total = 0;
+    uint64_t max_scan_len = 0, ubits_total = 0, ph_total = 0, rt_total = 0;
+    uint32_t nseg_np = 0, n_psync = 0;
     alignas(64) unsigned char tmap[128]; bool tmap_ok = false;
     uint32_t n_nonstd = 0, n_std = 0;
     int launches = 0;
@@ -122,7 +125,7 @@ void jsgpu_free(jsgpu_ctx* ctx)
     ctx->kids.clear();
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = { &ctx->d_ctab, &ctx->d_li, &ctx->d_lf, &ctx->d_sym, &ctx->d_tables, &ctx->d_img, &ctx->d_items, &ctx->d_litems, &ctx->d_tiles, &ctx->d_ubits, &ctx->d_seg64, &ctx->d_bits, &ctx->d_seg,
+    DevBuf* bufs[] = { &ctx->d_ctab, &ctx->d_li, &ctx->d_lf, &ctx->d_sym, &ctx->d_tables, &ctx->d_img, &ctx->d_items, &ctx->d_litems, &ctx->d_tiles, &ctx->d_ubits, &ctx->d_seg64, &ctx->d_ph, &ctx->d_rowtab, &ctx->d_bits, &ctx->d_seg,
                        &ctx->d_coef, &ctx->d_mcubits, &ctx->d_pix, &ctx->d_dib, &ctx->d_blk, &ctx->d_mcumap, &ctx->d_histo, &ctx->d_stats, &ctx->d_misc };
     for (auto* b : bufs) b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -214,74 +217,6 @@ int jsgpu_set_options(jsgpu_ctx* ctx, const jsgpu_options* opt)
 }
 int jsgpu_get_options(jsgpu_ctx* ctx, jsgpu_options* opt) { if (!ctx || !opt) return JSGPU_EINVAL; *opt = ctx->opt; return JSGPU_OK; }
 
-// zig-zag position -> natural index (T.81 Figure A.6; same permutation as glb_anZigZag, General.cpp:257-267)
-static const uint8_t kZigZagNat[64] = {
-     0, 1, 8,16, 9, 2, 3,10, 17,24,32,25,18,11, 4, 5, 12,19,26,33,40,48,41,34, 27,20,13, 6, 7,14,21,28,
-    35,42,49,56,57,50,43,36, 29,22,15,23,30,37,44,51, 58,59,52,45,38,31,39,46, 53,60,61,54,47,55,62,63 };
-
-// Build the device decode tables of one set.  The direct LUT must give exactly what
-// ReadScanVal's "first matching entry in SetDhtEntry order" search gives (ImgDecode.cpp:1145-1164):
-// for each JS_LUT_BITS-bit prefix we walk the entries in order; a short entry that matches decides
-// the prefix, a longer entry that COULD match sends the prefix to the slow in-order search.
-static void build_table_set(const jsgpu_tables& t, DevTableSet& d)
-{
-    memset(&d, 0, sizeof d);
-    for (int cls = 0; cls < 2; cls++) for (int id = 0; id < 4; id++) {
-        int slot = cls * 4 + id;
-        uint32_t n = std::min<uint32_t>(t.dht_size[cls][id], JS_MAX_CODES);
-        d.ent_n[slot] = n;
-        for (uint32_t i = 0; i < n; i++) {
-            uint32_t len = t.dht_len[cls][id][i];
-            d.ent_len[slot][i] = (uint8_t)len;
-            uint32_t mask = (len >= 1 && len <= 32) ? (0xffffffffu << (32 - len)) : 0;
-            d.ent_bits[slot][i] = t.dht_bits[cls][id][i] & mask;
-            d.ent_sym[slot][i] = t.dht_code[cls][id][i];
-        }
-        // Fill both levels in entry order; an entry never overwrites what an earlier entry claimed.
-        uint32_t nsub = 0; bool overflow = false;
-        for (uint32_t i = 0; i < n && !overflow; i++) {
-            const uint32_t len = d.ent_len[slot][i];
-            if (len == 0 || len > 16) continue;
-            const uint32_t bits = d.ent_bits[slot][i];
-            const uint16_t val = (uint16_t)((len << 8) | d.ent_sym[slot][i]);
-            const uint32_t p0 = bits >> (32 - JS_LUT_BITS);
-            const uint32_t np = (len <= JS_LUT_BITS) ? (1u << (JS_LUT_BITS - len)) : 1u;
-            for (uint32_t p = p0; p < p0 + np && p < JS_LUT_SIZE; p++) {
-                uint16_t& e = d.lut[slot][p];
-                if (len <= JS_LUT_BITS) {
-                    if (e == 0) e = val;
-                    else if (e & 0x8000) { uint16_t* sub = &d.lut2[slot][e & 0x7FFF]; for (uint32_t k = 0; k < (1u << JS_LUT2_BITS); k++) if (sub[k] == 0) sub[k] = val; }
-                } else {
-                    if (e != 0 && !(e & 0x8000)) continue;           // an earlier short code owns this prefix
-                    if (e == 0) {
-                        if ((nsub + 1) * (1u << JS_LUT2_BITS) > JS_LUT2_SIZE) { overflow = true; break; }
-                        e = (uint16_t)(0x8000 | (nsub << JS_LUT2_BITS)); nsub++;
-                    }
-                    uint16_t* sub = &d.lut2[slot][e & 0x7FFF];
-                    const uint32_t k0 = (bits >> (32 - 16)) & ((1u << JS_LUT2_BITS) - 1);
-                    const uint32_t nk = 1u << (16 - len);
-                    for (uint32_t k = k0; k < k0 + nk && k < (1u << JS_LUT2_BITS); k++) if (sub[k] == 0) sub[k] = val;
-                }
-            }
-        }
-        d.lut2_overflow[slot] = overflow ? 1 : 0;
-        d.lut2_used[slot] = nsub << JS_LUT2_BITS;
-        if (overflow) {       // pathological table: every long prefix goes to the in-order search
-            memset(d.lut[slot], 0, sizeof d.lut[slot]);
-            for (uint32_t p = 0; p < JS_LUT_SIZE; p++) {
-                const uint32_t top = p << (32 - JS_LUT_BITS);
-                for (uint32_t i = 0; i < n; i++) {
-                    const uint32_t len = d.ent_len[slot][i];
-                    if (len == 0 || len > 16) continue;
-                    if (len <= JS_LUT_BITS) { if ((top & (0xffffffffu << (32 - len))) == d.ent_bits[slot][i]) { d.lut[slot][p] = (uint16_t)((len << 8) | d.ent_sym[slot][i]); break; } }
-                    else if ((d.ent_bits[slot][i] & (0xffffffffu << (32 - JS_LUT_BITS))) == top) { d.lut[slot][p] = 0x8000; break; }
-                }
-            }
-        }
-    }
-    for (int q = 0; q < 4; q++) for (int k = 0; k < 64; k++) d.qz[q][k] = (uint32_t)t.dqt_zz[q][k] | ((uint32_t)kZigZagNat[k] << 16);
-}
-
 int jsgpu_upload_tables(jsgpu_ctx* ctx, const jsgpu_tables* sets, uint32_t nsets)
 {
     if (!ctx || !sets || nsets == 0) return JSGPU_EINVAL;
@@ -346,8 +281,13 @@ static bool plan_image(const jsgpu_image_desc& d, uint32_t nsets, DevImage& im)
     // are identical and either fully sampled or 1 in each direction, Hmax is a power of two
     bool stdl = (H[0] == hmax && V[0] == vmax) && (hmax == 1 || hmax == 2 || hmax == 4);
     if (ns == 3) stdl = stdl && H[1] == H[2] && V[1] == V[2] && (H[1] == 1 || H[1] == hmax) && (V[1] == 1 || V[1] == vmax);
-    im.std_layout = stdl ? 1 : 0;
     im.tile_mcus = 32 / hmax;
+    // the fused kernel double-buffers a tile's sample planes in <= 48 KB of shared memory: layouts with more than 192
+    // blocks per tile (three components at 4x4, 2x4 ...) take the simple kernels like the other exotic layouts
+    if (stdl && (uint64_t)im.bpm * im.tile_mcus * 128u * 2u > 48u * 1024u) stdl = false;
+    im.std_layout = stdl ? 1 : 0;
+    // long restart intervals (no DRI, or a DRI of an MCU row and more): the self-synchronising Huffman passes apply
+    im.psync = ((uint64_t)im.ri * im.bpm >= JS_PSYNC_MIN_BLOCKS) ? 1 : 0;
     im.tiles_per_row = (im.mcu_xmax + im.tile_mcus - 1) / im.tile_mcus;
     im.tile_groups = (im.bpm * im.tile_mcus + 31) / 32;
     im.valid = 1;
@@ -364,8 +304,9 @@ int jsgpu_batch_begin(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, 
     ctx->himg.assign(n, DevImage());
     ctx->layout.assign(n, jsgpu_image_layout());
     uint64_t pix = 0, dib = 0, blk = 0, mcu = 0, rows = 0, max_scan = 0, ub = 0;
-    uint32_t seg = 0, n_std = 0, n_nonstd = 0, plane_bytes = 0;
-    std::vector<uint2> items, litems;
+    uint32_t seg = 0, n_std = 0, n_nonstd = 0, plane_bytes = 0, seg_np = 0, n_psync = 0;
+    uint64_t pht = 0, rtt = 0;
+    std::vector<uint2> items, litems, items_np, litems_np, vitems;
     std::vector<uint4> tiles, tcls[3];
     for (uint32_t i = 0; i < n; i++) {
         DevImage& im = ctx->himg[i];
@@ -375,7 +316,8 @@ int jsgpu_batch_begin(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, 
         if (ok && (imgs[i].scan_offset > bitstream_bytes || imgs[i].scan_length > bitstream_bytes - imgs[i].scan_offset))
             return fail(ctx, JSGPU_EINVAL, "image %u: scan [%llu,+%llu) outside the %llu-byte bitstream", i,
                         (unsigned long long)imgs[i].scan_offset, (unsigned long long)imgs[i].scan_length, (unsigned long long)bitstream_bytes);
-        if (ok && imgs[i].scan_length >= 0xfffffff0ull) return fail(ctx, JSGPU_EINVAL, "image %u: scan longer than 4 GiB", i);
+        if (ok && imgs[i].scan_length >= 0x1ffffff0ull) return fail(ctx, JSGPU_EINVAL, "image %u: scan longer than 512 MiB (bit positions are 32-bit)", i);
+        if (ok && (imgs[i].scan_offset & 15)) return fail(ctx, JSGPU_EINVAL, "image %u: scan_offset %llu is not 16-byte aligned (jsgpu_image_desc)", i, (unsigned long long)imgs[i].scan_offset);
         if (!ok) {            // skipped image: no pool space, but keep seg_first monotone (k_finalize_mcumap binary-searches it)
             im.valid = 0; im.nseg = 0; im.seg_first = seg; lo.status = 0x80000000u; continue;
         }
@@ -389,7 +331,18 @@ int jsgpu_batch_begin(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, 
         for (uint32_t k = 0; k < im.nseg; k += JS_HUFF_WARPS) items.push_back(make_uint2(i, k));
         im.nitems = (uint32_t)items.size() - im.item_first;
         for (uint32_t k = 0; k < im.nseg; k += JS_LANE_SEGS) litems.push_back(make_uint2(i, k));
-        im.ubits_off = ub; ub += align_up(im.scan_len + (uint64_t)JS_USLACK * im.nseg + 128, 256);
+        const uint64_t uregion = align_up(im.scan_len + (uint64_t)JS_USLACK * im.nseg + 128, 256);
+        im.ubits_off = ub; ub += uregion;
+        if (im.psync) {           // slots of the self-synchronising passes + row table of k_unstuff
+            n_psync++;
+            im.ph_nslots = (uint32_t)(uregion >> 9) + im.nseg + 2; im.ph_first = pht; pht += (uint64_t)im.ph_nslots + 1;
+            im.rt_off = rtt; rtt += (im.scan_len >> 7) + 2ull * im.nseg + 4;
+            for (uint32_t k = 0; k < im.ph_nslots; k += JS_LANE_SEGS) vitems.push_back(make_uint2(i, k));
+        } else {
+            seg_np += im.nseg;
+            for (uint32_t k = 0; k < im.nseg; k += JS_HUFF_WARPS) items_np.push_back(make_uint2(i, k));
+            for (uint32_t k = 0; k < im.nseg; k += JS_LANE_SEGS) litems_np.push_back(make_uint2(i, k));
+        }
         if (im.std_layout) {
             n_std++;
             const uint32_t ehc = (im.ns == 3) ? im.eh[1] : 1, cls = (ehc == 1) ? 0 : (ehc == 2) ? 1 : 2;
@@ -409,14 +362,17 @@ int jsgpu_batch_begin(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, 
     for (int k = 0; k < 3; k++) { tcls_first[k] = (uint32_t)tiles.size(); tcls_count[k] = (uint32_t)tcls[k].size(); tiles.insert(tiles.end(), tcls[k].begin(), tcls[k].end()); }
     ctx->bits_len = bitstream_bytes; ctx->pix_total = pix; ctx->dib_total = dib; ctx->blk_total = blk; ctx->mcu_total = mcu;
     ctx->coef_rows = rows; ctx->max_scan_len = max_scan; ctx->ubits_total = ub; ctx->n_std = n_std; ctx->n_nonstd = n_nonstd;
+    ctx->ph_total = pht; ctx->rt_total = rtt; ctx->nseg_np = seg_np; ctx->n_psync = n_psync;
     ctx->host_delivered = false; ctx->layout_only = ctx->plan_only;
     if (ctx->plan_only) { ctx->planned = true; return JSGPU_OK; }
     // allocate
     CK(ctx->d_img.reserve(sizeof(DevImage) * (size_t)n));
-    CK(ctx->d_items.reserve(sizeof(uint2) * std::max<size_t>(items.size(), 1)));
+    CK(ctx->d_items.reserve(sizeof(uint2) * std::max<size_t>(items.size() + items_np.size(), 1)));
     CK(ctx->d_bits.reserve(bitstream_bytes + 64));
     CK(ctx->d_ubits.reserve(ub + 16384));          // + slack: a reader of corrupt data stops at the next MCU boundary, at most one MCU (<= 12 KB of bits) past the end
-    CK(ctx->d_litems.reserve(sizeof(uint2) * std::max<size_t>(litems.size(), 1)));
+    CK(ctx->d_litems.reserve(sizeof(uint2) * std::max<size_t>(litems.size() + litems_np.size() + vitems.size(), 1)));
+    CK(ctx->d_ph.reserve(pht * 64 + 256));                      // x 8 + ver 4 + k 4 + cnt 16 + aux 16 + pre 16 bytes per slot
+    CK(ctx->d_rowtab.reserve(rtt * 20 + 256));                  // rowtab 4 + rowmask 16 bytes per 128-byte raw row
     CK(ctx->d_tiles.reserve(sizeof(uint4) * std::max<size_t>(tiles.size(), 1)));
     CK(ctx->d_seg64.reserve(8 * (size_t)seg + 16));
     CK(ctx->d_seg.reserve(sizeof(uint32_t) * ((7 + JS_STUFF_LIST) * (size_t)seg + 2 * (size_t)n + 16)));
@@ -428,8 +384,12 @@ int jsgpu_batch_begin(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, 
     CK(ctx->d_mcumap.reserve(mcu * 4 + 16));
     CK(ctx->d_histo.reserve((size_t)n * 2 * 4 * 17 * 4));
     CK(ctx->d_stats.reserve((size_t)n * 16 * 4));
-    CK(ctx->d_misc.reserve((size_t)n * (8 + 8 + 4) + 64));
+    CK(ctx->d_misc.reserve((size_t)n * (8 + 8 + 4) + 64 + 64));
     CK(cudaMemcpyAsync(ctx->d_img.p, ctx->himg.data(), sizeof(DevImage) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    const size_t n_it = items.size(), n_lit = litems.size();
+    items.insert(items.end(), items_np.begin(), items_np.end());                   // [all | without self-synchronised images]
+    litems.insert(litems.end(), litems_np.begin(), litems_np.end());               // [all | without ... | slots of the self-synchronised images]
+    litems.insert(litems.end(), vitems.begin(), vitems.end());
     if (!items.empty()) CK(cudaMemcpyAsync(ctx->d_items.p, items.data(), sizeof(uint2) * items.size(), cudaMemcpyHostToDevice, ctx->stream));
     if (!litems.empty()) CK(cudaMemcpyAsync(ctx->d_litems.p, litems.data(), sizeof(uint2) * litems.size(), cudaMemcpyHostToDevice, ctx->stream));
     if (!tiles.empty()) CK(cudaMemcpyAsync(ctx->d_tiles.p, tiles.data(), sizeof(uint4) * tiles.size(), cudaMemcpyHostToDevice, ctx->stream));
@@ -444,11 +404,20 @@ int jsgpu_batch_begin(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, 
     b.scan_end = sp + 5 * (size_t)seg; b.nseg_found = b.scan_end + n; b.nseg_total = seg;
     b.seg_nstuff = b.nseg_found + n; b.seg_stuff = b.seg_nstuff + seg; b.ovf_list = b.seg_stuff + (size_t)JS_STUFF_LIST * seg;
     b.seg_uoff = (unsigned long long*)ctx->d_seg64.p; b.ubits = (uint8_t*)ctx->d_ubits.p;
-    b.litems = (const uint2*)ctx->d_litems.p; b.nlitems = (uint32_t)litems.size();
+    b.litems = (const uint2*)ctx->d_litems.p; b.nlitems = (uint32_t)n_lit;
+    b.litems_np = b.litems + n_lit; b.nlitems_np = (uint32_t)litems_np.size();
+    b.vitems = b.litems_np + litems_np.size(); b.nvitems = (uint32_t)vitems.size();
+    {   // slot arrays, 16-byte members first
+        uint8_t* q = (uint8_t*)ctx->d_ph.p;
+        b.ph_cnt = (uint4*)q; q += pht * 16; b.ph_aux = (uint4*)q; q += pht * 16; b.ph_pre = (uint4*)q; q += pht * 16;
+        b.ph_x = (unsigned long long*)q; q += pht * 8; b.ph_ver = (uint32_t*)q; q += pht * 4; b.ph_k = (uint32_t*)q;
+        b.rowmask = (uint4*)ctx->d_rowtab.p; b.rowtab = (uint32_t*)((uint8_t*)ctx->d_rowtab.p + rtt * 16);
+    }
     b.tiles = (const uint4*)ctx->d_tiles.p; b.ntiles = (uint32_t)tiles.size(); b.tile_plane_bytes = plane_bytes;
     for (int k = 0; k < 3; k++) { b.tcls_first[k] = tcls_first[k]; b.tcls_count[k] = tcls_count[k]; }
     ctx->tmap_ok = (js_make_coef_tensor_map(ctx->tmap, ctx->d_coef.p, rows + 8) == 0);
-    b.items = (const uint2*)ctx->d_items.p; b.nitems = (uint32_t)items.size();
+    b.items = (const uint2*)ctx->d_items.p; b.nitems = (uint32_t)n_it;
+    b.items_np = b.items + n_it; b.nitems_np = (uint32_t)items_np.size();
     b.coef = (int16_t*)ctx->d_coef.p; b.mcu_bitpos = (uint32_t*)ctx->d_mcubits.p;
     b.pix_y = (int16_t*)ctx->d_pix.p; b.pix_cb = b.pix_y + pix; b.pix_cr = b.pix_cb + pix;
     b.dib = (uint8_t*)ctx->d_dib.p;
@@ -456,6 +425,7 @@ int jsgpu_batch_begin(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, 
     b.mcu_map = (uint32_t*)ctx->d_mcumap.p;
     b.histo = (uint32_t*)ctx->d_histo.p; b.stats = (int32_t*)ctx->d_stats.p;
     b.bright_key = (unsigned long long*)ctx->d_misc.p; b.sum_y = b.bright_key + n; b.img_status = (uint32_t*)(b.sum_y + n); b.ovf_count = b.img_status + n;
+    b.ph_nchg = b.ovf_count + 1;
     ctx->planned = true;
     return JSGPU_OK;
 }
@@ -572,10 +542,22 @@ int jsgpu_batch_decode(jsgpu_ctx* ctx)
     launches += js_launch_unstuff(b, s);
     CK(cudaEventRecord(ctx->ev[1], s));
     {
+        // huff_kernel: 1 = one warp per restart interval for everything, 2 = one lane per restart interval for everything,
+        // 0/3 = images with long intervals (no DRI ...) through the self-synchronising passes + the lane kernel over their
+        // virtual intervals, the others through the lane kernel when there are many intervals, else the warp kernel
         int hk = ctx->opt.huff_kernel;
-        if (hk == 0) hk = (b.nseg_total >= 4096) ? 2 : 1;       // many short intervals -> lane kernel
-        if (hk == 2) launches += js_launch_huffman_lane(b, ctx->sm_count, s);
-        else launches += js_launch_huffman_warp(b, ctx->sm_count, s);
+        const bool selfsync = (hk == 0 || hk == 3) && b.nvitems > 0 && b.lane_l2_smem;
+        DevBatch bh = b;
+        uint32_t nseg_short = b.nseg_total;
+        if (selfsync) { bh.items = b.items_np; bh.nitems = b.nitems_np; bh.litems = b.litems_np; bh.nlitems = b.nlitems_np; nseg_short = ctx->nseg_np; }
+        else bh.nvitems = 0;
+        if (hk == 0 || hk == 3) hk = (nseg_short >= 4096) ? 2 : 1;       // many short intervals -> lane kernel
+        if (hk == 2) launches += js_launch_huffman_lane(bh, ctx->sm_count, s);
+        else launches += js_launch_huffman_warp(bh, ctx->sm_count, s);
+        if (selfsync) {
+            launches += js_launch_selfsync(bh, ctx->sm_count, s);
+            launches += js_launch_huffman_lane_vseg(bh, ctx->sm_count, s);
+        }
     }
     CK(cudaEventRecord(ctx->ev[2], s));
     {
@@ -622,6 +604,22 @@ int jsgpu_timer_stop(jsgpu_ctx* ctx, float* ms)
 }
 
 int jsgpu_batch_launches(jsgpu_ctx* ctx) { return ctx ? ctx->launches : JSGPU_EINVAL; }
+
+int jsgpu_batch_selfsync_info(jsgpu_ctx* ctx, uint32_t* info, uint32_t n)
+{
+    if (!ctx || !info || n < 4) return JSGPU_EINVAL;
+    if (!ctx->decoded || ctx->host_delivered) return fail(ctx, JSGPU_ESTATE, "no device-resident decode to report on");
+    cudaSetDevice(ctx->device);
+    memset(info, 0, sizeof(uint32_t) * n);
+    info[0] = ctx->n_psync; info[1] = (uint32_t)std::min<uint64_t>(ctx->ph_total, 0xffffffffu); info[2] = PH_MAX_ROUNDS;
+    uint32_t h[PH_MAX_ROUNDS + 2] = {};
+    if (ctx->n_psync) {
+        CK(cudaMemcpyAsync(h, ctx->batch.ph_nchg, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    for (uint32_t r = 1; r <= PH_MAX_ROUNDS && 2 + r < n; r++) info[2 + r] = h[r];
+    return JSGPU_OK;
+}
 
 int jsgpu_batch_stage_ms(jsgpu_ctx* ctx, float* ms5)
 {

@@ -16,6 +16,7 @@
 // dequantised int16 coefficient rows in natural order (DecodeIdctSet, :2270-2303) whose slot 0
 // holds the running DC predictor sum (m_nDcLum += m_anDctBlock[0], :3280).
 #include "jsgpu_internal.h"
+#include "jsgpu_phuff_core.cuh"
 #include <algorithm>
 #include <cstdlib>
 
@@ -68,6 +69,9 @@ __global__ void __launch_bounds__(128) k_unstuff(DevBatch b)
     const uint32_t* abase = reinterpret_cast<const uint32_t*>(seg - mis);
     uint32_t wr = 0, fl = 0, carry = 0;
     const uint32_t lt = (1u << lane) - 1;
+    // self-synchronised images: per 128-byte raw row, the unstuffed bytes before it and the mask of its bytes that do not
+    // reach the output, so that k_finalize_mcumap_fast turns an unstuffed index into a file offset without re-walking
+    const size_t rt0 = im.psync ? (size_t)(im.rt_off + (s0 >> 7) + 2u * k) : 0;
     if (lane == 0) s_cnt[wid] = 0;
     __syncwarp();
     // rows are requested one ahead of their use
@@ -95,6 +99,12 @@ __global__ void __launch_bounds__(128) k_unstuff(DevBatch b)
         const uint32_t rm = dn | (vn ^ 15u);                                                // bytes that do not reach the output
         const uint32_t kk = __byte_perm(word, 0, s_sel[rm]);
         const uint32_t cnt = 4 - __popc(rm);                                                // 0..4 kept bytes
+        if (im.psync) {                          // warp-uniform
+            uint32_t mw = rm << ((lane & 7) * 4);
+            mw |= __shfl_xor_sync(FULL, mw, 1); mw |= __shfl_xor_sync(FULL, mw, 2); mw |= __shfl_xor_sync(FULL, mw, 4);
+            if ((lane & 7) == 0) reinterpret_cast<uint32_t*>(b.rowmask + rt0 + (rpos >> 7))[lane >> 3] = mw;
+            if (lane == 0) b.rowtab[rt0 + (rpos >> 7)] = wr;
+        }
         const uint32_t b0 = __ballot_sync(FULL, cnt & 1), b1 = __ballot_sync(FULL, cnt & 2), b2 = __ballot_sync(FULL, cnt & 4);
         const uint32_t o = wr + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
         if (__any_sync(FULL, dn != 0)) {              // remember where bytes were dropped (MCU file map): unstuffed index of the preceding FF
@@ -131,7 +141,7 @@ __global__ void __launch_bounds__(128) k_unstuff(DevBatch b)
     if (lane == 0) {
         const uint32_t nstuff = s_cnt[wid];
         b.seg_ulen[gw] = wr; b.seg_uoff[gw] = dst0; b.seg_nstuff[gw] = nstuff;
-        if (nstuff > JS_STUFF_LIST) b.ovf_list[atomicAdd(b.ovf_count, 1u)] = gw;     // rare: the MCU map of this interval needs the raw re-walk
+        if (nstuff > JS_STUFF_LIST && !im.psync) b.ovf_list[atomicAdd(b.ovf_count, 1u)] = gw;     // rare: the MCU map of this interval needs the raw re-walk
     }
     __syncwarp();
     }
@@ -487,7 +497,7 @@ int js_launch_huffman_warp(const DevBatch& b, int sm_count, cudaStream_t s)
 #define LN_WARPS   (JS_LANE_SEGS / 32)
 #define ROW_PITCH  208                      // bytes per lane row: 64 coefficients, 8 dummy slots, 16 code-length counters; 16-byte aligned
 #define ROW_HIST   144                      // byte offset of the counter for length 1 (length 0 = "no code" lands in the dummy slots)
-#define LN_TAB     (JS_LUT_SIZE + JS_LANE_L2S)   // entries per staged table: first level, then its second level
+#define LN_TAB     JS_LANE_TAB                   // entries per staged table: first level, then its second level
 // Dynamic shared memory of the lane kernel:
 //   LaneHdr | lane rows [LN_WARPS][32][ROW_PITCH] | tables [nl][LN_TAB]
 // nl = DevBatch::lane_nlut: the distinct (class,Th) tables an image selects are staged once each (Cb and Cr
@@ -516,6 +526,15 @@ struct Win {
         hi = __ldg(base); lo = __ldg(base + 1);
         nx = __ldg(base + 2); idx = 3; nb = 64;
     }
+    // start at absolute bit `bitpos` of the interval (virtual restart intervals): idx stays an absolute word index,
+    // so consumed() is the absolute bit position
+    __device__ __forceinline__ void init_at(const uint8_t* b, uint32_t bitpos) {
+        base = reinterpret_cast<const uint32_t*>(b);
+        const uint32_t w = bitpos >> 5;
+        hi = __ldg(base + w); lo = __ldg(base + w + 1);
+        nx = __ldg(base + w + 2); idx = w + 3; nb = 64;
+        consume(bitpos & 31);
+    }
     // Top up when 32 bits or fewer are left (6 <= nb then).  The look-ahead word is reloaded IN PLACE by a
     // predicated load: written as a C++ conditional, the compiler loads into a temporary and copies it into
     // `nx` at the end of the same step, i.e. waits for the global load it was supposed to hide (22 % of the
@@ -537,7 +556,9 @@ struct Win {
 // GENERIC = false: the common case compiled without run-time feature checks (AC decode on, 8-bit
 // precision).  GENERIC = true: DC-only mode and 12-bit precision honoured at run time.
 // HISTO: also count code lengths per (class, table) (CimgDecode::m_anDhtHisto, ImgDecode.cpp:1217).
-template <bool GENERIC, bool HISTO>
+// VSEG: the lanes decode VIRTUAL restart intervals — the 4096-bit slots of long real intervals, whose first MCU start,
+// MCU index and DC predictors the self-synchronising passes found (jsgpu_phuff_core.cuh) — instead of real ones.
+template <bool GENERIC, bool HISTO, bool VSEG>
 __global__ void __launch_bounds__(LN_WARPS * 32, 3) k_huff_lane(DevBatch b)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -550,8 +571,9 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 3) k_huff_lane(DevBatch b)
     for (uint32_t i = lane; i < 32 * ROW_PITCH / 4; i += 32) reinterpret_cast<uint32_t*>(myrows)[i] = 0;
     const bool want_ac = GENERIC ? (b.decode_ac != 0) : true;
     uint32_t cur_img = 0xffffffffu, cur_sig = 0xffffffffu, cur_set = 0xffffffffu;
-    for (uint32_t it = blockIdx.x; it < b.nlitems; it += gridDim.x) {      // strided: images of different entropy spread over all CTAs
-        const uint2 item = b.litems[it];                      // (image, first interval); JS_LANE_SEGS intervals per item
+    const uint32_t nit = VSEG ? b.nvitems : b.nlitems;
+    for (uint32_t it = blockIdx.x; it < nit; it += gridDim.x) {      // strided: images of different entropy spread over all CTAs
+        const uint2 item = VSEG ? b.vitems[it] : b.litems[it];       // (image, first interval or slot); JS_LANE_SEGS of them per item
         const DevImage& gim = b.img[item.x];
         const DevTableSet* ts = b.tables + gim.table_set;
         if (item.x != cur_img) {
@@ -590,19 +612,35 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 3) k_huff_lane(DevBatch b)
             __syncthreads();
         }
         const uint32_t kbase = item.y + wid * 32;
-        if (kbase >= gim.nseg) continue;                       // warp-uniform
+        if (kbase >= (VSEG ? gim.ph_nslots : gim.nseg)) continue;   // warp-uniform
         const uint32_t k = kbase + lane;
-        const bool live = k < gim.nseg;
         const uint32_t ns = gim.ns, ri = gim.ri, nmcu = gim.nmcu, mcu_xmax = gim.mcu_xmax;
         const uint32_t pshift = (GENERIC && gim.precision > 8) ? gim.precision - 8 : 0;
-        const uint32_t sidx = gim.seg_first + (live ? k : kbase);
-        Win s; s.init(b.ubits + b.seg_uoff[sidx]);
-        const uint32_t m0 = k * ri;
-        const uint32_t nm = live ? (min(m0 + ri, nmcu) - m0) : 0;   // MCUs this lane decodes
-        uint32_t mx = m0 % mcu_xmax, my = m0 / mcu_xmax;
+        bool live, vfinal = true; uint32_t sidx, m0, nm, nm_max;
         int dc0 = 0, dc1 = 0, dc2 = 0;
+        Win s;
+        if (!VSEG) {
+            live = k < gim.nseg;
+            sidx = gim.seg_first + (live ? k : kbase);
+            s.init(b.ubits + b.seg_uoff[sidx]);
+            m0 = k * ri;
+            nm = live ? (min(m0 + ri, nmcu) - m0) : 0;               // MCUs this lane decodes
+            nm_max = min(ri, nmcu - kbase * ri);                     // longest interval in this warp (the first lane's)
+        } else {
+            PhSegs sg; sg.start = b.seg_start + gim.seg_first; sg.ulen = b.seg_ulen + gim.seg_first; sg.uoff = b.seg_uoff + gim.seg_first; sg.nseg = gim.nseg;
+            PhSlots a; a.x = b.ph_x + gim.ph_first; a.ver = b.ph_ver + gim.ph_first; a.k = b.ph_k + gim.ph_first;
+            a.cnt = b.ph_cnt + gim.ph_first; a.aux = b.ph_aux + gim.ph_first; a.pre = b.ph_pre + gim.ph_first;
+            PhVseg v; v.k = 0; v.bit = 0; v.m0 = 0; v.nm = 0; v.dc0 = v.dc1 = v.dc2 = 0; v.final = false;
+            live = (k < gim.ph_nslots) && ph_vseg(sg, ri, nmcu, a, k, v);
+            sidx = gim.seg_first + (live ? v.k : 0u);
+            s.init_at(b.ubits + b.seg_uoff[sidx], live ? v.bit : 0u);
+            m0 = live ? v.m0 : 0u; nm = live ? v.nm : 0u; vfinal = v.final;
+            if (live) { dc0 = v.dc0; dc1 = v.dc1; dc2 = v.dc2; }
+            nm_max = __reduce_max_sync(FULL, nm);
+            if (nm_max == 0) continue;                               // warp-uniform
+        }
+        uint32_t mx = m0 % mcu_xmax, my = m0 / mcu_xmax;
         uint32_t status = 0;
-        const uint32_t nm_max = min(ri, nmcu - kbase * ri);         // longest interval in this warp (the first lane's)
         const uint32_t avail = b.seg_ulen[sidx] * 8;
         #pragma unroll 1
         for (uint32_t mi = 0; mi < nm_max; mi++) {
@@ -716,39 +754,62 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 3) k_huff_lane(DevBatch b)
         }
         if (live) {
             const uint32_t consumed = s.consumed();
-            if (consumed > avail) status |= 2;
-            else if (!(status & 5) && avail - consumed >= 8) status |= 16;
-            b.seg_endbits[sidx] = consumed;
-            b.seg_status[sidx] = status;
-            if (status) atomicOr(&b.img_status[item.x], status);
+            if (!VSEG) {
+                if (consumed > avail) status |= 2;
+                else if (!(status & 5) && avail - consumed >= 8) status |= 16;
+                b.seg_endbits[sidx] = consumed;
+                b.seg_status[sidx] = status;
+                if (status) atomicOr(&b.img_status[item.x], status);
+            } else {
+                if (vfinal) {                                   // the virtual interval that ends the real one reports its end state
+                    if (consumed > avail) status |= 2;
+                    else if (!(status & 5) && avail - consumed >= 8) status |= 16;
+                    b.seg_endbits[sidx] = consumed;
+                }
+                if (status) { atomicOr(&b.seg_status[sidx], status); atomicOr(&b.img_status[item.x], status); }   // cleared by k_ph_scan
+            }
         }
     }
     __syncthreads();
     if (HISTO && cur_img != 0xffffffffu) flush_histo(b, cur_img, sh.histo);
 }
 
+template <bool VSEG>
+static int launch_lane(const DevBatch& b, int sm_count, cudaStream_t s)
+{
+    static bool attr_set[JS_MAX_DEVICES] = {};
+    int dev = 0; cudaGetDevice(&dev);
+    if (dev >= 0 && dev < JS_MAX_DEVICES && !attr_set[dev]) {       // the attribute is per device
+        const int mx = (int)lane_smem_bytes(6, true);
+        cudaFuncSetAttribute(k_huff_lane<false, false, VSEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(k_huff_lane<true, false, VSEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(k_huff_lane<false, true, VSEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(k_huff_lane<true, true, VSEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        attr_set[dev] = true;
+    }
+    const size_t smem = lane_smem_bytes(b.lane_nlut, b.want_histo != 0);
+    const uint32_t nit = VSEG ? b.nvitems : b.nlitems;
+    uint32_t grid = (uint32_t)sm_count * 3;
+    if (grid > nit) grid = nit;
+    const bool generic = !b.decode_ac || b.any_p12;
+    const dim3 blk(LN_WARPS * 32);
+    if (b.want_histo) {
+        if (generic) k_huff_lane<true, true, VSEG><<<grid, blk, smem, s>>>(b); else k_huff_lane<false, true, VSEG><<<grid, blk, smem, s>>>(b);
+    } else {
+        if (generic) k_huff_lane<true, false, VSEG><<<grid, blk, smem, s>>>(b); else k_huff_lane<false, false, VSEG><<<grid, blk, smem, s>>>(b);
+    }
+    return 1;
+}
+
 int js_launch_huffman_lane(const DevBatch& b, int sm_count, cudaStream_t s)
 {
     if (b.nlitems == 0) return 0;
     if (!b.lane_l2_smem) return js_launch_huffman_warp(b, sm_count, s);   // a second level too large to stage (pathological DHT): the warp kernel reads it from global memory
-    static bool attr_set = false;
-    if (!attr_set) {
-        const int mx = (int)lane_smem_bytes(6, true);
-        cudaFuncSetAttribute(k_huff_lane<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-        cudaFuncSetAttribute(k_huff_lane<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-        cudaFuncSetAttribute(k_huff_lane<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-        cudaFuncSetAttribute(k_huff_lane<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-        attr_set = true;
-    }
-    const size_t smem = lane_smem_bytes(b.lane_nlut, b.want_histo != 0);
-    uint32_t grid = (uint32_t)sm_count * 3;
-    if (grid > b.nlitems) grid = b.nlitems;
-    const bool generic = !b.decode_ac || b.any_p12;
-    const dim3 blk(LN_WARPS * 32);
-    if (b.want_histo) {
-        if (generic) k_huff_lane<true, true><<<grid, blk, smem, s>>>(b); else k_huff_lane<false, true><<<grid, blk, smem, s>>>(b);
-    } else {
-        if (generic) k_huff_lane<true, false><<<grid, blk, smem, s>>>(b); else k_huff_lane<false, false><<<grid, blk, smem, s>>>(b);
-    }
-    return 1;
+    return launch_lane<false>(b, sm_count, s);
+}
+
+int js_launch_huffman_lane_vseg(const DevBatch& b, int sm_count, cudaStream_t s)
+{
+    if (b.nvitems == 0) return 0;
+    return launch_lane<true>(b, sm_count, s);
 }

@@ -316,7 +316,9 @@ int js_idct_baked_matches(const int32_t* li) { return memcmp(li, kBakedLi, sizeo
 template <int TAB>
 static int launch_tab(const DevBatch& b, const IdctSym* sym, const ColorTabs* ctab, int sm_count, cudaStream_t s)
 {
-    static bool attr_set = false;
+    static bool attr_set_dev[JS_MAX_DEVICES] = {};       // the attribute is per device
+    int dev_ = 0; cudaGetDevice(&dev_); if (dev_ < 0 || dev_ >= JS_MAX_DEVICES) dev_ = 0;
+    bool& attr_set = attr_set_dev[dev_];
     const int mx = (int)(sizeof(Idct2Tables) + sizeof(TileGeo) + 48 * 1024);
     if (!attr_set) {
         cudaFuncSetAttribute(k_idct_tile<TAB, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);

@@ -224,7 +224,9 @@ int js_launch_idct_tma(const DevBatch& b, const IdctSym* sym, const ColorTabs* c
     uint32_t groups = (b.tile_plane_bytes / 128 + 31) / 32;
     const uint32_t nw = groups < 1 ? 1 : groups > T2_MAXWARPS ? T2_MAXWARPS : groups;
     const size_t smem = 1024 + (size_t)nw * 4096 + sizeof(Idct2Tables) + 64 + b.tile_plane_bytes;
-    static bool attr_set = false;
+    static bool attr_set_dev[JS_MAX_DEVICES] = {};       // the attribute is per device
+    int dev_ = 0; cudaGetDevice(&dev_); if (dev_ < 0 || dev_ >= JS_MAX_DEVICES) dev_ = 0;
+    bool& attr_set = attr_set_dev[dev_];
     if (!attr_set) {
         const int mx = 1024 + T2_MAXWARPS * 4096 + (int)sizeof(Idct2Tables) + 64 + 48 * 1024;
         cudaFuncSetAttribute(k_idct_tma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);

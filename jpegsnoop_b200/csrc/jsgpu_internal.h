@@ -11,6 +11,7 @@
 #define JS_MAX_CODES  260
 #define JS_USLACK     48                 // bytes of slack per restart interval in the unstuffed pool (16 pad + flush rounding + alignment)
 #define JS_STUFF_LIST 6                  // stuffed-byte positions recorded per restart interval
+#define JS_MAX_DEVICES 64                // per-device "function attribute set" flags of the launchers
 #define JS_NSLOT      8                  // (class,Th) pairs: slot = class*4 + Th
 
 // Device form of one jsgpu_tables set.
@@ -57,6 +58,10 @@ struct DevImage {
     uint32_t tile_groups;           // 32-block groups per IDCT tile
     uint32_t item_first, nitems;    // Huffman work items (groups of HUFF_WARPS segments)
     uint32_t tile_first, ntiles;    // IDCT tiles
+    uint32_t psync;                 // 1 = long restart intervals: decoded through the self-synchronising passes (jsgpu_phuff_core.cuh)
+    uint32_t ph_nslots;             // ... number of 4096-bit slots reserved for this image (its slot arrays hold ph_nslots + 1 entries)
+    uint64_t ph_first;              // ... first entry of this image in the slot arrays
+    uint64_t rt_off;                // first entry of this image in the row table (k_unstuff: unstuffed bytes before every 128-byte raw row of a long interval)
 };
 
 // Everything a kernel needs about the current batch (passed by value).
@@ -84,6 +89,17 @@ struct DevBatch {
     uint32_t           nitems;
     const uint2*       litems;      // Huffman, lane kernel: (image, first segment), JS_LANE_SEGS per item
     uint32_t           nlitems;
+    const uint2*       items_np;    // the same two lists without the images that take the self-synchronising path
+    uint32_t           nitems_np;
+    const uint2*       litems_np;
+    uint32_t           nlitems_np;
+    const uint2*       vitems;      // self-synchronising passes and the lane kernel over virtual intervals: (image, first slot), JS_LANE_SEGS per item
+    uint32_t           nvitems;
+    // slot arrays of the self-synchronising passes (all images back to back, see PhSlots)
+    unsigned long long* ph_x; uint32_t* ph_ver; uint32_t* ph_k; uint4* ph_cnt; uint4* ph_aux; uint4* ph_pre;
+    uint32_t*          ph_nchg;     // [PH_MAX_ROUNDS + 2] slots whose exit state changed in fix round r
+    uint32_t*          rowtab;      // self-synchronised images: unstuffed bytes before every 128-byte raw row of an interval ...
+    uint4*             rowmask;     // ... and which of the row's 128 raw bytes do not reach the unstuffed copy (MCU file map without a re-walk)
     const uint4*       tiles;       // IDCT: (image, mcu_row, mcu_col0, nmcu) [ntiles], grouped by chroma replication class
     uint32_t           ntiles;
     uint32_t           tcls_first[3], tcls_count[3];   // tiles whose images have chroma eh = 1, 2, 4
@@ -114,12 +130,17 @@ struct DevBatch {
 #define JS_HUFF_WARPS 4              // warps (= restart intervals in flight) per Huffman CTA, warp kernel
 #define JS_LANE_SEGS  256            // restart intervals per CTA pass, lane kernel (8 warps x 32 lanes)
 #define JS_LANE_L2S   512            // second-level entries per table the lane kernel stages in shared memory
+#define JS_LANE_TAB   (JS_LUT_SIZE + JS_LANE_L2S)   // entries per staged table: first level, then its second level
+#define JS_ROWTAB_MIN 2048           // raw bytes from which an interval gets a row table
+#define JS_PSYNC_MIN_BLOCKS 192      // blocks per restart interval from which an image takes the self-synchronising path
 
 // launchers (jsgpu_kernels.cu) — each returns the number of kernels it enqueued
 int js_launch_marker_scan(const DevBatch& b, uint64_t max_scan_len, cudaStream_t s);
 int js_launch_unstuff(const DevBatch& b, cudaStream_t s);
 int js_launch_huffman_warp(const DevBatch& b, int sm_count, cudaStream_t s);
 int js_launch_huffman_lane(const DevBatch& b, int sm_count, cudaStream_t s);
+int js_launch_huffman_lane_vseg(const DevBatch& b, int sm_count, cudaStream_t s);   // over the virtual intervals the self-synchronising passes found
+int js_launch_selfsync(const DevBatch& b, int sm_count, cudaStream_t s);            // guess + fix rounds + scan (jsgpu_phuff.cu)
 int js_launch_idct_simple(const DevBatch& b, const int32_t* li, const float* lf, uint64_t total_blocks,
                           uint64_t total_pix, cudaStream_t s);
 struct IdctSym; struct ColorTabs;

@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(256) k_finalize_mcumap_fast(DevBatch b)
         else { k -= 1; bit = b.seg_endbits[im.seg_first + k]; }       // lazy restart: end state of the previous interval
         const uint32_t sidx = im.seg_first + k;
         const uint32_t ns = b.seg_nstuff[sidx];
-        if (ns > JS_STUFF_LIST) continue;                               // handled by the raw re-walk kernel
+        if (ns > JS_STUFF_LIST && !im.psync) continue;                  // handled by the raw re-walk kernel
         const uint32_t D = b.seg_ulen[sidx];
         uint32_t u = bit >> 3, al = bit & 7;
         uint32_t val;
@@ -325,6 +325,21 @@ __global__ void __launch_bounds__(256) k_finalize_mcumap_fast(DevBatch b)
             u = D - 1; al = 0;
         }
         uint32_t raw = u;
+        if (ns > JS_STUFF_LIST) {                                       // self-synchronised image: row table of k_unstuff
+            const uint32_t s0 = b.seg_start[sidx], len = b.seg_end[sidx] - s0;
+            const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(b.bits + im.scan_off + s0) & 3);
+            const size_t rt0 = (size_t)(im.rt_off + (s0 >> 7) + 2u * k);
+            const uint32_t nrows = (len + mis + 127) >> 7;
+            uint32_t lo = u >> 7, hi = min(nrows - 1, (u + ns + mis) >> 7);      // rowtab[r] <= 128 r: the row holding u is not before u / 128
+            while (lo < hi) { const uint32_t mid = (lo + hi + 1) >> 1; if (b.rowtab[rt0 + mid] <= u) lo = mid; else hi = mid - 1; }
+            uint32_t need = u - b.rowtab[rt0 + lo];                     // kept bytes of the row before the one we want
+            const uint4 mk = b.rowmask[rt0 + lo];
+            uint32_t w = ~mk.x, off = 0, c = __popc(w);                  // set bit = this raw byte of the row is kept
+            if (need >= c) { need -= c; w = ~mk.y; off = 32; c = __popc(w);
+                if (need >= c) { need -= c; w = ~mk.z; off = 64; c = __popc(w);
+                    if (need >= c) { need -= c; w = ~mk.w; off = 96; } } }
+            raw = (lo << 7) - mis + off + __fns(w, 0, (int)need + 1);
+        } else
         for (uint32_t j = 0; j < ns; j++) raw += (b.seg_stuff[(size_t)sidx * JS_STUFF_LIST + j] < u) ? 1u : 0u;
         val = ((im.file_pos + b.seg_start[sidx] + raw) << 4) + al;
         b.mcu_map[im.mcu_off + m] = val;

@@ -235,6 +235,11 @@ class BatchDecoder:
     def stream(self): return self.L.jsgpu_stream(self.ctx)
     def launches(self): return int(self.L.jsgpu_batch_launches(self.ctx))
 
+    def selfsync_info(self):
+        """(images on the self-synchronising path, slots, [slots changed in fix round 1, 2, ...])"""
+        a = np.zeros(16, np.uint32); self._ck(self.L.jsgpu_batch_selfsync_info(self.ctx, a.ctypes.data, 16))
+        return int(a[0]), int(a[1]), [int(v) for v in a[3:3 + int(a[2])]]
+
     def timer_start(self): self._ck(self.L.jsgpu_timer_start(self.ctx))
 
     def timer_stop(self):

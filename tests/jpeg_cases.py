@@ -53,6 +53,25 @@ def mini_cases():
     ]
 
 
+def long_cases():
+    """(name, jpeg bytes): long restart intervals — scans without restart markers (BASELINE config 5) or with a DRI of
+    whole MCU rows — which take the self-synchronising Huffman passes, plus one full 4K frame with DRI = 8 (config 3)."""
+    import mini_jpeg as MJ
+    ac_fit = MJ.long_code_table(MJ.all_ac_symbols(), n11=8)
+    return [
+        ("420_norst_4k", enc(synth_rgb(3840, 2160, 41), quality=85, subsampling=2)),                              # one image of config 5
+        ("420_dri8_4k", enc(synth_rgb(3840, 2160, 42), quality=85, subsampling=2, restart_marker_blocks=8)),      # one image of config 3
+        ("444_norst_640x480", enc(synth_rgb(640, 480, 43), quality=90, subsampling=0)),
+        ("422_opt_norst_800x600", enc(synth_rgb(800, 600, 44), quality=60, subsampling=1, optimize=True)),
+        ("gray_norst_1024x768_q30", enc(synth_rgb(1024, 768, 45)[:, :, 0], quality=30)),
+        ("420_rst2rows_1080p", enc(synth_rgb(1920, 1080, 46), quality=80, subsampling=2, restart_marker_rows=2)),
+        ("420_norst_flat", enc(np.full((480, 640, 3), 128, np.uint8), quality=85, subsampling=2)),                # hundreds of MCUs per slot
+        ("mini_longcodes_fit_420_norst", MJ.encode(synth_rgb(320, 176, 47), quality=90, samp=((2, 2), (1, 1), (1, 1)), ac_tabs=[ac_fit, ac_fit])),
+        ("mini_411_norst_shared_tables", MJ.encode(synth_rgb(400, 304, 48), quality=75, samp=((4, 1), (1, 1), (1, 1)))),   # block phase not observable: settles through k_ph_fix_cta
+        ("444_q100_noise_norst", enc(np.random.default_rng(7).integers(0, 256, (96, 128, 3)).astype(np.uint8), quality=100, subsampling=0)),
+    ]
+
+
 def compare(a, b, what=("geom", "pix_y", "pix_cb", "pix_cr", "dib", "mcu_map", "blk_dc", "dht_histo", "stats")):
     """Bit-exact comparison of two Decoded-like objects; returns list of mismatching field names."""
     bad = []

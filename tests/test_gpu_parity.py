@@ -73,19 +73,49 @@ def test_unusual_tables_and_layouts_match_oracle(built, huff):
         assert not JC.compare(orc.decode(j), got, what=("geom", "pix_y", "pix_cb", "pix_cr", "dib", "mcu_map", "blk_dc", "dht_histo")), name
 
 
-@pytest.mark.parametrize("huff", [1, 2], ids=["warp", "lane"])
+@pytest.mark.parametrize("huff", [0, 1, 2], ids=["auto_selfsync", "warp", "lane"])
+def test_long_intervals_match_oracle(built, huff):
+    """Scans without restart markers (BASELINE config 5: the reference's single serial walk, ImgDecode.cpp:3164-3630) and
+    DRIs of whole MCU rows, incl. a full 4K 4:2:0 frame; plus a full 4K frame with DRI = 8 (config 3).  huff_kernel 0 takes
+    the self-synchronising passes; 1 and 2 decode the same images as one chain per interval.  Single-image drop-in and one
+    mixed batch (long and short intervals side by side), every output buffer."""
+    from jpegsnoop_b200 import CimgDecode, BatchDecoder
+    orc = _oracle(True)
+    cases = JC.long_cases()
+    want = [orc.decode(j) for _, j in cases]
+    dec = CimgDecode(idct_fixedpt=True, huff_kernel=huff, idct_kernel=0)
+    for (name, j), w in zip(cases, want):
+        got = dec.decode(j)
+        assert got.nerr == 0 and w.nerr == 0, (name, dec.log_lines(3))
+        bad = JC.compare(w, got)
+        assert not bad, f"{name}: mismatch in {bad}"
+    short = JC.small_cases()[:2]
+    allc = [cases[0], short[0]] + cases[2:] + [short[1], cases[1]]
+    bd = BatchDecoder(huff_kernel=huff, idct_kernel=0)
+    bd.set_batch([j for _, j in allc]); bd.decode(); bd.sync()
+    if huff == 0:
+        nimg, nslots, chg = bd.selfsync_info()
+        assert nimg >= len(cases) - 1 and nslots > 0, (nimg, nslots)
+    for i, (name, j) in enumerate(allc):
+        got = bd.fetch(i)
+        assert got.status == 0, (name, got.status)
+        bad = JC.compare(orc.decode(j), got, what=("geom", "pix_y", "pix_cb", "pix_cr", "dib", "mcu_map", "blk_dc", "dht_histo"))
+        assert not bad, f"{name} (batch): mismatch in {bad}"
+
+
+@pytest.mark.parametrize("huff", [0, 1, 2], ids=["auto", "warp", "lane"])
 def test_dc_only_mode_matches_oracle(built, cases, huff):
     """CSnoopConfig::bDecodeScanImgAc = false: AC symbols are parsed but not stored (ImgDecode.cpp:1759-1766)."""
     from jpegsnoop_b200 import CimgDecode
     orc = Oracle("ref_fixed", decode_ac=False) if ref_available("fixed") else Oracle("port", idct_fixed=True, decode_ac=False)
     dec = CimgDecode(decode_ac=False, idct_fixedpt=True, huff_kernel=huff, idct_kernel=0)
-    for name, j in cases[:6] + JC.mini_cases()[:2]:
+    for name, j in cases[:6] + JC.mini_cases()[:2] + JC.long_cases()[2:4]:
         want = orc.decode(j); got = dec.decode(j)
         assert got.nerr == 0 and want.nerr == 0, (name, dec.log_lines(3))
         assert not JC.compare(want, got), name
 
 
-@pytest.mark.parametrize("huff", [1, 2], ids=["warp", "lane"])
+@pytest.mark.parametrize("huff", [0, 1, 2], ids=["auto", "warp", "lane"])
 def test_corrupt_streams_are_reported_not_fatal(built, cases, huff):
     """Truncated / bit-flipped / zero-filled scans: every kernel terminates, the damaged images carry a non-zero
     status (m_bScanBad), and a healthy image in the same batch is still bit-exact (the
@@ -192,9 +222,6 @@ def test_host_marker_walk_equals_device_marker_scan(built, cases):
         assert not JC.compare(a, b, what=("pix_y", "dib", "mcu_map", "dht_histo")), name
 
 
-# kept last in the file: not yet run on a GPU after its fix (see the reason string)
-@pytest.mark.xfail(strict=False, reason="written when round 1's GPU budget was spent: its only run failed (MCU map of an image behind a "
-                                       "skipped one) BEFORE the seg_first fix in jsgpu_batch_begin; the fix itself has not run on a GPU yet")
 def test_unsupported_images_in_a_batch_are_skipped(built, cases):
     """Images the reference's DecodeScanImg would refuse (here: 4-component CMYK scans) occupy no pool space, carry
     status 0x80000000 and do not disturb their neighbours — also at the start of an image range of the pipelined
