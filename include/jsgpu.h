@@ -200,6 +200,17 @@ int jsgpu_batch_launches(jsgpu_ctx* ctx);
  * n = capacity of info in words (16 is enough).  Forces a sync. */
 int jsgpu_batch_selfsync_info(jsgpu_ctx* ctx, uint32_t* info, uint32_t n);
 
+/* Checksums of the outputs of every image of the last jsgpu_batch_decode, computed on the device (forces a sync):
+ * ck[i][0..2] m_pPixValY/Cb/Cr, [3] the DIB, [4..6] m_pBlkDcValY/Cb/Cr, [7] m_pMcuFileMap, [8] m_anDhtHisto, [9] the nine
+ * scalars m_nAvgY, m_nBrightY/Cb/Cr, m_nBrightR/G/B, m_ptBrightMcu.x/.y, [10] the status word, [11] (img_x << 32) | img_y.
+ * Entries of absent buffers (Cb/Cr of a one-component scan, skipped images) are 0.  Each checksum is
+ *   sum over 32-bit little-endian words w_i of the buffer (16-bit buffers: two elements per word, an odd last element
+ *   zero-extended) of  mix(w_i, i),  mix(w, i): x = w + (i+1)*0x9E3779B97F4A7C15; x ^= x >> 32; x *= 0xD6E8FEB86659FD93;
+ *   x ^= x >> 29   (64-bit wrap-around arithmetic),
+ * so a caller holding the reference's buffers (ImgDecode.h:444-461) can verify a whole batch without copying it back. */
+#define JSGPU_CK_WORDS 12
+int jsgpu_batch_checksums(jsgpu_ctx* ctx, uint64_t* ck, uint32_t n);
+
 /* One-call end-to-end form: host bitstream in, host outputs out (any pointer may be NULL to
  * skip that output).  Output buffers hold the images back to back in batch order using the
  * element offsets of jsgpu_batch_layout.  Small batches run H2D, decode and D2H on the context
@@ -220,6 +231,11 @@ int jsgpu_decode_batch_host(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32
 /* Pinned host memory helpers (for callers that want true async copies). */
 void* jsgpu_host_alloc(uint64_t bytes);
 void  jsgpu_host_free(void* p);
+/* Raw copy rate of this box between pinned host memory and the context's device: `bytes` are copied `reps` times with
+ * cudaMemcpyAsync on the context stream and timed with CUDA events; direction 0 = host->device, 1 = device->host.
+ * *gbs receives the best repetition in GB/s.  This is the ceiling jsgpu_decode_batch_host can reach (its time is the
+ * device->host copy of the reference's outputs); bench.py reports its end-to-end figure as a fraction of it. */
+int jsgpu_host_copy_rate(jsgpu_ctx* ctx, int direction, uint64_t bytes, int reps, float* gbs);
 
 #ifdef __cplusplus
 }

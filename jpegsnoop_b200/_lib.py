@@ -63,8 +63,8 @@ JSGPU_SYMBOLS = [
     "jsgpu_init", "jsgpu_free", "jsgpu_last_error", "jsgpu_strerror", "jsgpu_version", "jsgpu_stream", "jsgpu_sync",
     "jsgpu_set_idct_tables", "jsgpu_set_options", "jsgpu_get_options", "jsgpu_upload_tables",
     "jsgpu_batch_begin", "jsgpu_batch_layout", "jsgpu_batch_pools", "jsgpu_batch_upload", "jsgpu_batch_decode",
-    "jsgpu_batch_download", "jsgpu_batch_stage_ms", "jsgpu_timer_start", "jsgpu_timer_stop", "jsgpu_batch_launches", "jsgpu_batch_selfsync_info", "jsgpu_decode_batch_host",
-    "jsgpu_host_alloc", "jsgpu_host_free"]
+    "jsgpu_batch_download", "jsgpu_batch_stage_ms", "jsgpu_timer_start", "jsgpu_timer_stop", "jsgpu_batch_launches", "jsgpu_batch_selfsync_info", "jsgpu_batch_checksums", "jsgpu_decode_batch_host",
+    "jsgpu_host_alloc", "jsgpu_host_free", "jsgpu_host_copy_rate"]
 JSIMG_SYMBOLS = [
     "jsimg_create", "jsimg_destroy", "jsimg_config", "jsimg_set_file", "jsimg_overlay_install", "jsimg_Reset", "jsimg_ResetState",
     "jsimg_SetDqtEntry", "jsimg_SetDqtTables", "jsimg_GetDqtEntry", "jsimg_SetDhtTables", "jsimg_SetDhtEntry",
@@ -106,11 +106,13 @@ def load():
     L.jsgpu_batch_stage_ms.argtypes = [vp, vp]
     L.jsgpu_batch_launches.argtypes = [vp]
     L.jsgpu_batch_selfsync_info.argtypes = [vp, vp, u32]
+    L.jsgpu_batch_checksums.argtypes = [vp, vp, u32]
     L.jsgpu_timer_start.argtypes = [vp]
     L.jsgpu_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
     L.jsgpu_decode_batch_host.argtypes = [vp, vp, u32, vp, u64, C.POINTER(jsgpu_host_outputs)]
     L.jsgpu_host_alloc.argtypes = [u64]; L.jsgpu_host_alloc.restype = vp
     L.jsgpu_host_free.argtypes = [vp]; L.jsgpu_host_free.restype = None
+    L.jsgpu_host_copy_rate.argtypes = [vp, i32, u64, i32, C.POINTER(C.c_float)]
     L.jsimg_create.restype = vp
     L.jsimg_destroy.argtypes = [vp]; L.jsimg_destroy.restype = None
     L.jsimg_config.argtypes = [vp] + [i32] * 6; L.jsimg_config.restype = None

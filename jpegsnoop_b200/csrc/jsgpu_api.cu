@@ -605,6 +605,24 @@ int jsgpu_timer_stop(jsgpu_ctx* ctx, float* ms)
 
 int jsgpu_batch_launches(jsgpu_ctx* ctx) { return ctx ? ctx->launches : JSGPU_EINVAL; }
 
+int jsgpu_batch_checksums(jsgpu_ctx* ctx, uint64_t* ck, uint32_t n)
+{
+    if (!ctx || !ck) return JSGPU_EINVAL;
+    if (!ctx->decoded || ctx->host_delivered) return fail(ctx, JSGPU_ESTATE, "no device-resident decode to checksum");
+    if (n > ctx->himg.size()) n = (uint32_t)ctx->himg.size();
+    cudaSetDevice(ctx->device);
+    static_assert(JSGPU_CK_WORDS == JSGPU_CK_WORDS_INTERNAL, "checksum layout");
+    DevBuf tmp;
+    CK(tmp.reserve((size_t)ctx->himg.size() * JSGPU_CK_WORDS * 8));
+    js_launch_checksums(ctx->batch, (unsigned long long*)tmp.p, ctx->stream);
+    cudaError_t e = cudaMemcpyAsync(ck, tmp.p, (size_t)n * JSGPU_CK_WORDS * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    tmp.release();
+    if (e != cudaSuccess) return fail(ctx, JSGPU_ECUDA, "checksum kernel failed: %s", cudaGetErrorString(e));
+    return JSGPU_OK;
+}
+
 int jsgpu_batch_selfsync_info(jsgpu_ctx* ctx, uint32_t* info, uint32_t n)
 {
     if (!ctx || !info || n < 4) return JSGPU_EINVAL;
@@ -755,6 +773,31 @@ int jsgpu_decode_batch_host(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32
         ctx->launches += k->launches;
     }
     ctx->decoded = true; ctx->host_delivered = true;
+    return JSGPU_OK;
+}
+
+int jsgpu_host_copy_rate(jsgpu_ctx* ctx, int direction, uint64_t bytes, int reps, float* gbs)
+{
+    if (!ctx || !gbs || bytes == 0 || reps < 1 || direction < 0 || direction > 1) return JSGPU_EINVAL;
+    cudaSetDevice(ctx->device);
+    void* h = nullptr; void* d = nullptr;
+    if (cudaMallocHost(&h, bytes) != cudaSuccess) return fail(ctx, JSGPU_ENOMEM, "pinned allocation of %llu bytes failed", (unsigned long long)bytes);
+    if (cudaMalloc(&d, bytes) != cudaSuccess) { cudaFreeHost(h); return fail(ctx, JSGPU_ENOMEM, "device allocation of %llu bytes failed", (unsigned long long)bytes); }
+    memset(h, 1, bytes);                                        // touch the pages (first-touch NUMA placement happens here)
+    cudaMemsetAsync(d, 0, bytes, ctx->stream);
+    float best = 0.f; cudaError_t e = cudaSuccess;
+    for (int r = 0; r < reps + 1 && e == cudaSuccess; r++) {     // first repetition = warm-up
+        cudaEventRecord(ctx->tev[0], ctx->stream);
+        e = direction ? cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx->stream) : cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream);
+        cudaEventRecord(ctx->tev[1], ctx->stream);
+        if (e == cudaSuccess) e = cudaEventSynchronize(ctx->tev[1]);
+        float ms = 0.f;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, ctx->tev[0], ctx->tev[1]);
+        if (r > 0 && ms > 0.f) best = std::max(best, (float)(bytes / 1e6 / ms));
+    }
+    cudaFree(d); cudaFreeHost(h);
+    if (e != cudaSuccess) return fail(ctx, JSGPU_ECUDA, "copy-rate probe failed: %s", cudaGetErrorString(e));
+    *gbs = best;
     return JSGPU_OK;
 }
 

@@ -151,6 +151,8 @@ int js_upload_idct_constants(const IdctSym* host_sym, cudaStream_t s);
 int js_make_coef_tensor_map(void* out_tmap, void* coef, uint64_t rows);
 int js_launch_idct_tma(const DevBatch& b, const IdctSym* sym, const ColorTabs* ctab, const void* tmap_host, int sm_count, cudaStream_t s);
 int js_launch_finalize(const DevBatch& b, cudaStream_t s);
+#define JSGPU_CK_WORDS_INTERNAL 12   // == JSGPU_CK_WORDS (include/jsgpu.h)
+int js_launch_checksums(const DevBatch& b, unsigned long long* ck, cudaStream_t s);
 int js_launch_finalize_emptied(const DevBatch& b, cudaStream_t s);   // after js_launch_finalize: drained-interval MCU map entries
 
 // Quadrant-symmetric decomposition of the integer IDCT table (built on the host at table upload,

@@ -358,3 +358,76 @@ int js_launch_finalize(const DevBatch& b, cudaStream_t s)
     }
     return n;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Output checksums (jsgpu_batch_checksums): one 64-bit sum per output buffer of every image, computed where the
+// outputs live, so that a batch caller (bench.py verifies EVERY image of EVERY rank this way) can compare a whole
+// batch with the reference's CPU decode without moving 21 MB per image over PCIe.  The sum is over 32-bit words w_i
+// (16-bit buffers: two elements per word, an odd last element zero-extended) of mix(w_i, i): order-independent to
+// accumulate, position-sensitive.  tests/oracle harness (oracle/ref_harness.cpp: ck_words) computes the same.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ck_mix(uint32_t w, unsigned long long i)
+{
+    unsigned long long x = (unsigned long long)w + (i + 1ull) * 0x9E3779B97F4A7C15ull;
+    x ^= x >> 32; x *= 0xD6E8FEB86659FD93ull; x ^= x >> 29;
+    return x;
+}
+// words [0, nfull) of p, plus (odd16) the low half of word nfull
+__device__ __forceinline__ unsigned long long ck_span(const uint32_t* p, unsigned long long nfull, bool odd16, unsigned long long first, unsigned long long step)
+{
+    unsigned long long s = 0;
+    for (unsigned long long i = first; i < nfull; i += step) s += ck_mix(__ldg(p + i), i);
+    if (odd16 && first == 0) s += ck_mix((uint32_t)reinterpret_cast<const uint16_t*>(p)[2 * nfull], nfull);
+    return s;
+}
+__global__ void __launch_bounds__(256) k_checksums(DevBatch b, unsigned long long* ck)
+{
+    __shared__ unsigned long long s_red[8];
+    const uint32_t ii = blockIdx.y;
+    const DevImage& im = b.img[ii];
+    if (!im.valid) return;
+    const unsigned long long first = blockIdx.x * blockDim.x + threadIdx.x, step = (unsigned long long)gridDim.x * blockDim.x;
+    const unsigned long long npx = (unsigned long long)im.wp * im.hp, nblk = (unsigned long long)im.blk_xmax * im.blk_ymax;
+    for (int w = 0; w < 10; w++) {
+        unsigned long long s = 0;
+        const bool c3 = im.ns == 3;
+        switch (w) {
+        case 0: s = ck_span(reinterpret_cast<const uint32_t*>(b.pix_y + im.pix_off), npx >> 1, npx & 1, first, step); break;
+        case 1: if (c3) s = ck_span(reinterpret_cast<const uint32_t*>(b.pix_cb + im.pix_off), npx >> 1, npx & 1, first, step); break;
+        case 2: if (c3) s = ck_span(reinterpret_cast<const uint32_t*>(b.pix_cr + im.pix_off), npx >> 1, npx & 1, first, step); break;
+        case 3: s = ck_span(reinterpret_cast<const uint32_t*>(b.dib + im.dib_off), npx, false, first, step); break;
+        case 4: s = ck_span(reinterpret_cast<const uint32_t*>(b.blk_y + im.blk_off), nblk >> 1, nblk & 1, first, step); break;
+        case 5: if (c3) s = ck_span(reinterpret_cast<const uint32_t*>(b.blk_cb + im.blk_off), nblk >> 1, nblk & 1, first, step); break;
+        case 6: if (c3) s = ck_span(reinterpret_cast<const uint32_t*>(b.blk_cr + im.blk_off), nblk >> 1, nblk & 1, first, step); break;
+        case 7: s = ck_span(b.mcu_map + im.mcu_off, im.nmcu, false, first, step); break;
+        case 8: s = ck_span(b.histo + (size_t)ii * 2 * 4 * 17, 2 * 4 * 17, false, first, step); break;
+        case 9: s = ck_span(reinterpret_cast<const uint32_t*>(b.stats + (size_t)ii * 16 + 2), 9, false, first, step); break;    // m_nAvgY, brightest pixel Y/Cb/Cr/R/G/B, its MCU
+        }
+        #pragma unroll
+        for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(FULL, s, d);
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long t = 0;
+            for (int q = 0; q < 8; q++) t += s_red[q];
+            if (t) atomicAdd(&ck[(size_t)ii * JSGPU_CK_WORDS_INTERNAL + w], t);
+        }
+        __syncthreads();
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        ck[(size_t)ii * JSGPU_CK_WORDS_INTERNAL + 10] = b.img_status[ii];
+        ck[(size_t)ii * JSGPU_CK_WORDS_INTERNAL + 11] = ((unsigned long long)im.wp << 32) | im.hp;
+    }
+}
+
+int js_launch_checksums(const DevBatch& b, unsigned long long* ck, cudaStream_t s)
+{
+    if (b.nimg == 0) return 0;
+    cudaMemsetAsync(ck, 0, (size_t)b.nimg * JSGPU_CK_WORDS_INTERNAL * 8, s);
+    for (uint32_t i0 = 0; i0 < b.nimg; i0 += 65535u) {           // grid.y limit
+        DevBatch bb = b; bb.img = b.img + i0; bb.nimg = std::min<uint32_t>(b.nimg - i0, 65535u);
+        bb.histo = b.histo + (size_t)i0 * 2 * 4 * 17; bb.stats = b.stats + (size_t)i0 * 16; bb.img_status = b.img_status + i0;
+        k_checksums<<<dim3(32, bb.nimg), 256, 0, s>>>(bb, ck + (size_t)i0 * JSGPU_CK_WORDS_INTERNAL);
+    }
+    return 1;
+}

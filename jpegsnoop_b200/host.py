@@ -235,6 +235,14 @@ class BatchDecoder:
     def stream(self): return self.L.jsgpu_stream(self.ctx)
     def launches(self): return int(self.L.jsgpu_batch_launches(self.ctx))
 
+    def host_copy_rate(self, direction=1, nbytes=1 << 30, reps=3):
+        """GB/s of a plain cudaMemcpyAsync between pinned host memory and this GPU (1 = device->host)."""
+        g = C.c_float(0); self._ck(self.L.jsgpu_host_copy_rate(self.ctx, direction, nbytes, reps, C.byref(g))); return float(g.value)
+
+    def checksums(self):
+        """uint64 [n][12]: device-side checksums of every output buffer of every image (include/jsgpu.h)."""
+        a = np.zeros((self.n, 12), np.uint64); self._ck(self.L.jsgpu_batch_checksums(self.ctx, a.ctypes.data, self.n)); return a
+
     def selfsync_info(self):
         """(images on the self-synchronising path, slots, [slots changed in fix round 1, 2, ...])"""
         a = np.zeros(16, np.uint32); self._ck(self.L.jsgpu_batch_selfsync_info(self.ctx, a.ctypes.data, 16))

@@ -213,4 +213,58 @@ double ref_bench(const uint8_t* const* datas,const uint64_t* lens,int n,int thre
 	return std::chrono::duration<double>(t1-t0).count();
 }
 
+// Checksums of one decode's outputs, as include/jsgpu.h defines them for jsgpu_batch_checksums (the GPU path computes
+// the same sums on the device): bench.py verifies every image of every rank by comparing the two.
+static inline uint64_t ck_mix(uint32_t w,uint64_t i) {
+	uint64_t x=(uint64_t)w+(i+1)*0x9E3779B97F4A7C15ull; x^=x>>32; x*=0xD6E8FEB86659FD93ull; x^=x>>29; return x;
+}
+static uint64_t ck_words(const void* p,uint64_t nbytes) {       // nbytes even; 32-bit LE words, an odd 16-bit tail zero-extended
+	if (!p) return 0;
+	const uint8_t* b=(const uint8_t*)p; uint64_t s=0,nw=nbytes/4;
+	for (uint64_t i=0;i<nw;i++) { uint32_t w; memcpy(&w,b+4*i,4); s+=ck_mix(w,i); }
+	if (nbytes&2) { uint16_t h; memcpy(&h,b+4*nw,2); s+=ck_mix(h,nw); }
+	return s;
+}
+static void ck_decode(RefCtx* c,uint64_t* ck /*[12]*/) {
+	CimgDecode* d=c->dec;
+	const bool c3=(d->m_nNumSosComps==3);
+	const uint64_t npx=(uint64_t)d->m_nImgSizeX*d->m_nImgSizeY, nblk=(uint64_t)d->m_nBlkXMax*d->m_nBlkYMax, nmcu=(uint64_t)d->m_nMcuXMax*d->m_nMcuYMax;
+	ck[0]=ck_words(d->m_pPixValY,npx*2); ck[1]=c3?ck_words(d->m_pPixValCb,npx*2):0; ck[2]=c3?ck_words(d->m_pPixValCr,npx*2):0;
+	ck[3]=ck_words(ref_dib(c),npx*4);
+	ck[4]=ck_words(d->m_pBlkDcValY,nblk*2); ck[5]=c3?ck_words(d->m_pBlkDcValCb,nblk*2):0; ck[6]=c3?ck_words(d->m_pBlkDcValCr,nblk*2):0;
+	ck[7]=ck_words(d->m_pMcuFileMap,nmcu*4);
+	ck[8]=ck_words(d->m_anDhtHisto,sizeof(d->m_anDhtHisto));
+	int32_t st[12]; ref_stats(c,st);
+	int32_t nine[9]={st[0],st[2],st[3],st[4],st[5],st[6],st[7],st[8],st[9]};
+	ck[9]=ck_words(nine,sizeof nine);
+	ck[10]=(uint64_t)c->log.errs.size();
+	ck[11]=((uint64_t)d->m_nImgSizeX<<32)|d->m_nImgSizeY;
+}
+
+// ref_bench + checksums: every image is decoded once; ck receives 12 words per image.
+double ref_bench_ck(const uint8_t* const* datas,const uint64_t* lens,int n,int threads,uint64_t* ck,int* err_lines)
+{
+	if (threads<1) threads=1;
+	std::vector<std::unique_ptr<RefCtx>> ctx;
+	for (int t=0;t<threads;t++) ctx.emplace_back(new RefCtx());
+	std::atomic<int> next(0); std::atomic<int> errs(0);
+	auto t0=std::chrono::steady_clock::now();
+	std::vector<std::thread> th;
+	for (int t=0;t<threads;t++) th.emplace_back([&,t]{
+		RefCtx* c=ctx[(size_t)t].get();
+		for (;;) {
+			int k=next.fetch_add(1); if (k>=n) break;
+			c->log.Clear();
+			int r=walk_and_decode(c,datas[k],lens[k],1,1);
+			if (r<0) { errs.fetch_add(1); memset(ck+(size_t)k*12,0,96); continue; }
+			errs.fetch_add((int)c->log.errs.size());
+			ck_decode(c,ck+(size_t)k*12);
+		}
+	});
+	for (auto& x:th) x.join();
+	auto t1=std::chrono::steady_clock::now();
+	if (err_lines) *err_lines=errs.load();
+	return std::chrono::duration<double>(t1-t0).count();
+}
+
 } // extern "C"

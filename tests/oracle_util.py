@@ -121,6 +121,19 @@ class Oracle:
         d.nerr = self._f("num_err_lines")(self.ctx)
         return d
 
+    def bench_ck(self, jpegs, threads=1):
+        """Decode every JPEG once on `threads` host threads; returns (wall seconds, error lines, uint64 [n][12] checksums
+        of every output buffer — the layout of jsgpu_batch_checksums, include/jsgpu.h).  Compiled reference only."""
+        assert self.kind != "port"
+        bufs = [np.frombuffer(j, np.uint8) for j in jpegs]
+        n = len(bufs)
+        ptrs = (C.c_void_p * n)(*[b.ctypes.data for b in bufs])
+        lens = (C.c_uint64 * n)(*[b.size for b in bufs])
+        ck = np.zeros((n, 12), np.uint64); errs = C.c_int(0)
+        self.lib.ref_bench_ck.restype = C.c_double
+        t = self.lib.ref_bench_ck(ptrs, lens, n, threads, C.c_void_p(ck.ctypes.data), C.byref(errs))
+        return float(t), int(errs.value), ck
+
     def bench(self, jpegs, threads=1, reps=1):
         """Wall seconds to decode every JPEG in `jpegs` `reps` times on `threads` host threads."""
         bufs = [np.frombuffer(j, np.uint8).copy() for j in jpegs]
@@ -133,6 +146,27 @@ class Oracle:
         else:
             t = self.lib.ref_bench(ptrs, lens, n, threads, reps, C.byref(errs))
         return float(t), int(errs.value)
+
+
+def effective_cores():
+    """Host threads this process can really use: the affinity mask, capped by the cgroup CPU quota (a container on a
+    128-thread box may be limited to a handful of cores: os.cpu_count() says nothing about that)."""
+    import math
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    quota = None
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            quota = float(q) / float(p)
+    except Exception:
+        try:
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read()); p = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / p
+        except Exception:
+            pass
+    eff = n if quota is None else max(1, min(n, int(math.ceil(quota))))
+    return eff, {"os_cpu_count": os.cpu_count(), "affinity": n, "cgroup_quota_cores": quota}
 
 
 def dib_to_rgb(dib):
