@@ -53,7 +53,7 @@ struct jsgpu_ctx {
     DevBatch batch;
     uint64_t bits_len = 0, pix_total = 0, dib_total = 0, blk_total = 0, mcu_total = 0, coef_rows = 0;
     uint64_t max_scan_len = 0, ubits_total = 0, ph_total = 0, rt_total = 0;
-    uint32_t nseg_np = 0, n_psync = 0;
+    uint32_t nseg_np = 0, n_psync = 0, max_cs = 0; uint64_t cs_total = 0;
     alignas(64) unsigned char tmap[128]; bool tmap_ok = false;
     uint32_t n_nonstd = 0, n_std = 0;
     int launches = 0;
@@ -305,7 +305,7 @@ int jsgpu_batch_begin(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, 
     ctx->layout.assign(n, jsgpu_image_layout());
     uint64_t pix = 0, dib = 0, blk = 0, mcu = 0, rows = 0, max_scan = 0, ub = 0;
     uint32_t seg = 0, n_std = 0, n_nonstd = 0, plane_bytes = 0, seg_np = 0, n_psync = 0;
-    uint64_t pht = 0, rtt = 0;
+    uint64_t pht = 0, rtt = 0, cst = 0; uint32_t max_cs = 0;
     std::vector<uint2> items, litems, items_np, litems_np, vitems;
     std::vector<uint4> tiles, tcls[3];
     for (uint32_t i = 0; i < n; i++) {
@@ -337,6 +337,7 @@ int jsgpu_batch_begin(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, 
             n_psync++;
             im.ph_nslots = (uint32_t)(uregion >> 9) + im.nseg + 2; im.ph_first = pht; pht += (uint64_t)im.ph_nslots + 1;
             im.rt_off = rtt; rtt += (im.scan_len >> 7) + 2ull * im.nseg + 4;
+            im.cs_nslots = (uint32_t)(im.scan_len >> 12) + 2 * im.nseg + 2; im.cs_first = cst; cst += im.cs_nslots; max_cs = std::max(max_cs, im.cs_nslots);
             for (uint32_t k = 0; k < im.ph_nslots; k += JS_LANE_SEGS) vitems.push_back(make_uint2(i, k));
         } else {
             seg_np += im.nseg;
@@ -362,7 +363,7 @@ int jsgpu_batch_begin(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, 
     for (int k = 0; k < 3; k++) { tcls_first[k] = (uint32_t)tiles.size(); tcls_count[k] = (uint32_t)tcls[k].size(); tiles.insert(tiles.end(), tcls[k].begin(), tcls[k].end()); }
     ctx->bits_len = bitstream_bytes; ctx->pix_total = pix; ctx->dib_total = dib; ctx->blk_total = blk; ctx->mcu_total = mcu;
     ctx->coef_rows = rows; ctx->max_scan_len = max_scan; ctx->ubits_total = ub; ctx->n_std = n_std; ctx->n_nonstd = n_nonstd;
-    ctx->ph_total = pht; ctx->rt_total = rtt; ctx->nseg_np = seg_np; ctx->n_psync = n_psync;
+    ctx->ph_total = pht; ctx->rt_total = rtt; ctx->nseg_np = seg_np; ctx->n_psync = n_psync; ctx->max_cs = max_cs; ctx->cs_total = cst;
     ctx->host_delivered = false; ctx->layout_only = ctx->plan_only;
     if (ctx->plan_only) { ctx->planned = true; return JSGPU_OK; }
     // allocate
@@ -372,7 +373,7 @@ int jsgpu_batch_begin(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, 
     CK(ctx->d_ubits.reserve(ub + 16384));          // + slack: a reader of corrupt data stops at the next MCU boundary, at most one MCU (<= 12 KB of bits) past the end
     CK(ctx->d_litems.reserve(sizeof(uint2) * std::max<size_t>(litems.size() + litems_np.size() + vitems.size(), 1)));
     CK(ctx->d_ph.reserve(pht * 64 + 256));                      // x 8 + ver 4 + k 4 + cnt 16 + aux 16 + pre 16 bytes per slot
-    CK(ctx->d_rowtab.reserve(rtt * 20 + 256));                  // rowtab 4 + rowmask 16 bytes per 128-byte raw row
+    CK(ctx->d_rowtab.reserve(rtt * 20 + cst * 12 + 256));       // rowtab 4 + rowmask 16 bytes per 128-byte raw row; 3 words per 4 KB chunk
     CK(ctx->d_tiles.reserve(sizeof(uint4) * std::max<size_t>(tiles.size(), 1)));
     CK(ctx->d_seg64.reserve(8 * (size_t)seg + 16));
     CK(ctx->d_seg.reserve(sizeof(uint32_t) * ((7 + JS_STUFF_LIST) * (size_t)seg + 2 * (size_t)n + 16)));
@@ -412,6 +413,7 @@ int jsgpu_batch_begin(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, 
         b.ph_cnt = (uint4*)q; q += pht * 16; b.ph_aux = (uint4*)q; q += pht * 16; b.ph_pre = (uint4*)q; q += pht * 16;
         b.ph_x = (unsigned long long*)q; q += pht * 8; b.ph_ver = (uint32_t*)q; q += pht * 4; b.ph_k = (uint32_t*)q;
         b.rowmask = (uint4*)ctx->d_rowtab.p; b.rowtab = (uint32_t*)((uint8_t*)ctx->d_rowtab.p + rtt * 16);
+        b.cs_cnt = b.rowtab + rtt; b.cs_off = b.cs_cnt + cst; b.cs_seg = b.cs_off + cst;
     }
     b.tiles = (const uint4*)ctx->d_tiles.p; b.ntiles = (uint32_t)tiles.size(); b.tile_plane_bytes = plane_bytes;
     for (int k = 0; k < 3; k++) { b.tcls_first[k] = tcls_first[k]; b.tcls_count[k] = tcls_count[k]; }
@@ -539,7 +541,10 @@ int jsgpu_batch_decode(jsgpu_ctx* ctx)
         CK(cudaStreamSynchronize(s));
         host_marker_walk(ctx, hb.data());
     }
-    launches += js_launch_unstuff(b, s);
+    // long intervals: chunk-parallel unstuffing into the pre-zeroed pool (chunk edges are OR-ed in)
+    if (ctx->n_psync) CK(cudaMemsetAsync(ctx->d_ubits.p, 0, ctx->ubits_total + 16384, s));
+    if (ctx->n_psync < ctx->n_std + ctx->n_nonstd) launches += js_launch_unstuff(b, s);
+    if (ctx->n_psync) launches += js_launch_unstuff_long(b, ctx->max_cs, s);
     CK(cudaEventRecord(ctx->ev[1], s));
     {
         // huff_kernel: 1 = one warp per restart interval for everything, 2 = one lane per restart interval for everything,

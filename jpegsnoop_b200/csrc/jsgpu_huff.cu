@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(128) k_unstuff(DevBatch b)
     };
     for (uint32_t ii = blockIdx.y; ii < b.nimg; ii += gridDim.y) {            // grid.y = image (strided beyond 65535 images)
     const DevImage& im = b.img[ii];
-    if (!im.valid) continue;
+    if (!im.valid || im.psync) continue;        // long intervals: k_unstuff_long (a warp per 4 KB, not per interval)
     const uint32_t nseg = im.nseg, seg_first = im.seg_first, kstep = (gridDim.x * blockDim.x) >> 5;
     const uint8_t* const scan = b.bits + im.scan_off;
     const uint64_t ubase = im.ubits_off;
@@ -69,9 +69,6 @@ __global__ void __launch_bounds__(128) k_unstuff(DevBatch b)
     const uint32_t* abase = reinterpret_cast<const uint32_t*>(seg - mis);
     uint32_t wr = 0, fl = 0, carry = 0;
     const uint32_t lt = (1u << lane) - 1;
-    // self-synchronised images: per 128-byte raw row, the unstuffed bytes before it and the mask of its bytes that do not
-    // reach the output, so that k_finalize_mcumap_fast turns an unstuffed index into a file offset without re-walking
-    const size_t rt0 = im.psync ? (size_t)(im.rt_off + (s0 >> 7) + 2u * k) : 0;
     if (lane == 0) s_cnt[wid] = 0;
     __syncwarp();
     // rows are requested one ahead of their use
@@ -99,12 +96,6 @@ __global__ void __launch_bounds__(128) k_unstuff(DevBatch b)
         const uint32_t rm = dn | (vn ^ 15u);                                                // bytes that do not reach the output
         const uint32_t kk = __byte_perm(word, 0, s_sel[rm]);
         const uint32_t cnt = 4 - __popc(rm);                                                // 0..4 kept bytes
-        if (im.psync) {                          // warp-uniform
-            uint32_t mw = rm << ((lane & 7) * 4);
-            mw |= __shfl_xor_sync(FULL, mw, 1); mw |= __shfl_xor_sync(FULL, mw, 2); mw |= __shfl_xor_sync(FULL, mw, 4);
-            if ((lane & 7) == 0) reinterpret_cast<uint32_t*>(b.rowmask + rt0 + (rpos >> 7))[lane >> 3] = mw;
-            if (lane == 0) b.rowtab[rt0 + (rpos >> 7)] = wr;
-        }
         const uint32_t b0 = __ballot_sync(FULL, cnt & 1), b1 = __ballot_sync(FULL, cnt & 2), b2 = __ballot_sync(FULL, cnt & 4);
         const uint32_t o = wr + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
         if (__any_sync(FULL, dn != 0)) {              // remember where bytes were dropped (MCU file map): unstuffed index of the preceding FF
@@ -141,7 +132,7 @@ __global__ void __launch_bounds__(128) k_unstuff(DevBatch b)
     if (lane == 0) {
         const uint32_t nstuff = s_cnt[wid];
         b.seg_ulen[gw] = wr; b.seg_uoff[gw] = dst0; b.seg_nstuff[gw] = nstuff;
-        if (nstuff > JS_STUFF_LIST && !im.psync) b.ovf_list[atomicAdd(b.ovf_count, 1u)] = gw;     // rare: the MCU map of this interval needs the raw re-walk
+        if (nstuff > JS_STUFF_LIST) b.ovf_list[atomicAdd(b.ovf_count, 1u)] = gw;     // rare: the MCU map of this interval needs the raw re-walk
     }
     __syncwarp();
     }
@@ -157,6 +148,197 @@ int js_launch_unstuff(const DevBatch& b, cudaStream_t s)
     if (grid.x > want) grid.x = want < 1 ? 1 : want;
     k_unstuff<<<grid, 128, 0, s>>>(b);
     return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// unstuff, long intervals (images on the self-synchronising path): one warp per 4096 raw bytes instead of one warp
+// per interval, so that a scan without restart markers (one 2.5 MB interval per 4K image) is not one serial walk:
+//   k_unstuff_count   warp per chunk: how many bytes of the chunk reach the output
+//   k_unstuff_scan    warp per interval: exclusive prefix sums -> output offset of every chunk; interval totals
+//   k_unstuff_long    warp per chunk: the same row logic as k_unstuff, written at the chunk's output offset.  Chunk
+//                     boundaries fall inside 16-byte groups and 32-bit words of the output, so the first group and the
+//                     tail of every chunk are OR-ed into the (pre-zeroed) pool with atomics; everything in between
+//                     leaves as whole 16-byte stores.
+// The row tables for the MCU file map (rowtab / rowmask) are written as in k_unstuff.
+// ------------------------------------------------------------------------------------------------
+#define UL_WARPS 8
+__device__ __forceinline__ uint32_t ul_base(uint32_t s0, uint32_t k) { return (s0 >> 12) + 2u * k; }
+// interval (index inside the image) owning chunk slot cs and the chunk's index inside it; false = unused slot
+__device__ __forceinline__ bool ul_find(const DevBatch& b, const DevImage& im, uint32_t cs, uint32_t& k, uint32_t& j, uint32_t& s0, uint32_t& len, uint32_t& mis)
+{
+    uint32_t lo = 0, hi = im.nseg - 1;
+    while (lo < hi) { const uint32_t mid = (lo + hi + 1) >> 1; if (ul_base(b.seg_start[im.seg_first + mid], mid) <= cs) lo = mid; else hi = mid - 1; }
+    k = lo; s0 = b.seg_start[im.seg_first + k]; len = b.seg_end[im.seg_first + k] - s0;
+    mis = (uint32_t)(reinterpret_cast<uintptr_t>(b.bits + im.scan_off + s0) & 3);
+    const uint32_t base = ul_base(s0, k), nch = len ? ((len + mis + 4095) >> 12) : 0u;
+    if (cs < base || cs - base >= nch) return false;
+    j = cs - base;
+    return true;
+}
+// One 128-byte raw row of an interval: this lane's word, the nibble `rm` of its bytes that do not reach the output
+// (stuffed zeros, bytes outside the interval) and the stuffed-zero nibble `dn`.  carry = the previous row's last word.
+__device__ __forceinline__ void ul_row(const uint32_t* abase, uint32_t rpos, uint32_t lane, uint32_t mis, uint32_t len, uint32_t& carry, uint32_t& word, uint32_t& rm)
+{
+    const int rel0 = (int)(rpos + 4 * lane) - (int)mis;
+    word = (rel0 + 3 >= 0 && rel0 < (int)len) ? __ldg(abase + (rpos >> 2) + lane) : 0u;
+    uint32_t up = __shfl_up_sync(FULL, word, 1);
+    if (lane == 0) up = carry;
+    carry = __shfl_sync(FULL, word, 31);
+    const int vlo = max(0, -rel0), vhi = min(4, (int)len - rel0);
+    const uint32_t vn = (vhi > vlo) ? (((1u << vhi) - 1u) & ~((1u << vlo) - 1u)) : 0u;
+    const uint32_t an = (rel0 <= 0 && rel0 > -4) ? (vn & ~(1u << (-rel0))) : vn;
+    const uint32_t pw = __byte_perm(up, word, 0x6543);
+    const uint32_t npw = ~pw;
+    const uint32_t z = ~(((word & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | word | 0x7F7F7F7Fu);
+    const uint32_t f = ~(((npw & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | npw | 0x7F7F7F7Fu);
+    const uint32_t dn = ((((z & f) >> 7) * 0x00204081u) >> 21) & an;
+    rm = dn | (vn ^ 15u);
+}
+
+__global__ void __launch_bounds__(UL_WARPS * 32) k_unstuff_count(DevBatch b)
+{
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint32_t ii = blockIdx.y; ii < b.nimg; ii += gridDim.y) {
+        const DevImage& im = b.img[ii];
+        if (!im.valid || !im.psync) continue;
+        for (uint32_t cs = blockIdx.x * UL_WARPS + wid; cs < im.cs_nslots; cs += gridDim.x * UL_WARPS) {
+            uint32_t k, j, s0, len, mis;
+            if (!ul_find(b, im, cs, k, j, s0, len, mis)) { if (lane == 0) { b.cs_cnt[im.cs_first + cs] = 0; b.cs_seg[im.cs_first + cs] = 0xffffffffu; } continue; }
+            const uint32_t* abase = reinterpret_cast<const uint32_t*>(b.bits + im.scan_off + s0 - mis);
+            uint32_t carry = j ? __ldg(abase + (j << 10) - 1) : 0u, tot = 0;
+            uint32_t rp0 = j << 12;
+            for (uint32_t r = 0; r < 32 && rp0 + 128 * r < len + mis; r++) {
+                uint32_t word, rm;
+                ul_row(abase, rp0 + 128 * r, lane, mis, len, carry, word, rm);
+                tot += 4 - __popc(rm);
+            }
+            tot = __reduce_add_sync(FULL, tot);
+            if (lane == 0) { b.cs_cnt[im.cs_first + cs] = tot; b.cs_seg[im.cs_first + cs] = k; }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_unstuff_scan(DevBatch b)
+{
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint32_t ii = blockIdx.x; ii < b.nimg; ii += gridDim.x) {
+        const DevImage& im = b.img[ii];
+        if (!im.valid || !im.psync) continue;
+        for (uint32_t k = wid; k < im.nseg; k += 4) {
+            const uint32_t gw = im.seg_first + k, s0 = b.seg_start[gw], len = b.seg_end[gw] - s0;
+            const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(b.bits + im.scan_off + s0) & 3);
+            const uint32_t nch = len ? ((len + mis + 4095) >> 12) : 0u;
+            const size_t c0 = im.cs_first + ul_base(s0, k);
+            uint32_t run = 0;
+            for (uint32_t c = 0; c < nch; c += 32) {
+                const uint32_t v = (c + lane < nch) ? b.cs_cnt[c0 + c + lane] : 0u;
+                uint32_t inc = v;
+                #pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(FULL, inc, d); if (lane >= (uint32_t)d) inc += y; }
+                if (c + lane < nch) b.cs_off[c0 + c + lane] = run + inc - v;
+                run += __shfl_sync(FULL, inc, 31);
+            }
+            if (lane == 0) {
+                b.seg_ulen[gw] = run; b.seg_nstuff[gw] = len - run;
+                b.seg_uoff[gw] = im.ubits_off + (uint64_t)(s0 & ~15u) + (unsigned long long)JS_USLACK * k;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(UL_WARPS * 32) k_unstuff_long(DevBatch b)
+{
+    __shared__ __align__(16) uint32_t s_ring[UL_WARPS][US_RING / 4];
+    __shared__ uint32_t s_sel[16];
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t* const ring = s_ring[wid];
+    if (threadIdx.x < 16) {
+        uint32_t sel = 0, n = 0;
+        for (uint32_t j = 0; j < 4; j++) if (!(threadIdx.x >> j & 1)) sel |= j << (4 * n++);
+        for (; n < 4; n++) sel |= 4u << (4 * n);
+        s_sel[threadIdx.x] = sel;
+    }
+    for (uint32_t i = lane; i < US_RING / 4; i += 32) ring[i] = 0;
+    __syncthreads();
+    auto place = [&](uint32_t kk, uint32_t o) {
+        const uint32_t sh = (o & 3) * 8, A = (o >> 2) & (US_RING / 4 - 1);
+        atomicOr(&ring[A], kk << sh);
+        atomicOr(&ring[(A + 1) & (US_RING / 4 - 1)], __funnelshift_l(kk, 0, sh));
+    };
+    // one 16-byte group of the ring -> big-endian words at dst; shared = other chunks own part of the group: OR it in
+    auto flush_group = [&](uint8_t* dst, uint32_t ring_off, bool shared) {
+        uint4* rp = reinterpret_cast<uint4*>(ring + ((ring_off & (US_RING - 1)) >> 2));
+        const uint4 v = *rp;
+        *rp = make_uint4(0, 0, 0, 0);
+        const uint4 o = make_uint4(__byte_perm(v.x, 0, 0x0123), __byte_perm(v.y, 0, 0x0123), __byte_perm(v.z, 0, 0x0123), __byte_perm(v.w, 0, 0x0123));
+        if (!shared) *reinterpret_cast<uint4*>(dst) = o;
+        else {
+            uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+            if (o.x) atomicOr(d, o.x); if (o.y) atomicOr(d + 1, o.y); if (o.z) atomicOr(d + 2, o.z); if (o.w) atomicOr(d + 3, o.w);
+        }
+    };
+    const uint32_t lt = (1u << lane) - 1;
+    for (uint32_t ii = blockIdx.y; ii < b.nimg; ii += gridDim.y) {
+        const DevImage& im = b.img[ii];
+        if (!im.valid || !im.psync) continue;
+        for (uint32_t cs = blockIdx.x * UL_WARPS + wid; cs < im.cs_nslots; cs += gridDim.x * UL_WARPS) {
+            const uint32_t k = b.cs_seg[im.cs_first + cs];
+            if (k == 0xffffffffu) continue;
+            const uint32_t gw = im.seg_first + k, s0 = b.seg_start[gw], len = b.seg_end[gw] - s0;
+            const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(b.bits + im.scan_off + s0) & 3);
+            const uint32_t j = cs - ul_base(s0, k), nch = (len + mis + 4095) >> 12;
+            const uint32_t O = b.cs_off[im.cs_first + cs];                      // unstuffed bytes of the interval before this chunk
+            uint8_t* const dst = b.ubits + b.seg_uoff[gw] + (O & ~15u);          // 16-byte group holding the chunk's first output byte
+            const uint32_t* abase = reinterpret_cast<const uint32_t*>(b.bits + im.scan_off + s0 - mis);
+            const size_t rt0 = (size_t)(im.rt_off + (s0 >> 7) + 2u * k);
+            uint32_t carry = j ? __ldg(abase + (j << 10) - 1) : 0u;
+            uint32_t wr = O & 15u, fl = 0;
+            const uint32_t wr0 = wr, rp0 = j << 12;
+            for (uint32_t r = 0; r < 32 && rp0 + 128 * r < len + mis; r++) {
+                const uint32_t rpos = rp0 + 128 * r;
+                uint32_t word, rm;
+                ul_row(abase, rpos, lane, mis, len, carry, word, rm);
+                const uint32_t kk = __byte_perm(word, 0, s_sel[rm]);
+                const uint32_t cnt = 4 - __popc(rm);
+                {
+                    uint32_t mw = rm << ((lane & 7) * 4);
+                    mw |= __shfl_xor_sync(FULL, mw, 1); mw |= __shfl_xor_sync(FULL, mw, 2); mw |= __shfl_xor_sync(FULL, mw, 4);
+                    if ((lane & 7) == 0) reinterpret_cast<uint32_t*>(b.rowmask + rt0 + (rpos >> 7))[lane >> 3] = mw;
+                    if (lane == 0) b.rowtab[rt0 + (rpos >> 7)] = O + (wr - wr0);
+                }
+                const uint32_t b0 = __ballot_sync(FULL, cnt & 1), b1 = __ballot_sync(FULL, cnt & 2), b2 = __ballot_sync(FULL, cnt & 4);
+                place(kk, wr + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt));
+                wr += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+                __syncwarp();
+                if (wr - fl >= 512) {
+                    flush_group(dst + fl + 16 * lane, fl + 16 * lane, fl == 0 && lane == 0);
+                    fl += 512;
+                    __syncwarp();
+                }
+            }
+            uint32_t end = wr;
+            if (j + 1 == nch) {            // last chunk of the interval: 16 bytes of 1-bits behind the data (readers over-fetch)
+                if (lane < 4) place(0xFFFFFFFFu, wr + 4 * lane);
+                end = wr + 16;
+                __syncwarp();
+            }
+            #pragma unroll 1
+            for (uint32_t off = 16 * lane; fl + off < end; off += 512) flush_group(dst + fl + off, fl + off, true);
+            __syncwarp();
+        }
+    }
+}
+
+int js_launch_unstuff_long(const DevBatch& b, uint32_t max_cs, cudaStream_t s)
+{
+    if (max_cs == 0) return 0;
+    dim3 grid((max_cs + UL_WARPS - 1) / UL_WARPS, b.nimg < 65535u ? b.nimg : 65535u);
+    const uint32_t want = (148u * 8u * 4u + grid.y - 1) / grid.y;
+    if (grid.x > want) grid.x = want < 1 ? 1 : want;
+    k_unstuff_count<<<grid, UL_WARPS * 32, 0, s>>>(b);
+    k_unstuff_scan<<<b.nimg < 65535u ? b.nimg : 65535u, 128, 0, s>>>(b);
+    k_unstuff_long<<<grid, UL_WARPS * 32, 0, s>>>(b);
+    return 3;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -61,6 +61,8 @@ struct DevImage {
     uint32_t psync;                 // 1 = long restart intervals: decoded through the self-synchronising passes (jsgpu_phuff_core.cuh)
     uint32_t ph_nslots;             // ... number of 4096-bit slots reserved for this image (its slot arrays hold ph_nslots + 1 entries)
     uint64_t ph_first;              // ... first entry of this image in the slot arrays
+    uint32_t cs_nslots;             // ... 4096-byte chunk slots of k_unstuff_long reserved for this image
+    uint64_t cs_first;              // ... first entry of this image in the chunk arrays
     uint64_t rt_off;                // first entry of this image in the row table (k_unstuff: unstuffed bytes before every 128-byte raw row of a long interval)
 };
 
@@ -98,6 +100,7 @@ struct DevBatch {
     // slot arrays of the self-synchronising passes (all images back to back, see PhSlots)
     unsigned long long* ph_x; uint32_t* ph_ver; uint32_t* ph_k; uint4* ph_cnt; uint4* ph_aux; uint4* ph_pre;
     uint32_t*          ph_nchg;     // [PH_MAX_ROUNDS + 2] slots whose exit state changed in fix round r
+    uint32_t*          cs_cnt; uint32_t* cs_off; uint32_t* cs_seg;    // k_unstuff_long: bytes kept per chunk, their exclusive prefix, owning interval
     uint32_t*          rowtab;      // self-synchronised images: unstuffed bytes before every 128-byte raw row of an interval ...
     uint4*             rowmask;     // ... and which of the row's 128 raw bytes do not reach the unstuffed copy (MCU file map without a re-walk)
     const uint4*       tiles;       // IDCT: (image, mcu_row, mcu_col0, nmcu) [ntiles], grouped by chroma replication class
@@ -137,6 +140,7 @@ struct DevBatch {
 // launchers (jsgpu_kernels.cu) — each returns the number of kernels it enqueued
 int js_launch_marker_scan(const DevBatch& b, uint64_t max_scan_len, cudaStream_t s);
 int js_launch_unstuff(const DevBatch& b, cudaStream_t s);
+int js_launch_unstuff_long(const DevBatch& b, uint32_t max_cs, cudaStream_t s);      // images with long intervals (DevImage::psync)
 int js_launch_huffman_warp(const DevBatch& b, int sm_count, cudaStream_t s);
 int js_launch_huffman_lane(const DevBatch& b, int sm_count, cudaStream_t s);
 int js_launch_huffman_lane_vseg(const DevBatch& b, int sm_count, cudaStream_t s);   // over the virtual intervals the self-synchronising passes found

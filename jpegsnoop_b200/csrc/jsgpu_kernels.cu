@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(256) k_finalize_mcumap_fast(DevBatch b)
         else { k -= 1; bit = b.seg_endbits[im.seg_first + k]; }       // lazy restart: end state of the previous interval
         const uint32_t sidx = im.seg_first + k;
         const uint32_t ns = b.seg_nstuff[sidx];
-        if (ns > JS_STUFF_LIST && !im.psync) continue;                  // handled by the raw re-walk kernel
+        if (ns > JS_STUFF_LIST && !im.psync) continue;                  // handled by the raw re-walk kernel (long intervals: row table below)
         const uint32_t D = b.seg_ulen[sidx];
         uint32_t u = bit >> 3, al = bit & 7;
         uint32_t val;
@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(256) k_finalize_mcumap_fast(DevBatch b)
             u = D - 1; al = 0;
         }
         uint32_t raw = u;
-        if (ns > JS_STUFF_LIST) {                                       // self-synchronised image: row table of k_unstuff
+        if (im.psync) {                                                 // long intervals: row table of k_unstuff_long
             const uint32_t s0 = b.seg_start[sidx], len = b.seg_end[sidx] - s0;
             const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(b.bits + im.scan_off + s0) & 3);
             const size_t rt0 = (size_t)(im.rt_off + (s0 >> 7) + 2u * k);
