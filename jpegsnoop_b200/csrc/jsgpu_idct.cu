@@ -22,9 +22,17 @@
 #include "build/idct_baked.h"
 #include <cstring>
 
+#ifndef IDCT_THREADS
 #define IDCT_THREADS 96        // 3 warps: one 32-block group each per pass over a tile
+#endif
 #ifndef IDCT_MIN_CTAS
 #define IDCT_MIN_CTAS 5
+#endif
+#ifndef IDCT_PREFETCH
+#define IDCT_PREFETCH 1        // 1: the next tile's coefficient rows are requested into registers before phase 2 (32 registers)
+#endif
+#ifndef IDCT_FIN_PACKED
+#define IDCT_FIN_PACKED 1      // 1: samples are finalised two at a time (packed s16x2 mask + add), see fin2_pair
 #endif
 
 // The quadrant table as kernel constants: every lane multiplies by the SAME entry, so it can be a
@@ -108,6 +116,7 @@ __global__ void __launch_bounds__(IDCT_THREADS, IDCT_MIN_CTAS) k_idct_tile(DevBa
     // coefficient rows and output rows advance sequentially).
     const uint32_t t_begin = (uint32_t)(((unsigned long long)tile_count * blockIdx.x) / gridDim.x);
     const uint32_t t_end = (uint32_t)(((unsigned long long)tile_count * (blockIdx.x + 1)) / gridDim.x);
+#if IDCT_PREFETCH
     uint4 nx4[8];
     #pragma unroll
     for (int k = 0; k < 8; k++) nx4[k] = make_uint4(0, 0, 0, 0);
@@ -120,6 +129,7 @@ __global__ void __launch_bounds__(IDCT_THREADS, IDCT_MIN_CTAS) k_idct_tile(DevBa
             for (int k = 0; k < 8; k++) nx4[k] = __ldg(rp + k);
         }
     }
+#endif
 
     for (uint32_t ti = t_begin; ti < t_end; ti++) {
         const uint4 tile = b.tiles[tile_first + ti];       // (image, mcu row, first mcu col, mcus in tile)
@@ -163,10 +173,13 @@ __global__ void __launch_bounds__(IDCT_THREADS, IDCT_MIN_CTAS) k_idct_tile(DevBa
             const bool valid = (g * 32 + lane < nblk) && (col < nmt * Hc);
             const size_t row = im.coef_row[c] + (size_t)(trow * im.V[c] + v) * im.cw[c] + (mcol0 * Hc + col);
             uint4 cw4[8];
+#if IDCT_PREFETCH
             if (g == wid) {                                        // prefetched while the previous tile was in phase 2
                 #pragma unroll
                 for (int k = 0; k < 8; k++) cw4[k] = nx4[k];
-            } else if (valid) {
+            } else
+#endif
+            if (valid) {
                 const uint4* rp = reinterpret_cast<const uint4*>(b.coef + row * 64);
                 #pragma unroll
                 for (int k = 0; k < 8; k++) cw4[k] = __ldg(rp + k);
@@ -176,6 +189,8 @@ __global__ void __launch_bounds__(IDCT_THREADS, IDCT_MIN_CTAS) k_idct_tile(DevBa
             }
             const uint32_t* cw = reinterpret_cast<const uint32_t*>(cw4);
             const int dc = (int)(short)(cw[0] & 0xFFFF);
+            const uint32_t dc2 = __byte_perm(cw[0], 0, 0x1010);    // the DC predictor sum in both halves
+            (void)dc2;
             int acc[4][16];
             #pragma unroll
             for (int p = 0; p < 4; p++)
@@ -227,16 +242,26 @@ __global__ void __launch_bounds__(IDCT_THREADS, IDCT_MIN_CTAS) k_idct_tile(DevBa
                         s2 += d2.x * cj[0] + d2.y * cj[1] + d2.z * cj[2] + d2.w * cj[3];
                         s3 += d3.x * cj[0] + d3.y * cj[1] + d3.z * cj[2] + d3.w * cj[3];
                     }
+#if IDCT_FIN_PACKED
+                    top[x] = fin_pre(s0); top[7 - x] = fin_pre(s1); bot[x] = fin_pre(s2); bot[7 - x] = fin_pre(s3);
+#else
                     top[x] = fin2(s0, dc); top[7 - x] = fin2(s1, dc); bot[x] = fin2(s2, dc); bot[7 - x] = fin2(s3, dc);
+#endif
                 }
                 if (valid) {
+#if IDCT_FIN_PACKED
+                    *reinterpret_cast<uint4*>(pl + y * ppc) = make_uint4(fin_pair(top[0], top[1], dc2), fin_pair(top[2], top[3], dc2), fin_pair(top[4], top[5], dc2), fin_pair(top[6], top[7], dc2));
+                    *reinterpret_cast<uint4*>(pl + (7 - y) * ppc) = make_uint4(fin_pair(bot[0], bot[1], dc2), fin_pair(bot[2], bot[3], dc2), fin_pair(bot[4], bot[5], dc2), fin_pair(bot[6], bot[7], dc2));
+#else
                     *reinterpret_cast<uint4*>(pl + y * ppc) = make_uint4(top[0] | (top[1] << 16), top[2] | (top[3] << 16), top[4] | (top[5] << 16), top[6] | (top[7] << 16));
                     *reinterpret_cast<uint4*>(pl + (7 - y) * ppc) = make_uint4(bot[0] | (bot[1] << 16), bot[2] | (bot[3] << 16), bot[4] | (bot[5] << 16), bot[6] | (bot[7] << 16));
+#endif
                 }
             }
         }
 #undef JS_COEF
         __syncthreads();
+#if IDCT_PREFETCH
         #pragma unroll
         for (int k = 0; k < 8; k++) nx4[k] = make_uint4(0, 0, 0, 0);
         if (ti + 1 < t_end) {                                      // request the next tile's rows; they land during phase 2
@@ -248,6 +273,7 @@ __global__ void __launch_bounds__(IDCT_THREADS, IDCT_MIN_CTAS) k_idct_tile(DevBa
                 for (int k = 0; k < 8; k++) nx4[k] = __ldg(rp + k);
             }
         }
+#endif
         // ---------------- phase 2: 8 pixels x (chroma row group) per thread, vector stores ----------------
         {
             P2x a;
@@ -329,6 +355,9 @@ static int launch_tab(const DevBatch& b, const IdctSym* sym, const ColorTabs* ct
     // one warp per 32-block group of a tile, at most 4 warps (larger tiles loop)
     uint32_t groups = (b.tile_plane_bytes / 128 + 31) / 32;
     uint32_t threads = 32 * (groups < 1 ? 1 : groups > IDCT_THREADS / 32 ? IDCT_THREADS / 32 : groups);
+#ifdef IDCT_FORCE_WARPS
+    threads = 32 * IDCT_FORCE_WARPS;          // extra warps only take part in phase 2 (its row groups split evenly over 4 warps at 4:2:0)
+#endif
     const size_t smem = sizeof(Idct2Tables) + sizeof(TileGeo) + 2 * (size_t)b.tile_plane_bytes;
     int n = 0;
     for (int cls = 0; cls < 3; cls++) {

@@ -37,6 +37,23 @@ __device__ __forceinline__ uint32_t fin2(int s, int dc)
     return (uint32_t)(r * 8 + dc) & 0xFFFFu;      // low 16 bits of (short)r*8 + dc
 }
 
+// The same finalisation two samples at a time: ((s + bias) >> 12) * 8 == ((s + bias) >> 9) & ~7, so after the 32-bit
+// bias-and-shift the two results are packed, masked and level-shifted by the DC sum with packed 16-bit operations;
+// __viaddmin_s16x2(a, b, 0x7FFF7FFF) is a per-half wrapping add (min with the largest short never clamps), i.e. exactly
+// the reference's `short n = n*8 + dc` truncation (ImgDecode.cpp:2513-2515).
+__device__ __forceinline__ uint32_t fin_pre(int s) { return (uint32_t)((s - 3 * (s >> 31)) >> 9); }
+__device__ __forceinline__ uint32_t fin_pair(uint32_t a, uint32_t b, uint32_t dc2)
+{
+#if !defined(IDCT_FIN_PACKED) || IDCT_FIN_PACKED == 1
+    return __viaddmin_s16x2(__byte_perm(a, b, 0x5410) & 0xFFF8FFF8u, dc2, 0x7FFF7FFFu);
+#else
+    // carry-free per-half add: low 15 bits added, the top bits of each half by exclusive or
+    const uint32_t p = __byte_perm(a, b, 0x5410);
+    const uint32_t lo = (p & 0x7FF87FF8u) + (dc2 & 0x7FFF7FFFu);
+    return lo ^ ((p ^ dc2) & 0x80008000u);
+#endif
+}
+
 struct P2x {
     const uint8_t* planes; uint32_t pbase1, pbase2, ppitch0, ppitch1, ppitch2;
     uint32_t opr, px0, py0, wp, hp, mcu_h, ns, evc;
