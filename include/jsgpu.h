@@ -87,6 +87,9 @@ typedef struct {
 #define JSGPU_ST_COEFOVF   4u   /* nNumCoeffs > 64 (:1776-1797)                             */
 #define JSGPU_ST_MISSING   8u   /* fewer RSTn markers than the DRI interval implies (:3180) */
 #define JSGPU_ST_LEFTOVER 16u   /* data left in an interval after its last MCU              */
+#define JSGPU_ST_RSTSEQ   32u   /* an RSTn marker out of sequence (ImgDecode.cpp:1414-1424)   */
+#define JSGPU_ST_EXACT 0x40000000u  /* the image was decoded again by the serial reference-semantics path
+                                       (jsgpu_batch_errors has its error events; outputs are the reference's) */
 
 typedef struct {
     int32_t idct_mode;      /* 0 = integer IDCT (the -DIDCT_FIXEDPT build, ImgDecode.cpp:2402-2423,
@@ -100,7 +103,8 @@ typedef struct {
     int32_t want_histo;     /* accumulate m_anDhtHisto (ImgDecode.cpp:1190-1191); default 1      */
     int32_t want_mcu_map;   /* build m_pMcuFileMap (ImgDecode.cpp:3229); default 1               */
     int32_t device_markers; /* 1 = find RSTn/end-of-scan on the GPU (default), 0 = host walk      */
-    int32_t reserved;
+    int32_t scan_err_max;   /* CSnoopConfig::nErrMaxDecodeScan (SnoopConfig.cpp:89): capped error lines
+                               per scan; 0 = the reference's default, 20                          */
 } jsgpu_options;
 
 /* Device pointers of the output pools of the current batch (owned by the context). */
@@ -199,6 +203,39 @@ int jsgpu_batch_launches(jsgpu_ctx* ctx);
  * info[3..3+R] = slots whose state changed in fix round 1..R+... (0 from the round in which everything had settled).
  * n = capacity of info in words (16 is enough).  Forces a sync. */
 int jsgpu_batch_selfsync_info(jsgpu_ctx* ctx, uint32_t* info, uint32_t n);
+
+/* What the reference logs for a damaged scan.  An image whose status word came out non-zero is decoded a second time by a
+ * serial path that follows ReadScanVal / BuffAddByte / DecodeScanComp / DecodeScanImg literally (one-bit resynchronisation
+ * ImgDecode.cpp:1166-1187, stray markers :1486-1561 and :1683-1706, lazy restarts :1644-1680, error cap :1100-1110); its
+ * outputs replace the fast path's and its log events are kept for the caller.  code: see JSGPU_EV_*; a..e: the numbers the
+ * reference prints in that line (file position, bit alignment, table, accumulator ...). */
+#define JSGPU_EV_OVERREAD_BEFORE     1  /* "*** ERROR: Overread scan segment (before nCode)! @ Offset: %s"   a=pos b=align        */
+#define JSGPU_EV_OVERREAD_AFTER_CODE 2  /* "*** ERROR: Overread scan segment (after nCode)! @ Offset: %s"                         */
+#define JSGPU_EV_OVERREAD_AFTER_BITS 3  /* "*** ERROR: Overread scan segment (after bitstring)! @ Offset: %s"                     */
+#define JSGPU_EV_NOCODE              4  /* "*** ERROR: Can't find huffman bitstring @ %s, table %u, value [0x%08x]" c=tbl d=buff  */
+#define JSGPU_EV_CAP                 5  /* "    Only reported first %u instances of this message..."          a=cap               */
+#define JSGPU_EV_RST_MISMATCH        6  /* "  ERROR: Expected RST marker index RST%u got RST%u @ 0x%08X.0"    a,b,c               */
+#define JSGPU_EV_MARKER_NOTE         7  /* "  Scan Data encountered marker   0xFF%02X @ 0x%08X.0" (plain line) a=marker b=pos;
+                                           followed by "  NOTE: Marker wasn't EOI (0xFFD9)" (error line) unless a == 0xD9       */
+#define JSGPU_EV_BADMARK             8  /* "*** ERROR: Bad marker @ %s"                                                           */
+#define JSGPU_EV_BADCODE             9  /* "*** ERROR: Bad huffman code @ %s"                                                     */
+#define JSGPU_EV_NCOEF              10  /* "*** ERROR: @ %s, nNumCoeffs>64 [%u]"                             c=n                  */
+#define JSGPU_EV_MCU                11  /* "*** ERROR: Bad scan data in MCU(%u,%u): %s @ Offset %s" + "           MCU located at
+                                           pixel=(%u,%u)"  a=mcu x b=mcu y c=comp|h<<8|v<<16 d=pos e=align                        */
+#define JSGPU_EV_RST_MISSING        12  /* "  Expect Restart interval elapsed @ %s" (plain) + "    ERROR: Restart marker not detected" */
+#define JSGPU_MAX_EVENTS 256
+typedef struct { uint32_t code, a, b, c, d, e, pad0, pad1; } jsgpu_scan_event;
+typedef struct {
+    uint32_t nerr_lines;      /* error lines (AddLineErr) the reference writes for this scan                               */
+    uint32_t nevents;         /* events seen; the first JSGPU_MAX_EVENTS are in ev[]                                       */
+    uint32_t scan_bad;        /* m_bScanBad at the end of the scan                                                        */
+    uint32_t restart_read;    /* m_nRestartRead                                                                           */
+    uint32_t done, pad[3];
+    jsgpu_scan_event ev[JSGPU_MAX_EVENTS];
+} jsgpu_scan_errors;
+/* Error events of image `image` of the last decode (JSGPU_ESTATE when it did not take the serial path: status without
+ * JSGPU_ST_EXACT).  Forces a sync. */
+int jsgpu_batch_errors(jsgpu_ctx* ctx, uint32_t image, jsgpu_scan_errors* out);
 
 /* Checksums of the outputs of every image of the last jsgpu_batch_decode, computed on the device (forces a sync):
  * ck[i][0..2] m_pPixValY/Cb/Cr, [3] the DIB, [4..6] m_pBlkDcValY/Cb/Cr, [7] m_pMcuFileMap, [8] m_anDhtHisto, [9] the nine

@@ -22,6 +22,7 @@ void   jsimg_config(jsimg*, int decode_ac, int idct_fixedpt, int cuda_device, in
 /* byte source: CwindowBuf::BufFileSet equivalent on a memory buffer (caller keeps it alive) */
 void   jsimg_set_file(jsimg*, const uint8_t* data, uint64_t n);
 int    jsimg_overlay_install(jsimg*, uint32_t start, const uint8_t* data, uint32_t n);
+void   jsimg_overlay_remove_all(jsimg*);                       /* CwindowBuf::OverlayRemoveAll, WindowBuf.cpp:571 */
 
 void   jsimg_Reset(jsimg*);
 void   jsimg_ResetState(jsimg*);

@@ -43,7 +43,16 @@ class jsgpu_image_layout(C.Structure):
 class jsgpu_options(C.Structure):
     _fields_ = [("idct_mode", C.c_int32), ("decode_ac", C.c_int32), ("huff_kernel", C.c_int32),
                 ("idct_kernel", C.c_int32), ("want_histo", C.c_int32), ("want_mcu_map", C.c_int32),
-                ("device_markers", C.c_int32), ("reserved", C.c_int32)]
+                ("device_markers", C.c_int32), ("scan_err_max", C.c_int32)]
+
+
+class jsgpu_scan_event(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("code", "a", "b", "c", "d", "e", "pad0", "pad1")]
+
+
+class jsgpu_scan_errors(C.Structure):
+    _fields_ = [("nerr_lines", C.c_uint32), ("nevents", C.c_uint32), ("scan_bad", C.c_uint32), ("restart_read", C.c_uint32),
+                ("done", C.c_uint32), ("pad", C.c_uint32 * 3), ("ev", jsgpu_scan_event * 256)]
 
 
 class jsgpu_pools(C.Structure):
@@ -63,10 +72,10 @@ JSGPU_SYMBOLS = [
     "jsgpu_init", "jsgpu_free", "jsgpu_last_error", "jsgpu_strerror", "jsgpu_version", "jsgpu_stream", "jsgpu_sync",
     "jsgpu_set_idct_tables", "jsgpu_set_options", "jsgpu_get_options", "jsgpu_upload_tables",
     "jsgpu_batch_begin", "jsgpu_batch_layout", "jsgpu_batch_pools", "jsgpu_batch_upload", "jsgpu_batch_decode",
-    "jsgpu_batch_download", "jsgpu_batch_stage_ms", "jsgpu_timer_start", "jsgpu_timer_stop", "jsgpu_batch_launches", "jsgpu_batch_selfsync_info", "jsgpu_batch_checksums", "jsgpu_decode_batch_host",
+    "jsgpu_batch_download", "jsgpu_batch_stage_ms", "jsgpu_timer_start", "jsgpu_timer_stop", "jsgpu_batch_launches", "jsgpu_batch_selfsync_info", "jsgpu_batch_checksums", "jsgpu_batch_errors", "jsgpu_decode_batch_host",
     "jsgpu_host_alloc", "jsgpu_host_free", "jsgpu_host_copy_rate"]
 JSIMG_SYMBOLS = [
-    "jsimg_create", "jsimg_destroy", "jsimg_config", "jsimg_set_file", "jsimg_overlay_install", "jsimg_Reset", "jsimg_ResetState",
+    "jsimg_create", "jsimg_destroy", "jsimg_config", "jsimg_set_file", "jsimg_overlay_install", "jsimg_overlay_remove_all", "jsimg_Reset", "jsimg_ResetState",
     "jsimg_SetDqtEntry", "jsimg_SetDqtTables", "jsimg_GetDqtEntry", "jsimg_SetDhtTables", "jsimg_SetDhtEntry",
     "jsimg_SetDhtSize", "jsimg_SetPrecision", "jsimg_SetSofSampFactors", "jsimg_SetImageDetails",
     "jsimg_DecodeScanImg", "jsimg_IsPreviewReady", "jsimg_GetImageSize", "jsimg_GetPixMapPtrs", "jsimg_GetBitmapPtr",
@@ -107,6 +116,7 @@ def load():
     L.jsgpu_batch_launches.argtypes = [vp]
     L.jsgpu_batch_selfsync_info.argtypes = [vp, vp, u32]
     L.jsgpu_batch_checksums.argtypes = [vp, vp, u32]
+    L.jsgpu_batch_errors.argtypes = [vp, u32, C.POINTER(jsgpu_scan_errors)]
     L.jsgpu_timer_start.argtypes = [vp]
     L.jsgpu_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
     L.jsgpu_decode_batch_host.argtypes = [vp, vp, u32, vp, u64, C.POINTER(jsgpu_host_outputs)]
@@ -118,6 +128,7 @@ def load():
     L.jsimg_config.argtypes = [vp] + [i32] * 6; L.jsimg_config.restype = None
     L.jsimg_set_file.argtypes = [vp, vp, u64]; L.jsimg_set_file.restype = None
     L.jsimg_overlay_install.argtypes = [vp, u32, vp, u32]
+    L.jsimg_overlay_remove_all.argtypes = [vp]; L.jsimg_overlay_remove_all.restype = None
     for n in ("jsimg_Reset", "jsimg_ResetState", "jsimg_log_clear"):
         getattr(L, n).argtypes = [vp]; getattr(L, n).restype = None
     L.jsimg_SetDqtEntry.argtypes = [vp, u32, u32, u32, u32]

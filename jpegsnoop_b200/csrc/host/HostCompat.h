@@ -37,8 +37,9 @@ class CwindowBuf {
 public:
     void BufSet(const uint8_t* data, size_t n) { m_p = data; m_n = n; }
     uint8_t Buf(unsigned long off, bool bClean = false) const {
-        if (!bClean) for (auto& o : m_ovl) if (off >= o.start && off < o.start + o.data.size()) return o.data[off - o.start];
-        return (off < m_n) ? m_p[off] : 0;
+        uint8_t v = (off < m_n) ? m_p[off] : 0;
+        if (!bClean) for (auto& o : m_ovl) if (off >= o.start && off < o.start + o.data.size()) v = o.data[off - o.start];   // the last overlay installed wins (WindowBuf.cpp:659-670)
+        return v;
     }
     void BufLoadWindow(unsigned long) {}
     unsigned long GetPosEof() const { return (unsigned long)m_n; }

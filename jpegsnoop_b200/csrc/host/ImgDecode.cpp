@@ -297,6 +297,7 @@ void CimgDecode::DecodeScanImg(unsigned nStart, bool bDisplay, bool bQuiet)
     opt.huff_kernel = m_pAppConfig->nHuffKernel; opt.idct_kernel = m_pAppConfig->nIdctKernel;
     opt.device_markers = m_pAppConfig->bDeviceMarkers ? 1 : 0;
     opt.want_histo = 1; opt.want_mcu_map = 1;
+    opt.scan_err_max = (int32_t)m_nScanErrMax;
     jsgpu_set_options(m_pGpu, &opt);
 
     jsgpu_tables* pTables = new jsgpu_tables;
@@ -348,17 +349,54 @@ void CimgDecode::DecodeScanImg(unsigned nStart, bool bDisplay, bool bQuiet)
         m_bDibTempReady = true; m_bPreviewIsJpeg = true;                           // ref :3646-3649
     }
     m_nScanStatus = lo.status;
-    if (lo.status) {
-        // The device reports WHAT went wrong per restart interval; the reference's per-symbol
-        // resynchronisation (ref :1178-1187) is not reproduced.
-        m_bScanBad = true;
-        if (m_nWarnBadScanNum < m_nScanErrMax) {
-            m_pLog->AddLineErr(fmt("*** ERROR: Bad scan data (device status 0x%02X:%s%s%s%s%s) ***", lo.status,
-                (lo.status & JSGPU_ST_BADCODE) ? " bad-huffman-code" : "", (lo.status & JSGPU_ST_OVERRUN) ? " overread-scan-segment" : "",
-                (lo.status & JSGPU_ST_COEFOVF) ? " nNumCoeffs>64" : "", (lo.status & JSGPU_ST_MISSING) ? " restart-marker-not-detected" : "",
-                (lo.status & JSGPU_ST_LEFTOVER) ? " data-left-in-interval" : ""));
-            m_nWarnBadScanNum++;
+    if (lo.status & JSGPU_ST_EXACT) {
+        // A damaged scan: the device decoded it a second time the way ReadScanVal / BuffAddByte / DecodeScanComp do (one-bit
+        // resynchronisation, stray markers, lazy restarts, error cap: ref :1096-1115, 1166-1187, 1257-1282, 1486-1561,
+        // 1683-1706, 1737-1797, 2605-2660, 3180-3200) and kept what the reference would have logged; here it becomes text.
+        jsgpu_scan_errors* pErr = new jsgpu_scan_errors;
+        if (jsgpu_batch_errors(m_pGpu, 0, pErr) == JSGPU_OK) {
+            m_bScanBad = pErr->scan_bad != 0;
+            const unsigned nEv = pErr->nevents < JSGPU_MAX_EVENTS ? pErr->nevents : JSGPU_MAX_EVENTS;
+            for (unsigned i = 0; i < nEv; i++) {
+                const jsgpu_scan_event& e = pErr->ev[i];
+                switch (e.code) {
+                case JSGPU_EV_OVERREAD_BEFORE:     m_pLog->AddLineErr(fmt("*** ERROR: Overread scan segment (before nCode)! @ Offset: 0x%08X.%u", e.a, e.b)); break;
+                case JSGPU_EV_OVERREAD_AFTER_CODE: m_pLog->AddLineErr(fmt("*** ERROR: Overread scan segment (after nCode)! @ Offset: 0x%08X.%u", e.a, e.b)); break;
+                case JSGPU_EV_OVERREAD_AFTER_BITS: m_pLog->AddLineErr(fmt("*** ERROR: Overread scan segment (after bitstring)! @ Offset: 0x%08X.%u", e.a, e.b)); break;
+                case JSGPU_EV_NOCODE:              m_pLog->AddLineErr(fmt("*** ERROR: Can't find huffman bitstring @ 0x%08X.%u, table %u, value [0x%08x]", e.a, e.b, e.c, e.d)); break;
+                case JSGPU_EV_CAP:                 m_pLog->AddLineErr(fmt("    Only reported first %u instances of this message...", e.a)); break;
+                case JSGPU_EV_RST_MISMATCH:        m_pLog->AddLineErr(fmt("  ERROR: Expected RST marker index RST%u got RST%u @ 0x%08X.0", e.a, e.b, e.c)); break;
+                case JSGPU_EV_MARKER_NOTE:
+                    m_pLog->AddLine(fmt("  Scan Data encountered marker   0xFF%02X @ 0x%08X.0", e.a, e.b));
+                    if (e.a != 0xD9) m_pLog->AddLineErr("  NOTE: Marker wasn't EOI (0xFFD9)");
+                    break;
+                case JSGPU_EV_BADMARK:             m_pLog->AddLineErr(fmt("*** ERROR: Bad marker @ 0x%08X.%u", e.a, e.b)); break;
+                case JSGPU_EV_BADCODE:             m_pLog->AddLineErr(fmt("*** ERROR: Bad huffman code @ 0x%08X.%u", e.a, e.b)); break;
+                case JSGPU_EV_NCOEF:               m_pLog->AddLineErr(fmt("*** ERROR: @ 0x%08X.%u, nNumCoeffs>64 [%u]", e.a, e.b, e.c)); break;
+                case JSGPU_EV_MCU: {
+                    const unsigned nComp = e.c & 0xFF, nCssH = (e.c >> 8) & 0xFF, nCssV = (e.c >> 16) & 0xFF;
+                    std::string strComp = fmt(nComp == 0 ? "Lum CSS(%u,%u)" : nComp == 1 ? "Chr(Cb) CSS(%u,%u)" : "Chr(Cr) CSS(%u,%u)", nCssH, nCssV);
+                    m_pLog->AddLineErr(fmt("*** ERROR: Bad scan data in MCU(%u,%u): %s @ Offset 0x%08X.%u", e.a, e.b, strComp.c_str(), e.d, e.e));
+                    m_pLog->AddLineErr(fmt("           MCU located at pixel=(%u,%u)", m_nMcuWidth * e.a + nCssH * 8, m_nMcuHeight * e.b + nCssV * 8));
+                    break; }
+                case JSGPU_EV_RST_MISSING:
+                    m_pLog->AddLine(fmt("  Expect Restart interval elapsed @ 0x%08X.%u", e.a, e.b));
+                    m_pLog->AddLineErr("    ERROR: Restart marker not detected");
+                    break;
+                default: break;
+                }
+            }
+            if (pErr->nevents > JSGPU_MAX_EVENTS)
+                m_pLog->AddLineErr(fmt("    (%u further scan error events not itemised)", pErr->nevents - JSGPU_MAX_EVENTS));
+            m_nRestartRead = pErr->restart_read;
+        } else {
+            m_bScanBad = true;
+            m_pLog->AddLineErr(fmt("*** ERROR: Bad scan data (device status 0x%08X; error events unavailable: %s) ***", lo.status, jsgpu_last_error(m_pGpu)));
         }
+        delete pErr;
+    } else if (lo.status) {
+        m_bScanBad = true;
+        m_pLog->AddLineErr(fmt("*** ERROR: Bad scan data (device status 0x%08X) ***", lo.status));
     }
     if (!bQuiet) {
         m_pLog->AddLine("");

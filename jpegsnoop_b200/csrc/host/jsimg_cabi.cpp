@@ -17,6 +17,7 @@ void jsimg_config(jsimg* h, int ac, int fixed, int dev, int hk, int ik, int dm)
 { h->cfg.bDecodeScanImgAc = ac != 0; h->cfg.bIdctFixedPt = fixed != 0; h->cfg.nCudaDevice = dev; h->cfg.nHuffKernel = hk; h->cfg.nIdctKernel = ik; h->cfg.bDeviceMarkers = dm != 0; }
 void jsimg_set_file(jsimg* h, const uint8_t* d, uint64_t n) { h->wbuf.BufSet(d, (size_t)n); }
 int  jsimg_overlay_install(jsimg* h, uint32_t start, const uint8_t* d, uint32_t n) { return h->wbuf.OverlayInstall(start, d, n) ? 1 : 0; }
+void jsimg_overlay_remove_all(jsimg* h) { h->wbuf.OverlayRemoveAll(); }
 void jsimg_Reset(jsimg* h) { h->dec->Reset(); }
 void jsimg_ResetState(jsimg* h) { h->dec->ResetState(); }
 int  jsimg_SetDqtEntry(jsimg* h, unsigned t, unsigned i, unsigned z, unsigned v) { return h->dec->SetDqtEntry(t, i, z, (unsigned short)v); }

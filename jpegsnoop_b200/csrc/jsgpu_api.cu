@@ -41,7 +41,7 @@ struct jsgpu_ctx {
     bool have_idct = false;
     // device state
     DevBuf d_ctab; bool have_ctab = false;
-    DevBuf d_li, d_lf, d_sym, d_tables, d_img, d_items, d_litems, d_tiles, d_ubits, d_seg64, d_ph, d_rowtab;
+    DevBuf d_li, d_lf, d_sym, d_tables, d_img, d_items, d_litems, d_tiles, d_ubits, d_seg64, d_ph, d_rowtab, d_ex;
     bool sym_ok = false, baked_ok = false; int tab_mode = 0;
     DevBuf d_bits, d_seg, d_coef, d_mcubits, d_pix, d_dib, d_blk, d_mcumap, d_histo, d_stats, d_misc;
     uint32_t nsets = 0;
@@ -125,7 +125,7 @@ void jsgpu_free(jsgpu_ctx* ctx)
     ctx->kids.clear();
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = { &ctx->d_ctab, &ctx->d_li, &ctx->d_lf, &ctx->d_sym, &ctx->d_tables, &ctx->d_img, &ctx->d_items, &ctx->d_litems, &ctx->d_tiles, &ctx->d_ubits, &ctx->d_seg64, &ctx->d_ph, &ctx->d_rowtab, &ctx->d_bits, &ctx->d_seg,
+    DevBuf* bufs[] = { &ctx->d_ctab, &ctx->d_li, &ctx->d_lf, &ctx->d_sym, &ctx->d_tables, &ctx->d_img, &ctx->d_items, &ctx->d_litems, &ctx->d_tiles, &ctx->d_ubits, &ctx->d_seg64, &ctx->d_ph, &ctx->d_rowtab, &ctx->d_ex, &ctx->d_bits, &ctx->d_seg,
                        &ctx->d_coef, &ctx->d_mcubits, &ctx->d_pix, &ctx->d_dib, &ctx->d_blk, &ctx->d_mcumap, &ctx->d_histo, &ctx->d_stats, &ctx->d_misc };
     for (auto* b : bufs) b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -385,7 +385,8 @@ int jsgpu_batch_begin(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, 
     CK(ctx->d_mcumap.reserve(mcu * 4 + 16));
     CK(ctx->d_histo.reserve((size_t)n * 2 * 4 * 17 * 4));
     CK(ctx->d_stats.reserve((size_t)n * 16 * 4));
-    CK(ctx->d_misc.reserve((size_t)n * (8 + 8 + 4) + 64 + 64));
+    CK(ctx->d_misc.reserve((size_t)n * (8 + 8 + 4 + 4) + 64 + 64));
+    CK(ctx->d_ex.reserve((size_t)n * sizeof(JsExResult)));
     CK(cudaMemcpyAsync(ctx->d_img.p, ctx->himg.data(), sizeof(DevImage) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     const size_t n_it = items.size(), n_lit = litems.size();
     items.insert(items.end(), items_np.begin(), items_np.end());                   // [all | without self-synchronised images]
@@ -427,7 +428,7 @@ int jsgpu_batch_begin(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, 
     b.mcu_map = (uint32_t*)ctx->d_mcumap.p;
     b.histo = (uint32_t*)ctx->d_histo.p; b.stats = (int32_t*)ctx->d_stats.p;
     b.bright_key = (unsigned long long*)ctx->d_misc.p; b.sum_y = b.bright_key + n; b.img_status = (uint32_t*)(b.sum_y + n); b.ovf_count = b.img_status + n;
-    b.ph_nchg = b.ovf_count + 1;
+    b.ph_nchg = b.ovf_count + 1; b.ex_flag = b.ph_nchg + PH_MAX_ROUNDS + 2; b.ex_res = (JsExResult*)ctx->d_ex.p;
     ctx->planned = true;
     return JSGPU_OK;
 }
@@ -442,7 +443,10 @@ int jsgpu_batch_layout(jsgpu_ctx* ctx, jsgpu_image_layout* out, uint32_t n)
         std::vector<uint32_t> st(ctx->layout.size());
         CK(cudaMemcpyAsync(st.data(), ctx->batch.img_status, st.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
-        for (size_t i = 0; i < st.size(); i++) if (ctx->himg[i].valid) ctx->layout[i].status = st[i];
+        std::vector<uint32_t> ex(ctx->layout.size());
+        CK(cudaMemcpyAsync(ex.data(), ctx->batch.ex_flag, ex.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (size_t i = 0; i < st.size(); i++) if (ctx->himg[i].valid) ctx->layout[i].status = st[i] | (ex[i] ? JSGPU_ST_EXACT : 0u);
     }
     memcpy(out, ctx->layout.data(), sizeof(jsgpu_image_layout) * n);
     return JSGPU_OK;
@@ -479,6 +483,7 @@ static int host_marker_walk(jsgpu_ctx* ctx, const uint8_t* bits_host)
     uint32_t* s_start = seg.data(); uint32_t* s_end = s_start + b.nseg_total;
     uint32_t* scan_end = seg.data() + 5 * (size_t)b.nseg_total; uint32_t* nfound = scan_end + b.nimg;
     std::vector<int32_t> nrst(b.nimg, 0);
+    std::vector<uint32_t> rstseq(b.nimg, 0);
     for (uint32_t i = 0; i < b.nimg; i++) {
         const DevImage& im = ctx->himg[i];
         if (!im.valid) continue;
@@ -489,6 +494,7 @@ static int host_marker_walk(jsgpu_ctx* ctx, const uint8_t* bits_host)
             if (p[q] != 0xFF) continue;
             uint8_t m = p[q + 1];
             if (m >= 0xD0 && m <= 0xD7) {
+                if ((m & 7u) != (k & 7u)) rstseq[i] = 32u;
                 if (k < im.nseg) s_end[im.seg_first + k] = (uint32_t)q;
                 if (k + 1 < im.nseg) s_start[im.seg_first + k + 1] = (uint32_t)q + 2;
                 k++; q++;
@@ -498,7 +504,10 @@ static int host_marker_walk(jsgpu_ctx* ctx, const uint8_t* bits_host)
         if (nf <= im.nseg) s_end[im.seg_first + nf - 1] = endpos;
         for (uint32_t j = nf; j < im.nseg; j++) { s_start[im.seg_first + j] = endpos; s_end[im.seg_first + j] = endpos; }
         scan_end[i] = endpos; nfound[i] = nf; nrst[i] = (int32_t)k;
+        if (nf < im.nseg) rstseq[i] |= 8u;                     // JSGPU_ST_MISSING, as k_marker_scan reports it
+        if (nf > im.nseg) rstseq[i] |= 32u;
     }
+    cudaMemcpyAsync(b.img_status, rstseq.data(), (size_t)b.nimg * 4, cudaMemcpyHostToDevice, ctx->stream);
     cudaMemcpyAsync(b.seg_start, s_start, 2 * (size_t)b.nseg_total * 4, cudaMemcpyHostToDevice, ctx->stream);
     cudaMemcpyAsync(b.scan_end, scan_end, 2 * (size_t)b.nimg * 4, cudaMemcpyHostToDevice, ctx->stream);
     for (uint32_t i = 0; i < b.nimg; i++)
@@ -563,6 +572,8 @@ int jsgpu_batch_decode(jsgpu_ctx* ctx)
             launches += js_launch_selfsync(bh, ctx->sm_count, s);
             launches += js_launch_huffman_lane_vseg(bh, ctx->sm_count, s);
         }
+        // damaged images (status word != 0) are decoded again with the reference's semantics; returns at once for the others
+        launches += js_launch_exact(b, ctx->opt.scan_err_max > 0 ? ctx->opt.scan_err_max : 20, s);
     }
     CK(cudaEventRecord(ctx->ev[2], s));
     {
@@ -609,6 +620,21 @@ int jsgpu_timer_stop(jsgpu_ctx* ctx, float* ms)
 }
 
 int jsgpu_batch_launches(jsgpu_ctx* ctx) { return ctx ? ctx->launches : JSGPU_EINVAL; }
+
+int jsgpu_batch_errors(jsgpu_ctx* ctx, uint32_t image, jsgpu_scan_errors* out)
+{
+    if (!ctx || !out) return JSGPU_EINVAL;
+    if (!ctx->decoded || ctx->host_delivered) return fail(ctx, JSGPU_ESTATE, "no device-resident decode to report on");
+    if (image >= ctx->himg.size()) return fail(ctx, JSGPU_EINVAL, "image index out of range");
+    cudaSetDevice(ctx->device);
+    uint32_t flag = 0;
+    CK(cudaMemcpyAsync(&flag, ctx->batch.ex_flag + image, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (!flag) return fail(ctx, JSGPU_ESTATE, "image %u did not take the serial error path", image);
+    CK(cudaMemcpyAsync(out, ctx->batch.ex_res + image, sizeof *out, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return JSGPU_OK;
+}
 
 int jsgpu_batch_checksums(jsgpu_ctx* ctx, uint64_t* ck, uint32_t n)
 {

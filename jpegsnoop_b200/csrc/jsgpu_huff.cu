@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(128) k_finalize_mcumap_emptied(DevBatch b)
     __shared__ __align__(16) uint16_t s_lut[6][JS_LUT_SIZE];      // first-level tables of the current image, [comp*2 + class]
     for (uint32_t ii = blockIdx.y; ii < b.nimg; ii += gridDim.y) {            // grid.y = image (strided beyond 65535 images)
     const DevImage& im = b.img[ii];
-    if (!im.valid || !im.restart_en || im.nseg < 2) continue;
+    if (!im.valid || !im.restart_en || im.nseg < 2 || b.ex_flag[ii]) continue;
     if (blockIdx.x * EM_SPAN + 1 >= im.nseg) continue;
     const DevTableSet* ts = b.tables + im.table_set;
     const uint32_t ns = im.ns, ri = im.ri, nmcu = im.nmcu;

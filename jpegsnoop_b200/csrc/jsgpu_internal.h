@@ -3,6 +3,7 @@
 #pragma once
 #include <stdint.h>
 #include <cuda_runtime.h>
+#include "../../include/jsgpu.h"
 
 #define JS_LUT_BITS   10                 // direct Huffman look-up width (reference uses 9: ImgDecode.h:96)
 #define JS_LUT_SIZE   (1 << JS_LUT_BITS)
@@ -13,6 +14,22 @@
 #define JS_STUFF_LIST 6                  // stuffed-byte positions recorded per restart interval
 #define JS_MAX_DEVICES 64                // per-device "function attribute set" flags of the launchers
 #define JS_NSLOT      8                  // (class,Th) pairs: slot = class*4 + Th
+
+// serial reference-semantics path (jsgpu_exact.cu): per-image result = the public jsgpu_scan_errors
+typedef jsgpu_scan_errors JsExResult; typedef jsgpu_scan_event JsExEvent;
+#define JS_EX_MAX_EVENTS JSGPU_MAX_EVENTS
+#define JS_EX_OVERREAD_BEFORE JSGPU_EV_OVERREAD_BEFORE
+#define JS_EX_OVERREAD_AFTER_CODE JSGPU_EV_OVERREAD_AFTER_CODE
+#define JS_EX_OVERREAD_AFTER_BITS JSGPU_EV_OVERREAD_AFTER_BITS
+#define JS_EX_NOCODE JSGPU_EV_NOCODE
+#define JS_EX_CAP JSGPU_EV_CAP
+#define JS_EX_RST_MISMATCH JSGPU_EV_RST_MISMATCH
+#define JS_EX_MARKER_NOTE JSGPU_EV_MARKER_NOTE
+#define JS_EX_BADMARK JSGPU_EV_BADMARK
+#define JS_EX_BADCODE JSGPU_EV_BADCODE
+#define JS_EX_NCOEF JSGPU_EV_NCOEF
+#define JS_EX_MCU JSGPU_EV_MCU
+#define JS_EX_RST_MISSING JSGPU_EV_RST_MISSING
 
 // Device form of one jsgpu_tables set.
 struct DevTableSet {
@@ -118,6 +135,8 @@ struct DevBatch {
     unsigned long long* bright_key; // [nimg] packed (Y+32768)<<32 | ~pixel_index
     unsigned long long* sum_y;      // [nimg]
     uint32_t*          img_status;  // [nimg]
+    uint32_t*          ex_flag;     // [nimg] 1 = re-decoded by the serial reference-semantics path (k_huff_exact): the finalize kernels leave its MCU map alone
+    JsExResult*        ex_res;      // [nimg] its error events
     // options
     int                decode_ac, want_histo, idct_mode;
     uint32_t           max_nseg;             // most restart intervals in one image of the batch
@@ -154,6 +173,7 @@ int js_launch_build_color_tables(ColorTabs* t, cudaStream_t s);
 int js_upload_idct_constants(const IdctSym* host_sym, cudaStream_t s);
 int js_make_coef_tensor_map(void* out_tmap, void* coef, uint64_t rows);
 int js_launch_idct_tma(const DevBatch& b, const IdctSym* sym, const ColorTabs* ctab, const void* tmap_host, int sm_count, cudaStream_t s);
+int js_launch_exact(const DevBatch& b, int err_max, cudaStream_t s);       // damaged images, again, with the reference's semantics (jsgpu_exact.cu)
 int js_launch_finalize(const DevBatch& b, cudaStream_t s);
 #define JSGPU_CK_WORDS_INTERNAL 12   // == JSGPU_CK_WORDS (include/jsgpu.h)
 int js_launch_checksums(const DevBatch& b, unsigned long long* ck, cudaStream_t s);

@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(MS_THREADS) k_marker_scan(DevBatch b)
             uint32_t pos = (uint32_t)(off0 + i);
             if (rank < im.nseg) seg_end[rank] = pos;
             if (rank + 1 < im.nseg) seg_start[rank + 1] = pos + 2;
+            if (((uint32_t)p[pos + 1] & 7u) != (rank & 7u)) atomicOr(&b.img_status[blockIdx.x], 32u);    // out of sequence: the reference logs it (ImgDecode.cpp:1414-1424)
             rank++;
         }
         found += total;
@@ -112,6 +113,7 @@ __global__ void __launch_bounds__(MS_THREADS) k_marker_scan(DevBatch b)
         b.nseg_found[blockIdx.x] = nf;
         b.stats[(size_t)blockIdx.x * 16 + 11] = (int32_t)found;    // m_nRestartRead (ImgDecode.cpp:1414)
         if (nf < im.nseg) atomicOr(&b.img_status[blockIdx.x], 8u);
+        if (nf > im.nseg) atomicOr(&b.img_status[blockIdx.x], 32u);        // more restart markers than intervals: the reference restarts at each one it meets
     }
 }
 
@@ -259,7 +261,7 @@ __global__ void __launch_bounds__(128) k_finalize_mcumap(DevBatch b)
     uint32_t lo = 0, hi = b.nimg - 1;                       // image owning segment gw
     while (lo < hi) { uint32_t mid = (lo + hi + 1) >> 1; if (b.img[mid].seg_first <= gw) lo = mid; else hi = mid - 1; }
     const DevImage& im = b.img[lo];
-    if (!im.valid) continue;
+    if (!im.valid || b.ex_flag[lo]) continue;
     const uint32_t k = gw - im.seg_first;
     if (k >= im.nseg) continue;
     const uint32_t s0 = b.seg_start[gw], len = b.seg_end[gw] - s0;
@@ -308,7 +310,7 @@ __global__ void __launch_bounds__(128) k_finalize_mcumap(DevBatch b)
 __global__ void __launch_bounds__(256) k_finalize_mcumap_fast(DevBatch b)
 {
     const DevImage& im = b.img[blockIdx.y];
-    if (!im.valid) return;
+    if (!im.valid || b.ex_flag[blockIdx.y]) return;           // damaged image: k_huff_exact wrote its map
     for (uint32_t m = blockIdx.x * blockDim.x + threadIdx.x; m < im.nmcu; m += gridDim.x * blockDim.x) {
         uint32_t k = m / im.ri, t = m - k * im.ri, bit;
         if (t > 0) bit = b.mcu_bitpos[im.mcu_off + m];

@@ -165,7 +165,7 @@ class BatchDecoder:
         self._ck(self.L.jsgpu_set_idct_tables(self.ctx, li.ctypes.data, lf.ctypes.data))
         self.opt = B.jsgpu_options(idct_mode=0 if idct_fixedpt else 1, decode_ac=int(decode_ac), huff_kernel=huff_kernel,
                                    idct_kernel=idct_kernel, want_histo=int(want_histo), want_mcu_map=int(want_mcu_map),
-                                   device_markers=int(device_markers), reserved=0)
+                                   device_markers=int(device_markers), scan_err_max=0)
         self._ck(self.L.jsgpu_set_options(self.ctx, C.byref(self.opt)))
         self.n = 0; self.layout = None; self.descs = None; self.bitstream = None; self.nsof_pixels = 0
 
@@ -238,6 +238,10 @@ class BatchDecoder:
     def host_copy_rate(self, direction=1, nbytes=1 << 30, reps=3):
         """GB/s of a plain cudaMemcpyAsync between pinned host memory and this GPU (1 = device->host)."""
         g = C.c_float(0); self._ck(self.L.jsgpu_host_copy_rate(self.ctx, direction, nbytes, reps, C.byref(g))); return float(g.value)
+
+    def scan_errors(self, i):
+        """jsgpu_scan_errors of image i (only for images whose status carries JSGPU_ST_EXACT = 0x40000000)."""
+        e = B.jsgpu_scan_errors(); self._ck(self.L.jsgpu_batch_errors(self.ctx, i, C.byref(e))); return e
 
     def checksums(self):
         """uint64 [n][12]: device-side checksums of every output buffer of every image (include/jsgpu.h)."""

@@ -62,6 +62,9 @@ void ref_set_file(RefCtx* c,const uint8_t* data,uint64_t n) {
 	c->wbuf.BufLoadWindow(0);
 }
 
+// CwindowBuf overlays (WindowBuf.cpp:516-560): bytes the reader sees instead of the file's, as JPEGsnoop's "overlay" tool installs them
+int  ref_overlay_install(RefCtx* c,unsigned start,const uint8_t* d,unsigned n) { return c->wbuf.OverlayInstall(0,(BYTE*)d,n,start,0,0,0,0,0,0,0) ? 1 : 0; }
+void ref_overlay_remove_all(RefCtx* c) { c->wbuf.OverlayRemoveAll(); }
 void ref_Reset(RefCtx* c)      { c->dec->Reset(); }
 void ref_ResetState(RefCtx* c) { c->dec->ResetState(); }
 int  ref_SetDqtEntry(RefCtx* c,unsigned t,unsigned i,unsigned izz,unsigned v) { return c->dec->SetDqtEntry(t,i,izz,(unsigned short)v); }

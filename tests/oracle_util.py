@@ -94,10 +94,24 @@ class Oracle:
         self._f("idct_tables")(self.ctx, lf.ctypes.data, li.ctypes.data)
         return lf, li
 
-    def decode(self, jpeg_bytes):
-        """Marker walk + DecodeScanImg(start, bDisplay=true, bQuiet=true); returns Decoded."""
+    def err_lines(self):
+        """Error log lines (AddLineErr) of the last decode — compiled reference only."""
+        assert self.kind != "port"
+        self.lib.ref_err_line.restype = C.c_char_p; self.lib.ref_err_line.argtypes = [C.c_void_p, C.c_int]
+        return [self.lib.ref_err_line(self.ctx, i).decode("latin-1") for i in range(self._f("num_err_lines")(self.ctx))]
+
+    def decode(self, jpeg_bytes, overlays=()):
+        """Marker walk + DecodeScanImg(start, bDisplay=true, bQuiet=true); returns Decoded.
+        overlays: [(file offset, bytes)] installed in the reference's CwindowBuf before the decode (reference only)."""
         buf = np.frombuffer(jpeg_bytes, np.uint8).copy()
         self._keep = buf
+        if self.kind != "port":
+            self.lib.ref_log_clear.argtypes = [C.c_void_p]; self.lib.ref_log_clear(self.ctx)      # nerr counts THIS decode
+            self.lib.ref_overlay_remove_all.argtypes = [C.c_void_p]; self.lib.ref_overlay_remove_all(self.ctx)
+            for off, data in overlays:
+                ob = np.frombuffer(bytes(data), np.uint8).copy()
+                self.lib.ref_overlay_install.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_uint]
+                self.lib.ref_overlay_install(self.ctx, int(off), ob.ctypes.data, ob.size)
         r = self._f("decode_jpeg")(self.ctx, buf.ctypes.data, buf.size, 1)
         if r < 0:
             raise ValueError(f"marker walk failed ({r})")

@@ -115,34 +115,97 @@ def test_dc_only_mode_matches_oracle(built, cases, huff):
         assert not JC.compare(want, got), name
 
 
-@pytest.mark.parametrize("huff", [0, 1, 2], ids=["auto", "warp", "lane"])
-def test_corrupt_streams_are_reported_not_fatal(built, cases, huff):
-    """Truncated / bit-flipped / zero-filled scans: every kernel terminates, the damaged images carry a non-zero
-    status (m_bScanBad), and a healthy image in the same batch is still bit-exact (the
-    reference's bit-by-bit resynchronisation itself is not reproduced)."""
-    from jpegsnoop_b200 import BatchDecoder, CimgDecode
-    rng = np.random.default_rng(5)
+def _damaged_cases(cases):
+    """name -> (jpeg bytes, overlays): truncation, bit flips, zero fill, stray markers, FFFF runs, restart markers swapped /
+    removed / inserted — what JPEGsnoop exists to look at."""
     good_name, good = cases[2]                               # 1080p 4:2:0 DRI=4
     nodri = cases[3][1]                                      # no restart markers: one long interval
-    sos = good.index(b"\xff\xda"); body0 = sos + 14
-    def flipped(j, n):
+    g444 = cases[0][1]                                       # 4:4:4, RST every MCU row
+    body0 = good.index(b"\xff\xda") + 14
+
+    def flipped(j, n, seed):
+        r = np.random.default_rng(seed)
         a = bytearray(j); lo = j.index(b"\xff\xda") + 14
-        for p in rng.integers(lo, len(j) - 2, n): a[p] ^= 1 << int(rng.integers(0, 8))
+        for p in r.integers(lo, len(j) - 2, n): a[p] ^= 1 << int(r.integers(0, 8))
         return bytes(a)
-    bad = [good[: body0 + (len(good) - body0) // 2] + b"\xff\xd9",                 # truncated in the middle of the scan
-           flipped(good, 200), flipped(nodri, 40),
-           good[: body0 + 5000] + bytes(len(good) - body0 - 5002) + b"\xff\xd9",    # tail zero-filled
-           nodri[: len(nodri) // 2]]                                                # cut, no EOI
-    bd = BatchDecoder(huff_kernel=huff, idct_kernel=0)
-    bd.set_batch(bad + [good]); bd.decode(); bd.sync()
-    st = [bd.fetch(i).status for i in range(len(bad) + 1)]
-    assert all(x != 0 for x in st[:-1]), st
-    assert st[-1] == 0, st
-    orc = _oracle(True)
-    assert not JC.compare(orc.decode(good), bd.fetch(len(bad)), what=("pix_y", "pix_cb", "pix_cr", "dib", "mcu_map", "blk_dc", "dht_histo")), good_name
+
+    def rst_positions(j):
+        lo = j.index(b"\xff\xda") + 14
+        return [i for i in range(lo, len(j) - 1) if j[i] == 0xFF and 0xD0 <= j[i + 1] <= 0xD7]
+    rp = rst_positions(good)
+    swapped = bytearray(good); swapped[rp[10] + 1], swapped[rp[11] + 1] = swapped[rp[11] + 1], swapped[rp[10] + 1]
+    removed = good[:rp[20]] + good[rp[20] + 2:]
+    inserted = good[:rp[30] + 40] + b"\xff\xd3" + good[rp[30] + 40:]
+    mid = body0 + 30000
+    return {
+        "trunc_mid": (good[: body0 + (len(good) - body0) // 2] + b"\xff\xd9", ()),
+        "flip200": (flipped(good, 200, 1), ()),
+        "flip40_nodri": (flipped(nodri, 40, 2), ()),
+        "zerotail": (good[: body0 + 5000] + bytes(len(good) - body0 - 5002) + b"\xff\xd9", ()),
+        "cut_noeoi": (nodri[: len(nodri) // 2], ()),
+        "flip3_444": (flipped(g444, 3, 3), ()),
+        "flip1": (flipped(good, 1, 4), ()),
+        "flip2_nodri": (flipped(nodri, 2, 6), ()),
+        "stray_marker": (good[:mid] + b"\xff\xe1" + good[mid:], ()),
+        "early_eoi": (good[:mid] + b"\xff\xd9" + good[mid:], ()),
+        "ffff_run": (good[:mid] + b"\xff\xff\xff" + good[mid:], ()),
+        "rst_swapped": (bytes(swapped), ()),
+        "rst_removed": (removed, ()),
+        "rst_inserted": (inserted, ()),
+        "overlay_bytes": (good, ((mid, b"\x12\x34\x56\x78"), (mid + 2, b"\xab"))),      # CwindowBuf overlays (WindowBuf.cpp:516-560), the later one wins
+    }
+
+
+@pytest.mark.parametrize("huff", [0, 1, 2], ids=["auto", "warp", "lane"])
+def test_damaged_scans_match_the_reference(built, cases, huff):
+    """Damaged scans, single-image drop-in: every output buffer AND every error line equal to the compiled reference's —
+    its one-bit resynchronisation (ImgDecode.cpp:1166-1187), stray-marker handling (:1486-1561, 1683-1706), lazy restarts
+    (:1644-1680), underflowing blocks (:1737-1760), the one-MCU-per-row tail after an overread (:3621-3625) and the
+    nErrMaxDecodeScan cap (:1100-1110)."""
+    if not ref_available("fixed"):
+        pytest.skip("needs the compiled reference (oracle/_ref)")
+    from jpegsnoop_b200 import CimgDecode
+    orc = Oracle("ref_fixed")
     dec = CimgDecode(idct_fixedpt=True, huff_kernel=huff, idct_kernel=0)
-    assert dec.decode(bad[0]).nerr > 0
-    assert not JC.compare(orc.decode(good), dec.decode(good)), "decode after a damaged image"
+    for name, (j, ovl) in _damaged_cases(cases).items():
+        want = orc.decode(j, overlays=ovl); want_lines = orc.err_lines()
+        dec.L.jsimg_overlay_remove_all(dec.h)
+        keep = []
+        for off, data in ovl:
+            ob = np.frombuffer(bytes(data), np.uint8).copy(); keep.append(ob)
+            dec.L.jsimg_overlay_install(dec.h, int(off), ob.ctypes.data, ob.size)
+        got = dec.decode(j)
+        bad = JC.compare(want, got)
+        assert not bad, f"{name}: mismatch in {bad}"
+        assert np.array_equal(np.asarray(want.stats)[10:12], np.asarray(got.stats)[10:12]), (name, want.stats, got.stats)     # m_nRestartRead, m_bScanBad
+        got_lines = dec.log_lines(3)
+        assert got_lines == want_lines, (name, len(got_lines), len(want_lines), [(a, b) for a, b in zip(got_lines, want_lines) if a != b][:3])
+
+
+def test_damaged_images_in_a_batch_match_the_reference(built, cases):
+    """The same in one batch next to healthy images: the damaged ones carry JSGPU_ST_EXACT, their outputs are the reference's,
+    their neighbours are untouched; the error-line count comes back through jsgpu_batch_errors."""
+    if not ref_available("fixed"):
+        pytest.skip("needs the compiled reference (oracle/_ref)")
+    from jpegsnoop_b200 import BatchDecoder
+    orc = Oracle("ref_fixed")
+    dmg = {k: v for k, v in _damaged_cases(cases).items() if not v[1]}
+    names = ["ok0"] + list(dmg) + ["ok1"]
+    jpegs = [cases[2][1]] + [v[0] for v in dmg.values()] + [cases[1][1]]
+    WHAT = ("geom", "pix_y", "pix_cb", "pix_cr", "dib", "mcu_map", "blk_dc", "dht_histo")
+    for dc_only in (False, True):
+        o = Oracle("ref_fixed", decode_ac=not dc_only)
+        bd = BatchDecoder(huff_kernel=0, idct_kernel=0, decode_ac=not dc_only)
+        bd.set_batch(jpegs); bd.decode(); bd.sync()
+        for i, (name, j) in enumerate(zip(names, jpegs)):
+            want = o.decode(j); got = bd.fetch(i)
+            assert not JC.compare(want, got, what=WHAT), (name, dc_only)
+            if name.startswith("ok"):
+                assert got.status == 0, (name, hex(got.status))
+            elif want.nerr:
+                assert got.status & 0x40000000, (name, hex(got.status))
+                e = bd.scan_errors(i)
+                assert e.nerr_lines == want.nerr and e.scan_bad == int(want.stats[11]), (name, e.nerr_lines, want.nerr)
 
 
 @pytest.mark.parametrize("nrep", [1, 2], ids=["single_stream_15", "chunked_30"])
