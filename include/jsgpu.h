@@ -169,6 +169,14 @@ int jsgpu_get_options(jsgpu_ctx* ctx, jsgpu_options* opt);
  * builds the device look-up tables for `nsets` table sets. */
 int jsgpu_upload_tables(jsgpu_ctx* ctx, const jsgpu_tables* sets, uint32_t nsets);
 
+/* Multi-GPU: images of a batch are partitioned across GPUs (one process or thread per GPU, no data-path collective); the
+ * one exchange is this broadcast of the shared table blob (jsgpu_tables is POD) from rank `root` to every rank of an NCCL
+ * communicator, over NVLink.  `nccl_comm` is the caller's ncclComm_t for ctx's device; on `root`, sets[0..nsets) is the
+ * source, on the others the destination.  libnccl is resolved at run time (dlopen), so single-GPU users need no NCCL:
+ * JSGPU_EUNSUP if it cannot be found.  Blocks until the blob is in host memory on this rank; every rank then calls
+ * jsgpu_upload_tables().  (the Python driver's torch.distributed broadcast does the same thing.) */
+int jsgpu_bcast_tables(jsgpu_ctx* ctx, jsgpu_tables* sets, uint32_t nsets, void* nccl_comm, int root);
+
 /* --- batch decode (replaces the body of CimgDecode::DecodeScanImg, ImgDecode.cpp:2723-3745,
  *     i.e. HOT LOOPS 1-4 of SURVEY.md §3.3, for n images at once) ------------------------- */
 /* Geometry (ImgDecode.cpp:2773-2872), validation (:2755-2770,2821-2825,3047-3123) and device

@@ -70,7 +70,7 @@ OUT_PIX_Y, OUT_PIX_CB, OUT_PIX_CR, OUT_DIB, OUT_BLK_Y, OUT_BLK_CB, OUT_BLK_CR, O
 # every symbol include/jsgpu.h and include/jsimg.h declare (tests check they are all exported)
 JSGPU_SYMBOLS = [
     "jsgpu_init", "jsgpu_free", "jsgpu_last_error", "jsgpu_strerror", "jsgpu_version", "jsgpu_stream", "jsgpu_sync",
-    "jsgpu_set_idct_tables", "jsgpu_set_options", "jsgpu_get_options", "jsgpu_upload_tables",
+    "jsgpu_set_idct_tables", "jsgpu_set_options", "jsgpu_get_options", "jsgpu_upload_tables", "jsgpu_bcast_tables",
     "jsgpu_batch_begin", "jsgpu_batch_layout", "jsgpu_batch_pools", "jsgpu_batch_upload", "jsgpu_batch_decode",
     "jsgpu_batch_download", "jsgpu_batch_stage_ms", "jsgpu_timer_start", "jsgpu_timer_stop", "jsgpu_batch_launches", "jsgpu_batch_selfsync_info", "jsgpu_batch_checksums", "jsgpu_batch_errors", "jsgpu_decode_batch_host",
     "jsgpu_host_alloc", "jsgpu_host_free", "jsgpu_host_copy_rate"]
@@ -106,6 +106,7 @@ def load():
     L.jsgpu_set_options.argtypes = [vp, C.POINTER(jsgpu_options)]
     L.jsgpu_get_options.argtypes = [vp, C.POINTER(jsgpu_options)]
     L.jsgpu_upload_tables.argtypes = [vp, vp, u32]
+    L.jsgpu_bcast_tables.argtypes = [vp, vp, u32, vp, i32]
     L.jsgpu_batch_begin.argtypes = [vp, vp, u32, u64]
     L.jsgpu_batch_layout.argtypes = [vp, vp, u32]
     L.jsgpu_batch_pools.argtypes = [vp, C.POINTER(jsgpu_pools)]

@@ -14,6 +14,7 @@
 #include <vector>
 #include <array>
 #include <algorithm>
+#include <dlfcn.h>
 
 #define JSGPU_VERSION 100
 
@@ -230,6 +231,43 @@ int jsgpu_upload_tables(jsgpu_ctx* ctx, const jsgpu_tables* sets, uint32_t nsets
     ctx->set_l2.assign(nsets, {});
     for (uint32_t i = 0; i < nsets; i++) for (int k = 0; k < JS_NSLOT; k++) ctx->set_l2[i][k] = h[i].lut2_overflow[k] ? 0xffffffffu : h[i].lut2_used[k];
     ctx->nsets = nsets;
+    return JSGPU_OK;
+}
+
+// ncclBroadcast(sendbuff, recvbuff, count, ncclChar = 0, root, comm, stream), resolved at run time
+typedef int (*js_nccl_bcast_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+static js_nccl_bcast_fn js_nccl_broadcast()
+{
+    static js_nccl_bcast_fn fn = nullptr; static bool tried = false;
+    if (!tried) {
+        tried = true;
+        const char* names[] = { getenv("JSGPU_NCCL_LIB"), "libnccl.so.2", "libnccl.so" };
+        for (const char* nm : names) {
+            if (!nm) continue;
+            void* h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (h) { fn = (js_nccl_bcast_fn)dlsym(h, "ncclBroadcast"); if (fn) break; }
+        }
+    }
+    return fn;
+}
+
+int jsgpu_bcast_tables(jsgpu_ctx* ctx, jsgpu_tables* sets, uint32_t nsets, void* nccl_comm, int root)
+{
+    if (!ctx || !sets || nsets == 0 || !nccl_comm || root < 0) return JSGPU_EINVAL;
+    js_nccl_bcast_fn bcast = js_nccl_broadcast();
+    if (!bcast) return fail(ctx, JSGPU_EUNSUP, "libnccl not found (set JSGPU_NCCL_LIB to its path)");
+    cudaSetDevice(ctx->device);
+    const size_t bytes = sizeof(jsgpu_tables) * (size_t)nsets;
+    DevBuf tmp;
+    CK(tmp.reserve(bytes));
+    cudaError_t e = cudaMemcpyAsync(tmp.p, sets, bytes, cudaMemcpyHostToDevice, ctx->stream);     // only root's content matters
+    int nr = 0;
+    if (e == cudaSuccess) nr = bcast(tmp.p, tmp.p, bytes, 0 /* ncclChar */, root, nccl_comm, ctx->stream);
+    if (e == cudaSuccess && nr == 0) e = cudaMemcpyAsync(sets, tmp.p, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && nr == 0) e = cudaStreamSynchronize(ctx->stream);
+    tmp.release();
+    if (nr != 0) return fail(ctx, JSGPU_ECUDA, "ncclBroadcast failed (ncclResult %d)", nr);
+    if (e != cudaSuccess) return fail(ctx, JSGPU_ECUDA, "table broadcast failed: %s", cudaGetErrorString(e));
     return JSGPU_OK;
 }
 

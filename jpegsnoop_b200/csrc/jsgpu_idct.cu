@@ -22,14 +22,21 @@
 #include "build/idct_baked.h"
 #include <cstring>
 
+// Launch shape, measured on B200 (profiles/r2_k2_variants.md): 4 warps per CTA — three take one 32-block group each in
+// phase 1 (a 4:2:0 tile has 64 Y + 16 Cb + 16 Cr blocks), all four share phase 2, whose 8 chroma-row groups then split
+// evenly — and no register prefetch of the next tile, which frees 32 registers: 96 registers x 128 threads x 5 CTAs = 20
+// warps per SM instead of 15 hide the same latency better.
 #ifndef IDCT_THREADS
-#define IDCT_THREADS 96        // 3 warps: one 32-block group each per pass over a tile
+#define IDCT_THREADS 128
+#endif
+#ifndef IDCT_FORCE_WARPS
+#define IDCT_FORCE_WARPS 4
 #endif
 #ifndef IDCT_MIN_CTAS
 #define IDCT_MIN_CTAS 5
 #endif
 #ifndef IDCT_PREFETCH
-#define IDCT_PREFETCH 1        // 1: the next tile's coefficient rows are requested into registers before phase 2 (32 registers)
+#define IDCT_PREFETCH 0        // 1: the next tile's coefficient rows are requested into registers before phase 2 (32 registers)
 #endif
 #ifndef IDCT_FIN_PACKED
 #define IDCT_FIN_PACKED 1      // 1: samples are finalised two at a time (packed s16x2 mask + add), see fin2_pair
@@ -355,7 +362,7 @@ static int launch_tab(const DevBatch& b, const IdctSym* sym, const ColorTabs* ct
     // one warp per 32-block group of a tile, at most 4 warps (larger tiles loop)
     uint32_t groups = (b.tile_plane_bytes / 128 + 31) / 32;
     uint32_t threads = 32 * (groups < 1 ? 1 : groups > IDCT_THREADS / 32 ? IDCT_THREADS / 32 : groups);
-#ifdef IDCT_FORCE_WARPS
+#if IDCT_FORCE_WARPS
     threads = 32 * IDCT_FORCE_WARPS;          // extra warps only take part in phase 2 (its row groups split evenly over 4 warps at 4:2:0)
 #endif
     const size_t smem = sizeof(Idct2Tables) + sizeof(TileGeo) + 2 * (size_t)b.tile_plane_bytes;

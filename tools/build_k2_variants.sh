@@ -7,14 +7,14 @@ make -s >/dev/null
 mkdir -p build/var ../variants
 NV="/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v"
 declare -A V
-V[v0]="-DIDCT_FIN_PACKED=0"
-V[v1]="-DIDCT_FIN_PACKED=1"
-V[v2]="-DIDCT_FIN_PACKED=2"
-V[v3]="-DIDCT_FIN_PACKED=1 -DIDCT_PREFETCH=0 -DIDCT_MIN_CTAS=7"
-V[v4]="-DIDCT_FIN_PACKED=1 -DIDCT_PREFETCH=0 -DIDCT_MIN_CTAS=6"
-V[v5]="-DIDCT_FIN_PACKED=1 -DIDCT_PREFETCH=1 -DIDCT_MIN_CTAS=6"
-V[v6]="-DIDCT_FIN_PACKED=1 -DIDCT_THREADS=128 -DIDCT_FORCE_WARPS=4 -DIDCT_MIN_CTAS=4"
-V[v7]="-DIDCT_FIN_PACKED=1 -DIDCT_THREADS=128 -DIDCT_FORCE_WARPS=4 -DIDCT_MIN_CTAS=5 -DIDCT_PREFETCH=0"
+V[w0]=""
+V[w1]="-DIDCT_MIN_CTAS=6"
+V[w2]="-DIDCT_MIN_CTAS=4"
+V[w3]="-DIDCT_MIN_CTAS=4 -DIDCT_PREFETCH=1"
+V[w4]="-DIDCT_THREADS=96 -DIDCT_FORCE_WARPS=0 -DIDCT_MIN_CTAS=6"
+V[w5]="-DIDCT_FIN_PACKED=0"
+V[w6]="-DIDCT_THREADS=160 -DIDCT_FORCE_WARPS=5 -DIDCT_MIN_CTAS=4"
+V[w7]="-DIDCT_THREADS=256 -DIDCT_FORCE_WARPS=8 -DIDCT_MIN_CTAS=2"
 for n in "${!V[@]}"; do
   ( $NV ${V[$n]} -c jsgpu_idct.cu -o build/var/idct_$n.o 2> build/var/idct_$n.log
     OBJS=$(ls build/*.o | grep -v jsgpu_idct.o)
