@@ -43,7 +43,7 @@ struct jsgpu_ctx {
     // device state
     DevBuf d_ctab; bool have_ctab = false;
     DevBuf d_li, d_lf, d_sym, d_tables, d_img, d_items, d_litems, d_tiles, d_ubits, d_seg64, d_ph, d_rowtab, d_ex;
-    bool sym_ok = false, baked_ok = false; int tab_mode = 0;
+    bool sym_ok = false, baked_ok = false, bakedf_ok = false; int tab_mode = 0;
     DevBuf d_bits, d_seg, d_coef, d_mcubits, d_pix, d_dib, d_blk, d_mcumap, d_histo, d_stats, d_misc;
     uint32_t nsets = 0;
     std::vector<std::array<uint32_t, JS_NSLOT>> set_l2;   // per table set and slot: second-level entries used (0xffffffff = overflowed)
@@ -184,6 +184,7 @@ int jsgpu_set_idct_tables(jsgpu_ctx* ctx, const int32_t* li, const float* lf)
     IdctSym* sym = new IdctSym;
     ctx->sym_ok = build_idct_sym(li, *sym);
     ctx->baked_ok = js_idct_baked_matches(li) != 0;
+    ctx->bakedf_ok = js_idctf_baked_matches(lf) != 0;
     ctx->h_li.assign(li, li + 64 * 64); ctx->h_lf.assign(lf, lf + 64 * 64);
     {   // table source of the LDG tile kernel: env override for experiments, else immediates when the baked copy matches
         const char* e = getenv("JSGPU_IDCT_TABLE");
@@ -621,8 +622,12 @@ int jsgpu_batch_decode(jsgpu_ctx* ctx)
         // idct_kernel: 2 = TMA-staged tile kernel, 0/3 = tile kernel with per-lane vector loads (measured faster, profiles/r1_idct.md)
         if (fused && ctx->opt.idct_kernel == 2 && ctx->tmap_ok) launches += js_launch_idct_tma(b, (const IdctSym*)ctx->d_sym.p, (const ColorTabs*)ctx->d_ctab.p, ctx->tmap, ctx->sm_count, s);
         else if (fused) launches += js_launch_idct_fused(b, (const IdctSym*)ctx->d_sym.p, (const ColorTabs*)ctx->d_ctab.p, ctx->sm_count, ctx->tab_mode, s);
-        if (!fused || ctx->n_nonstd > 0) {
-            DevBatch bs = b; bs.simple_only_nonstd = fused ? 1 : 0;
+        // float IDCT (the reference's default build): fused tile kernel with the float table as immediates, when that table
+        // is the host's, bit for bit; idct_kernel = 1 forces the literal kernels
+        const bool fusedf = (ctx->opt.idct_kernel != 1) && ctx->opt.idct_mode == 1 && ctx->bakedf_ok && b.ntiles > 0;
+        if (fusedf) launches += js_launch_idct_fused_float(b, (const ColorTabs*)ctx->d_ctab.p, ctx->sm_count, s);
+        if (!(fused || fusedf) || ctx->n_nonstd > 0) {
+            DevBatch bs = b; bs.simple_only_nonstd = (fused || fusedf) ? 1 : 0;
             launches += js_launch_idct_simple(bs, (const int32_t*)ctx->d_li.p, (const float*)ctx->d_lf.p, 0, 0, s);
         }
     }

@@ -54,6 +54,29 @@ __device__ __forceinline__ uint32_t fin_pair(uint32_t a, uint32_t b, uint32_t dc
 #endif
 }
 
+// Per-CTA copy of what the tile loop needs from the current image's descriptor (a CTA walks a contiguous run of
+// tiles, i.e. stays on one image for hundreds of tiles: one global read per image instead of per tile).
+struct TileGeo {
+    uint32_t ns, tile_mcus, H[3], V[3], cw[3], mcu_w, mcu_h, wp, hp, evc, pad;
+    unsigned long long coef_row[3], pix_off, dib_off;
+};
+
+// Coefficient row of block `idx` (0..nblk-1: all Y blocks of the tile row-major, then Cb, then Cr) of a tile.
+template <typename Geo>
+__device__ __forceinline__ bool tile_block_row(const Geo& im, const uint4& tile, uint32_t idx, size_t& row)
+{
+    const uint32_t ns = im.ns, U = im.tile_mcus;
+    const uint32_t hu0 = im.H[0] * U, hu1 = (ns == 3) ? im.H[1] * U : 0, hu2 = (ns == 3) ? im.H[2] * U : 0;
+    const uint32_t cnt0 = hu0 * im.V[0], cnt1 = hu1 * im.V[1], cnt2 = hu2 * im.V[2];
+    uint32_t i = idx, c = 0;
+    if (i >= cnt0) { i -= cnt0; c = 1; if (i >= cnt1) { i -= cnt1; c = 2; } }
+    if (c >= ns) c = 0;
+    const uint32_t Hc = im.H[c], huc = (c == 0) ? hu0 : (c == 1) ? hu1 : hu2;
+    const uint32_t v = i / huc, col = i - v * huc;
+    row = im.coef_row[c] + (size_t)(tile.y * im.V[c] + v) * im.cw[c] + (tile.z * Hc + col);
+    return (idx < cnt0 + cnt1 + cnt2) && (col < tile.w * Hc);
+}
+
 struct P2x {
     const uint8_t* planes; uint32_t pbase1, pbase2, ppitch0, ppitch1, ppitch2;
     uint32_t opr, px0, py0, wp, hp, mcu_h, ns, evc;

@@ -169,6 +169,8 @@ int js_launch_idct_simple(const DevBatch& b, const int32_t* li, const float* lf,
 struct IdctSym; struct ColorTabs;
 int js_launch_idct_fused(const DevBatch& b, const IdctSym* sym, const ColorTabs* ctab, int sm_count, int tab_mode, cudaStream_t s);
 int js_idct_baked_matches(const int32_t* li);
+int js_idctf_baked_matches(const float* lf);
+int js_launch_idct_fused_float(const DevBatch& b, const ColorTabs* ctab, int sm_count, cudaStream_t s);   // float-IDCT build, fused (jsgpu_idctf.cu)
 int js_launch_build_color_tables(ColorTabs* t, cudaStream_t s);
 int js_upload_idct_constants(const IdctSym* host_sym, cudaStream_t s);
 int js_make_coef_tensor_map(void* out_tmap, void* coef, uint64_t rows);

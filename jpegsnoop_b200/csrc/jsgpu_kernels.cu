@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(256) k_idct_simple(DevBatch b, const int32_t* 
             float f = 0.f;
             for (int vu = 1; vu < 64; vu++) f = __fadd_rn(f, __fmul_rn(lf[yx * 64 + vu], (float)row[vu]));   // :2381-2383
             f = __fmul_rn(f, 0.25f);
-            short nv = (short)((short)(__fmul_rn(f, 8.0f)) + dc);                                   // :2517-2519
+            short nv = (short)((short)(int)__fmul_rn(f, 8.0f) + dc);                          // float -> int (cvttss2si) -> short, as the x86 build does                                   // :2517-2519
             out = nv;
         }
         // destination (SetFullRes addressing, :2498-2557)
