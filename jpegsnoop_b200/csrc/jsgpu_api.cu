@@ -411,7 +411,7 @@ int jsgpu_batch_begin(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, 
     CK(ctx->d_bits.reserve(bitstream_bytes + 64));
     CK(ctx->d_ubits.reserve(ub + 16384));          // + slack: a reader of corrupt data stops at the next MCU boundary, at most one MCU (<= 12 KB of bits) past the end
     CK(ctx->d_litems.reserve(sizeof(uint2) * std::max<size_t>(litems.size() + litems_np.size() + vitems.size(), 1)));
-    CK(ctx->d_ph.reserve(pht * 64 + 256));                      // x 8 + ver 4 + k 4 + cnt 16 + aux 16 + pre 16 bytes per slot
+    CK(ctx->d_ph.reserve(pht * 72 + (size_t)n * 8 + 256));      // x 8 + ver 4 + k 4 + cnt 16 + aux 16 + pre 16 + two work lists 8 bytes per slot; two list lengths per image
     CK(ctx->d_rowtab.reserve(rtt * 20 + cst * 12 + 256));       // rowtab 4 + rowmask 16 bytes per 128-byte raw row; 3 words per 4 KB chunk
     CK(ctx->d_tiles.reserve(sizeof(uint4) * std::max<size_t>(tiles.size(), 1)));
     CK(ctx->d_seg64.reserve(8 * (size_t)seg + 16));
@@ -451,7 +451,9 @@ int jsgpu_batch_begin(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, 
     {   // slot arrays, 16-byte members first
         uint8_t* q = (uint8_t*)ctx->d_ph.p;
         b.ph_cnt = (uint4*)q; q += pht * 16; b.ph_aux = (uint4*)q; q += pht * 16; b.ph_pre = (uint4*)q; q += pht * 16;
-        b.ph_x = (unsigned long long*)q; q += pht * 8; b.ph_ver = (uint32_t*)q; q += pht * 4; b.ph_k = (uint32_t*)q;
+        b.ph_x = (unsigned long long*)q; q += pht * 8; b.ph_ver = (uint32_t*)q; q += pht * 4; b.ph_k = (uint32_t*)q; q += pht * 4;
+        b.ph_list[0] = (uint32_t*)q; q += pht * 4; b.ph_list[1] = (uint32_t*)q; q += pht * 4;
+        b.ph_nl[0] = (uint32_t*)q; q += (size_t)n * 4; b.ph_nl[1] = (uint32_t*)q;
         b.rowmask = (uint4*)ctx->d_rowtab.p; b.rowtab = (uint32_t*)((uint8_t*)ctx->d_rowtab.p + rtt * 16);
         b.cs_cnt = b.rowtab + rtt; b.cs_off = b.cs_cnt + cst; b.cs_seg = b.cs_off + cst;
     }

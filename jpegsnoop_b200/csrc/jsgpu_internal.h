@@ -117,6 +117,8 @@ struct DevBatch {
     // slot arrays of the self-synchronising passes (all images back to back, see PhSlots)
     unsigned long long* ph_x; uint32_t* ph_ver; uint32_t* ph_k; uint4* ph_cnt; uint4* ph_aux; uint4* ph_pre;
     uint32_t*          ph_nchg;     // [PH_MAX_ROUNDS + 2] slots whose exit state changed in fix round r
+    uint32_t*          ph_list[2];  // fix round r >= 2 works through the slots whose predecessor changed in round r-1: per image a list (at its
+    uint32_t*          ph_nl[2];    // ph_first) written in round r-1 into ph_list[(r-1)&1], its length in ph_nl[(r-1)&1][image]
     uint32_t*          cs_cnt; uint32_t* cs_off; uint32_t* cs_seg;    // k_unstuff_long: bytes kept per chunk, their exclusive prefix, owning interval
     uint32_t*          rowtab;      // self-synchronised images: unstuffed bytes before every 128-byte raw row of an interval ...
     uint4*             rowmask;     // ... and which of the row's 128 raw bytes do not reach the unstuffed copy (MCU file map without a re-walk)

@@ -83,30 +83,40 @@ __device__ __forceinline__ PhSlots ph_slots(const DevBatch& b, const DevImage& i
     return a;
 }
 
+// MODE 0: guess.  MODE 1: fix round 1 (every slot).  MODE 2: fix round r >= 2 — only the slots whose predecessor changed in
+// round r-1, taken from the per-image list that round wrote (dense threads instead of one live lane in a warp here and there).
 template <int MODE>
 __global__ void __launch_bounds__(PH_THREADS) k_ph_sync(DevBatch b, uint32_t round)
 {
-    if (MODE == 1 && round > 1 && b.ph_nchg[round - 1] == 0) return;       // the previous round changed nothing: settled
+    if (MODE == 2 && b.ph_nchg[round - 1] == 0) return;                    // the previous round changed nothing: settled
     extern __shared__ __align__(16) uint8_t ph_smem[];
     PhShared& sh = *reinterpret_cast<PhShared*>(ph_smem);
     uint16_t* const lutb = reinterpret_cast<uint16_t*>(ph_smem + sizeof(PhShared));
     uint32_t cur_sig = 0xffffffffu, cur_set = 0xffffffffu, nchg = 0;
+    const uint32_t* const lin = b.ph_list[(round + 1) & 1]; const uint32_t* const nin = b.ph_nl[(round + 1) & 1];    // written by round - 1
+    uint32_t* const lout = b.ph_list[round & 1]; uint32_t* const nout = b.ph_nl[round & 1];
     for (uint32_t it = blockIdx.x; it < b.nvitems; it += gridDim.x) {
-        const uint2 item = b.vitems[it];                       // (image, first slot); PH_THREADS slots per item
+        const uint2 item = b.vitems[it];                       // (image, first slot or first list position); PH_THREADS per item
         const DevImage& im = b.img[item.x];
+        uint32_t nlist = 0;
+        if (MODE == 2) { nlist = nin[item.x]; if (item.y >= nlist) continue; }     // CTA-uniform
         if (im.tab_sig != cur_sig || im.table_set != cur_set) {
             ph_stage(sh, lutb, im, b.tables + im.table_set);
             cur_sig = im.tab_sig; cur_set = im.table_set;
         }
-        const uint32_t slot = item.y + threadIdx.x;
+        uint32_t slot = item.y + threadIdx.x;
+        if (MODE == 2) { if (slot >= nlist) continue; slot = lin[im.ph_first + slot]; }
         if (slot >= im.ph_nslots) continue;
         const PhTabs t = ph_tabs(sh, lutb);
         const PhSegs sg = ph_segs(b, im);
         const PhSlots a = ph_slots(b, im);
         if (MODE == 0) ph_guess_slot(t, sg, b.ubits, a, slot);
-        else nchg += ph_fix_slot(t, sg, b.ubits, a, slot, round) ? 1u : 0u;
+        else if (ph_fix_slot(t, sg, b.ubits, a, slot, round)) {
+            nchg++;
+            if (slot + 1 < im.ph_nslots && a.k[slot + 1] == a.k[slot]) lout[im.ph_first + atomicAdd(&nout[item.x], 1u)] = slot + 1;    // its successor decodes again next round
+        }
     }
-    if (MODE == 1) {
+    if (MODE != 0) {
         nchg = __reduce_add_sync(FULL, nchg);
         if ((threadIdx.x & 31) == 0 && nchg) atomicAdd(&b.ph_nchg[round], nchg);
     }
@@ -187,8 +197,13 @@ int js_launch_selfsync(const DevBatch& b, int sm_count, cudaStream_t s)
     const uint32_t grid = std::min<uint32_t>(b.nvitems, (uint32_t)sm_count * 8u);
     int n = 0;
     cudaMemsetAsync(b.ph_nchg, 0, (PH_MAX_ROUNDS + 2) * sizeof(uint32_t), s);
+    cudaMemsetAsync(b.ph_nl[1], 0, (size_t)b.nimg * 4, s);
     k_ph_sync<0><<<grid, PH_THREADS, smem, s>>>(b, 0u); n++;
-    for (uint32_t r = 1; r <= PH_MAX_ROUNDS; r++) { k_ph_sync<1><<<grid, PH_THREADS, smem, s>>>(b, r); n++; }
+    k_ph_sync<1><<<grid, PH_THREADS, smem, s>>>(b, 1u); n++;
+    for (uint32_t r = 2; r <= PH_MAX_ROUNDS; r++) {
+        cudaMemsetAsync(b.ph_nl[r & 1], 0, (size_t)b.nimg * 4, s);
+        k_ph_sync<2><<<grid, PH_THREADS, smem, s>>>(b, r); n++;
+    }
     k_ph_fix_cta<<<std::min<uint32_t>(b.nimg, (uint32_t)sm_count * 4u), PH_THREADS, smem, s>>>(b); n++;
     k_ph_scan<<<std::min<uint32_t>(b.nimg, 65535u), 256, 0, s>>>(b); n++;
     return n;

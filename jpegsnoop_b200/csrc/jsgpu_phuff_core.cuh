@@ -33,6 +33,9 @@
 #define PH_DEAD        0xffffffffffffffffull     // state of a slot that belongs to no interval
 #define PH_NONE        0xffffffffu
 #define PH_MAX_BPM     48                        // 3 components x 4 x 4 blocks
+#ifndef PH_GUESS_BITS
+#define PH_GUESS_BITS  2048u                     // the guess decodes only the last PH_GUESS_BITS of its slot: enough to lock on for ~9 slots in 10
+#endif
 #define PH_MAX_ROUNDS  10                        // fix rounds enqueued up front (each ends at once when the previous changed nothing)
 
 // Shared-memory staged decode tables of one image, as the lane kernel lays them out: table j at lutb + j * JS_LANE_TAB
@@ -202,7 +205,10 @@ JS_HD void ph_guess_slot(const PhTabs& t, const PhSegs& sg, const uint8_t* ubits
     a.cnt[slot] = make_uint4(0, 0, 0, 0); a.aux[slot] = make_uint4(PH_NONE, 0, 0, 0);
     if (k == PH_NONE) { a.x[slot] = PH_DEAD; return; }
     const uint32_t i = slot - ph_slot_base(sg.start[k], k), end = sg.ulen[k] * 8u;
-    const uint32_t pos0 = i << PH_SUB_SHIFT, lim = (pos0 + PH_SUB_BITS < end) ? pos0 + PH_SUB_BITS : end;
+    const uint32_t s0 = i << PH_SUB_SHIFT, lim = (s0 + PH_SUB_BITS < end) ? s0 + PH_SUB_BITS : end;
+    // slot 0 starts at the true start of the interval; the others only need their exit state, which a decoder started
+    // PH_GUESS_BITS before the slot's end reaches as well as one started at its beginning (the fix rounds repair the rest)
+    const uint32_t pos0 = (i == 0 || lim - s0 <= PH_GUESS_BITS) ? s0 : lim - PH_GUESS_BITS;
     PhCount o;
     a.x[slot] = ph_run<false>(t, reinterpret_cast<const uint32_t*>(ubits + sg.uoff[k]), pos0, 0, 0, lim, o);
 }
