@@ -132,6 +132,8 @@ typedef struct {
 #define JSGPU_STAT_BRIGHT_MX 9   /* m_ptBrightMcu                                               */
 #define JSGPU_STAT_BRIGHT_MY 10
 #define JSGPU_STAT_NRST      11  /* m_nRestartRead                                              */
+#define JSGPU_STAT_END_POS   12  /* m_anScanBuffPtr_pos[0] / m_nScanBuffPtr_align after the last MCU: the reference's      */
+#define JSGPU_STAT_END_ALIGN 13  /* "Next position in scan buffer" and compression-ratio lines (ImgDecode.cpp:3659-3726)  */
 #define JSGPU_STAT_WORDS     16
 
 /* Output selectors for jsgpu_batch_download */
@@ -238,7 +240,9 @@ typedef struct {
     uint32_t nevents;         /* events seen; the first JSGPU_MAX_EVENTS are in ev[]                                       */
     uint32_t scan_bad;        /* m_bScanBad at the end of the scan                                                        */
     uint32_t restart_read;    /* m_nRestartRead                                                                           */
-    uint32_t done, pad[3];
+    uint32_t done;
+    uint32_t end_pos, end_align;  /* m_anScanBuffPtr_pos[0], m_nScanBuffPtr_align after the last MCU */
+    uint32_t pad;
     jsgpu_scan_event ev[JSGPU_MAX_EVENTS];
 } jsgpu_scan_errors;
 /* Error events of image `image` of the last decode (JSGPU_ESTATE when it did not take the serial path: status without

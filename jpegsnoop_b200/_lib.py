@@ -52,7 +52,7 @@ class jsgpu_scan_event(C.Structure):
 
 class jsgpu_scan_errors(C.Structure):
     _fields_ = [("nerr_lines", C.c_uint32), ("nevents", C.c_uint32), ("scan_bad", C.c_uint32), ("restart_read", C.c_uint32),
-                ("done", C.c_uint32), ("pad", C.c_uint32 * 3), ("ev", jsgpu_scan_event * 256)]
+                ("done", C.c_uint32), ("end_pos", C.c_uint32), ("end_align", C.c_uint32), ("pad", C.c_uint32), ("ev", jsgpu_scan_event * 256)]
 
 
 class jsgpu_pools(C.Structure):

@@ -57,6 +57,16 @@ private:
     std::vector<Ovl> m_ovl;
 };
 
+// Stand-in for the reference's CDIB (Dib.h:32-55) as far as the decode path needs it: a w*h*4-byte BGRA buffer.
+class CDIB {
+public:
+    void  Kill() { m_bits.clear(); m_bits.shrink_to_fit(); }
+    bool  CreateDIB(unsigned w, unsigned h, unsigned short) { m_bits.assign((size_t)w * h * 4, 0); return true; }
+    void* GetDIBBitArray() const { return m_bits.empty() ? nullptr : (void*)m_bits.data(); }
+private:
+    std::vector<uint8_t> m_bits;
+};
+
 // The configuration fields DecodeScanImg reads (SnoopConfig.h:72-142, read at
 // ImgDecode.cpp:448, 2730-2741) plus this port's device knobs.
 struct CSnoopConfig {

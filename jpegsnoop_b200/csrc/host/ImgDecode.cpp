@@ -15,6 +15,31 @@ static std::string fmt(const char* f, ...)
     return std::string(buf);
 }
 
+// The only places where the two build modes differ: how a line reaches the log, how the scan bytes are fetched, and where
+// the device knobs (which the reference's CSnoopConfig does not have) come from.
+#ifdef JSGPU_HOST_EXTERNAL_TYPES
+#define JS_LOGSTR(x) CString(std::string(x).c_str())
+static void js_copy_scan(CwindowBuf* w, unsigned long off, size_t n, uint8_t* dst) { for (size_t i = 0; i < n; i++) dst[i] = w->Buf(off + (unsigned long)i); }
+#ifdef IDCT_FIXEDPT
+static const bool kCfgIdctFixed = true;      // the reference's own compile-time switch (ImgDecode.cpp:32)
+#else
+static const bool kCfgIdctFixed = false;
+#endif
+#define JS_CFG_IDCT_FIXED(c)   kCfgIdctFixed
+#define JS_CFG_DEVICE(c)       0
+#define JS_CFG_HUFF(c)         0
+#define JS_CFG_IDCTK(c)        0
+#define JS_CFG_DEVMARKERS(c)   true
+#else
+#define JS_LOGSTR(x) std::string(x)
+static void js_copy_scan(CwindowBuf* w, unsigned long off, size_t n, uint8_t* dst) { w->BufCopy(off, n, dst); }
+#define JS_CFG_IDCT_FIXED(c)   ((c)->bIdctFixedPt)
+#define JS_CFG_DEVICE(c)       ((c)->nCudaDevice)
+#define JS_CFG_HUFF(c)         ((c)->nHuffKernel)
+#define JS_CFG_IDCTK(c)        ((c)->nIdctKernel)
+#define JS_CFG_DEVMARKERS(c)   ((c)->bDeviceMarkers)
+#endif
+
 CimgDecode::CimgDecode(CDocLog* pLog, CwindowBuf* pWBuf, CSnoopConfig* pConfig)
 {
     m_pAppConfig = pConfig ? pConfig : &m_sOwnConfig;
@@ -126,13 +151,13 @@ bool CimgDecode::SetDqtEntry(unsigned nTblDestId, unsigned nCoeffInd, unsigned n
 unsigned CimgDecode::GetDqtEntry(unsigned nTblDestId, unsigned nCoeffInd)
 {
     if (nTblDestId < MAX_DQT_DEST_ID && nCoeffInd < MAX_DQT_COEFF) return m_anDqtCoeff[nTblDestId][nCoeffInd];
-    m_pLog->AddLineErr(fmt("ERROR: GetDqtEntry(nTblDestId=%u, nCoeffInd=%u) out of indexed range", nTblDestId, nCoeffInd));
+    m_pLog->AddLineErr(JS_LOGSTR(fmt("ERROR: GetDqtEntry(nTblDestId=%u, nCoeffInd=%u) out of indexed range", nTblDestId, nCoeffInd)));
     return 0;
 }
 bool CimgDecode::SetDqtTables(unsigned nCompId, unsigned nTbl)
 {
     if (nCompId < MAX_SOF_COMP_NF && nTbl < MAX_DQT_DEST_ID) { m_anDqtTblSel[nCompId] = (int)nTbl; return true; }
-    m_pLog->AddLineErr(fmt("ERROR: SetDqtTables(Comp ID=%u, Table=%u) out of indexed range", nCompId, nTbl));
+    m_pLog->AddLineErr(JS_LOGSTR(fmt("ERROR: SetDqtTables(Comp ID=%u, Table=%u) out of indexed range", nCompId, nTbl)));
     return false;
 }
 bool CimgDecode::SetDhtTables(unsigned nCompInd, unsigned nTblDc, unsigned nTblAc)
@@ -142,13 +167,13 @@ bool CimgDecode::SetDhtTables(unsigned nCompInd, unsigned nTblDc, unsigned nTblA
         m_anDhtTblSel[DHT_CLASS_AC][nCompInd] = (int)nTblAc;
         return true;
     }
-    m_pLog->AddLineErr(fmt("ERROR: SetDhtTables(comp=%u, TblDC=%u TblAC=%u) out of indexed range", nCompInd, nTblDc, nTblAc));
+    m_pLog->AddLineErr(JS_LOGSTR(fmt("ERROR: SetDhtTables(comp=%u, TblDC=%u TblAC=%u) out of indexed range", nCompInd, nTblDc, nTblAc)));
     return false;
 }
 bool CimgDecode::SetDhtEntry(unsigned nDestId, unsigned nClass, unsigned nInd, unsigned nLen, unsigned nBits, unsigned nMask, unsigned nCode)
 {
     if (nDestId >= MAX_DHT_DEST_ID || nClass >= MAX_DHT_CLASS || nInd >= MAX_DHT_CODES) {
-        m_pLog->AddLineErr("ERROR: Attempt to set DHT entry out of range");
+        m_pLog->AddLineErr(JS_LOGSTR("ERROR: Attempt to set DHT entry out of range"));
         return false;
     }
     m_anDhtLookup_bitlen[nClass][nDestId][nInd] = nLen;
@@ -163,7 +188,7 @@ bool CimgDecode::SetDhtEntry(unsigned nDestId, unsigned nClass, unsigned nInd, u
 bool CimgDecode::SetDhtSize(unsigned nDestId, unsigned nClass, unsigned nSize)
 {
     if (nDestId >= MAX_DHT_DEST_ID || nClass >= MAX_DHT_CLASS || nSize >= MAX_DHT_CODES) {
-        m_pLog->AddLineErr("ERROR: Attempt to set DHT table size out of range");
+        m_pLog->AddLineErr(JS_LOGSTR("ERROR: Attempt to set DHT table size out of range"));
         return false;
     }
     m_anDhtLookupSize[nClass][nDestId] = nSize;
@@ -218,15 +243,15 @@ bool CimgDecode::ExportImageDesc(jsgpu_image_desc& d, unsigned nStart) const
 bool CimgDecode::EnsureDevice()
 {
     if (m_pGpu) return true;
-    int r = jsgpu_init(m_pAppConfig->nCudaDevice, &m_pGpu);
+    int r = jsgpu_init(JS_CFG_DEVICE(m_pAppConfig), &m_pGpu);
     if (r != JSGPU_OK) {
         // No CPU fallback exists: the decode fails loudly, in the reference's own convention (a log line)
-        m_pLog->AddLineErr(fmt("*** ERROR: GPU scan decoder unavailable (%s) — scan not decoded ***", jsgpu_strerror(r)));
+        m_pLog->AddLineErr(JS_LOGSTR(fmt("*** ERROR: GPU scan decoder unavailable (%s) — scan not decoded ***", jsgpu_strerror(r))));
         m_pGpu = nullptr;
         return false;
     }
     r = jsgpu_set_idct_tables(m_pGpu, &m_anIdctLookup[0][0], &m_afIdctLookup[0][0]);
-    if (r != JSGPU_OK) { m_pLog->AddLineErr(fmt("*** ERROR: GPU scan decoder: %s ***", jsgpu_last_error(m_pGpu))); return false; }
+    if (r != JSGPU_OK) { m_pLog->AddLineErr(JS_LOGSTR(fmt("*** ERROR: GPU scan decoder: %s ***", jsgpu_last_error(m_pGpu)))); return false; }
     return true;
 }
 
@@ -239,19 +264,19 @@ void CimgDecode::DecodeScanImg(unsigned nStart, bool bDisplay, bool bQuiet)
     m_bDecodeScanAc = bDecodeScanAc;
     m_bPreviewIsJpeg = false;
 
-    if (!m_bImgDetailsSet) { m_pLog->AddLineErr("*** ERROR: Decoding image before Image components defined ***"); return; }
+    if (!m_bImgDetailsSet) { m_pLog->AddLineErr(JS_LOGSTR("*** ERROR: Decoding image before Image components defined ***")); return; }
     if (m_nNumSosComps != NUM_CHAN_GRAYSCALE && m_nNumSosComps != NUM_CHAN_YCC) {
-        m_pLog->AddLineWarn(fmt("  NOTE: Number of SOS components not supported [%u]", m_nNumSosComps));
+        m_pLog->AddLineWarn(JS_LOGSTR(fmt("  NOTE: Number of SOS components not supported [%u]", m_nNumSosComps)));
         return;
     }
     unsigned nHMax = 0, nVMax = 0;
     for (unsigned c = 1; c <= m_nNumSosComps; c++) { if (m_anSofSampFactH[c] > nHMax) nHMax = m_anSofSampFactH[c]; if (m_anSofSampFactV[c] > nVMax) nVMax = m_anSofSampFactV[c]; }
     if (m_nNumSosComps == 1) {                                                     // ref :2805-2817
-        if (m_anSofSampFactH[1] != 1 || m_anSofSampFactV[1] != 1) m_pLog->AddLineWarn("    Altering sampling factor for single component scan to 0x11");
+        if (m_anSofSampFactH[1] != 1 || m_anSofSampFactV[1] != 1) m_pLog->AddLineWarn(JS_LOGSTR("    Altering sampling factor for single component scan to 0x11"));
         m_anSofSampFactH[1] = 1; m_anSofSampFactV[1] = 1; nHMax = nVMax = 1;
     }
     if (nHMax == 0 || nVMax == 0 || nHMax > MAX_SAMP_FACT_H || nVMax > MAX_SAMP_FACT_V) {
-        m_pLog->AddLineWarn(fmt("  NOTE: Degree of subsampling factor not supported [HMax=%u, VMax=%u]", nHMax, nVMax));
+        m_pLog->AddLineWarn(JS_LOGSTR(fmt("  NOTE: Degree of subsampling factor not supported [HMax=%u, VMax=%u]", nHMax, nVMax)));
         return;
     }
     m_nMcuWidth = nHMax * 8; m_nMcuHeight = nVMax * 8;
@@ -269,33 +294,33 @@ void CimgDecode::DecodeScanImg(unsigned nStart, bool bDisplay, bool bQuiet)
     if (m_nNumSosComps == NUM_CHAN_YCC) { m_pPixValCb = new short[nPix](); m_pPixValCr = new short[nPix](); }
     if (bDisplay) m_pDibBits = new unsigned char[nPix * 4]();
 
-    if (!bQuiet) { m_pLog->AddLineHdr("*** Decoding SCAN Data ***"); m_pLog->AddLine(fmt("  OFFSET: 0x%08X", nStart)); }
+    if (!bQuiet) { m_pLog->AddLineHdr(JS_LOGSTR("*** Decoding SCAN Data ***")); m_pLog->AddLine(JS_LOGSTR(fmt("  OFFSET: 0x%08X", nStart))); }
     if (m_nNumSofComps != NUM_CHAN_GRAYSCALE && m_nNumSofComps != NUM_CHAN_YCC) {   // ref :3029-3035
-        m_pLog->AddLineWarn(fmt("  NOTE: Number of Image Components not supported [%u]", m_nNumSofComps));
+        m_pLog->AddLineWarn(JS_LOGSTR(fmt("  NOTE: Number of Image Components not supported [%u]", m_nNumSofComps)));
         return;
     }
     for (unsigned c = 1; c <= m_nNumSosComps; c++) if (m_anDqtTblSel[c] < 0) {
-        m_pLog->AddLineErr("*** ERROR: Decoding image before DQT Table Selection via JFIF_SOF ***"); return; }
+        m_pLog->AddLineErr(JS_LOGSTR("*** ERROR: Decoding image before DQT Table Selection via JFIF_SOF ***")); return; }
     bool bDhtReady = true;
     for (unsigned k = 0; k < 2; k++) for (unsigned c = 1; c <= m_nNumSosComps; c++) if (m_anDhtTblSel[k][c] < 0) bDhtReady = false;
     if (bDhtReady) for (unsigned c = 1; c <= m_nNumSosComps; c++) {
         if (m_anDhtLookupSize[0][m_anDhtTblSel[0][c]] == 0) bDhtReady = false;
         if (m_anDhtLookupSize[1][m_anDhtTblSel[1][c]] == 0) bDhtReady = false;
     }
-    if (!bDhtReady) { m_pLog->AddLineErr("*** ERROR: Decoding image before DHT Table Selection via JFIF_SOS ***"); return; }
+    if (!bDhtReady) { m_pLog->AddLineErr(JS_LOGSTR("*** ERROR: Decoding image before DHT Table Selection via JFIF_SOS ***")); return; }
     if (!bQuiet) {
-        m_pLog->AddLine(m_bDecodeScanAc ? "  Scan Decode Mode: Full IDCT (AC + DC)" : "  Scan Decode Mode: No IDCT (DC only)");
-        if (!m_bDecodeScanAc) m_pLog->AddLineWarn("    NOTE: Low-resolution DC component shown. Can decode full-res with [Options->Scan Segment->Full IDCT]");
-        m_pLog->AddLine("");
+        m_pLog->AddLine(JS_LOGSTR(m_bDecodeScanAc ? "  Scan Decode Mode: Full IDCT (AC + DC)" : "  Scan Decode Mode: No IDCT (DC only)"));
+        if (!m_bDecodeScanAc) m_pLog->AddLineWarn(JS_LOGSTR("    NOTE: Low-resolution DC component shown. Can decode full-res with [Options->Scan Segment->Full IDCT]"));
+        m_pLog->AddLine(JS_LOGSTR(""));
     }
 
     // ---- device decode (replaces HOT LOOPS 1-4, ref :3164-3630 and :4619-4821) -----------------
     if (!EnsureDevice()) { m_bScanBad = true; return; }
     jsgpu_options opt; jsgpu_get_options(m_pGpu, &opt);
-    opt.idct_mode = m_pAppConfig->bIdctFixedPt ? 0 : 1;
+    opt.idct_mode = JS_CFG_IDCT_FIXED(m_pAppConfig) ? 0 : 1;
     opt.decode_ac = m_bDecodeScanAc ? 1 : 0;
-    opt.huff_kernel = m_pAppConfig->nHuffKernel; opt.idct_kernel = m_pAppConfig->nIdctKernel;
-    opt.device_markers = m_pAppConfig->bDeviceMarkers ? 1 : 0;
+    opt.huff_kernel = JS_CFG_HUFF(m_pAppConfig); opt.idct_kernel = JS_CFG_IDCTK(m_pAppConfig);
+    opt.device_markers = JS_CFG_DEVMARKERS(m_pAppConfig) ? 1 : 0;
     opt.want_histo = 1; opt.want_mcu_map = 1;
     opt.scan_err_max = (int32_t)m_nScanErrMax;
     jsgpu_set_options(m_pGpu, &opt);
@@ -307,7 +332,7 @@ void CimgDecode::DecodeScanImg(unsigned nStart, bool bDisplay, bool bQuiet)
     const unsigned long nEof = m_pWBuf->GetPosEof();
     const size_t nScanBytes = (nStart < nEof) ? (size_t)(nEof - nStart) : 0;
     std::vector<uint8_t> scan(nScanBytes + 4, 0);
-    m_pWBuf->BufCopy(nStart, nScanBytes, scan.data());         // one bulk read instead of Buf() per byte (ref :1398-1399)
+    js_copy_scan(m_pWBuf, nStart, nScanBytes, scan.data());         // one bulk read instead of Buf() per byte (ref :1398-1399)
     d.table_set = 0; d.scan_offset = 0; d.scan_length = nScanBytes;
 
     int r = jsgpu_upload_tables(m_pGpu, pTables, 1);
@@ -319,7 +344,7 @@ void CimgDecode::DecodeScanImg(unsigned nStart, bool bDisplay, bool bQuiet)
     jsgpu_image_layout lo; memset(&lo, 0, sizeof lo);
     if (r == JSGPU_OK) r = jsgpu_batch_layout(m_pGpu, &lo, 1);
     if (r != JSGPU_OK) {
-        m_pLog->AddLineErr(fmt("*** ERROR: GPU scan decoder failed: %s (%s) ***", jsgpu_strerror(r), jsgpu_last_error(m_pGpu)));
+        m_pLog->AddLineErr(JS_LOGSTR(fmt("*** ERROR: GPU scan decoder failed: %s (%s) ***", jsgpu_strerror(r), jsgpu_last_error(m_pGpu))));
         m_bScanBad = true;
         return;
     }
@@ -360,64 +385,66 @@ void CimgDecode::DecodeScanImg(unsigned nStart, bool bDisplay, bool bQuiet)
             for (unsigned i = 0; i < nEv; i++) {
                 const jsgpu_scan_event& e = pErr->ev[i];
                 switch (e.code) {
-                case JSGPU_EV_OVERREAD_BEFORE:     m_pLog->AddLineErr(fmt("*** ERROR: Overread scan segment (before nCode)! @ Offset: 0x%08X.%u", e.a, e.b)); break;
-                case JSGPU_EV_OVERREAD_AFTER_CODE: m_pLog->AddLineErr(fmt("*** ERROR: Overread scan segment (after nCode)! @ Offset: 0x%08X.%u", e.a, e.b)); break;
-                case JSGPU_EV_OVERREAD_AFTER_BITS: m_pLog->AddLineErr(fmt("*** ERROR: Overread scan segment (after bitstring)! @ Offset: 0x%08X.%u", e.a, e.b)); break;
-                case JSGPU_EV_NOCODE:              m_pLog->AddLineErr(fmt("*** ERROR: Can't find huffman bitstring @ 0x%08X.%u, table %u, value [0x%08x]", e.a, e.b, e.c, e.d)); break;
-                case JSGPU_EV_CAP:                 m_pLog->AddLineErr(fmt("    Only reported first %u instances of this message...", e.a)); break;
-                case JSGPU_EV_RST_MISMATCH:        m_pLog->AddLineErr(fmt("  ERROR: Expected RST marker index RST%u got RST%u @ 0x%08X.0", e.a, e.b, e.c)); break;
+                case JSGPU_EV_OVERREAD_BEFORE:     m_pLog->AddLineErr(JS_LOGSTR(fmt("*** ERROR: Overread scan segment (before nCode)! @ Offset: 0x%08X.%u", e.a, e.b))); break;
+                case JSGPU_EV_OVERREAD_AFTER_CODE: m_pLog->AddLineErr(JS_LOGSTR(fmt("*** ERROR: Overread scan segment (after nCode)! @ Offset: 0x%08X.%u", e.a, e.b))); break;
+                case JSGPU_EV_OVERREAD_AFTER_BITS: m_pLog->AddLineErr(JS_LOGSTR(fmt("*** ERROR: Overread scan segment (after bitstring)! @ Offset: 0x%08X.%u", e.a, e.b))); break;
+                case JSGPU_EV_NOCODE:              m_pLog->AddLineErr(JS_LOGSTR(fmt("*** ERROR: Can't find huffman bitstring @ 0x%08X.%u, table %u, value [0x%08x]", e.a, e.b, e.c, e.d))); break;
+                case JSGPU_EV_CAP:                 m_pLog->AddLineErr(JS_LOGSTR(fmt("    Only reported first %u instances of this message...", e.a))); break;
+                case JSGPU_EV_RST_MISMATCH:        m_pLog->AddLineErr(JS_LOGSTR(fmt("  ERROR: Expected RST marker index RST%u got RST%u @ 0x%08X.0", e.a, e.b, e.c))); break;
                 case JSGPU_EV_MARKER_NOTE:
-                    m_pLog->AddLine(fmt("  Scan Data encountered marker   0xFF%02X @ 0x%08X.0", e.a, e.b));
-                    if (e.a != 0xD9) m_pLog->AddLineErr("  NOTE: Marker wasn't EOI (0xFFD9)");
+                    m_pLog->AddLine(JS_LOGSTR(fmt("  Scan Data encountered marker   0xFF%02X @ 0x%08X.0", e.a, e.b)));
+                    if (e.a != 0xD9) m_pLog->AddLineErr(JS_LOGSTR("  NOTE: Marker wasn't EOI (0xFFD9)"));
                     break;
-                case JSGPU_EV_BADMARK:             m_pLog->AddLineErr(fmt("*** ERROR: Bad marker @ 0x%08X.%u", e.a, e.b)); break;
-                case JSGPU_EV_BADCODE:             m_pLog->AddLineErr(fmt("*** ERROR: Bad huffman code @ 0x%08X.%u", e.a, e.b)); break;
-                case JSGPU_EV_NCOEF:               m_pLog->AddLineErr(fmt("*** ERROR: @ 0x%08X.%u, nNumCoeffs>64 [%u]", e.a, e.b, e.c)); break;
+                case JSGPU_EV_BADMARK:             m_pLog->AddLineErr(JS_LOGSTR(fmt("*** ERROR: Bad marker @ 0x%08X.%u", e.a, e.b))); break;
+                case JSGPU_EV_BADCODE:             m_pLog->AddLineErr(JS_LOGSTR(fmt("*** ERROR: Bad huffman code @ 0x%08X.%u", e.a, e.b))); break;
+                case JSGPU_EV_NCOEF:               m_pLog->AddLineErr(JS_LOGSTR(fmt("*** ERROR: @ 0x%08X.%u, nNumCoeffs>64 [%u]", e.a, e.b, e.c))); break;
                 case JSGPU_EV_MCU: {
                     const unsigned nComp = e.c & 0xFF, nCssH = (e.c >> 8) & 0xFF, nCssV = (e.c >> 16) & 0xFF;
                     std::string strComp = fmt(nComp == 0 ? "Lum CSS(%u,%u)" : nComp == 1 ? "Chr(Cb) CSS(%u,%u)" : "Chr(Cr) CSS(%u,%u)", nCssH, nCssV);
-                    m_pLog->AddLineErr(fmt("*** ERROR: Bad scan data in MCU(%u,%u): %s @ Offset 0x%08X.%u", e.a, e.b, strComp.c_str(), e.d, e.e));
-                    m_pLog->AddLineErr(fmt("           MCU located at pixel=(%u,%u)", m_nMcuWidth * e.a + nCssH * 8, m_nMcuHeight * e.b + nCssV * 8));
+                    m_pLog->AddLineErr(JS_LOGSTR(fmt("*** ERROR: Bad scan data in MCU(%u,%u): %s @ Offset 0x%08X.%u", e.a, e.b, strComp.c_str(), e.d, e.e)));
+                    m_pLog->AddLineErr(JS_LOGSTR(fmt("           MCU located at pixel=(%u,%u)", m_nMcuWidth * e.a + nCssH * 8, m_nMcuHeight * e.b + nCssV * 8)));
                     break; }
                 case JSGPU_EV_RST_MISSING:
-                    m_pLog->AddLine(fmt("  Expect Restart interval elapsed @ 0x%08X.%u", e.a, e.b));
-                    m_pLog->AddLineErr("    ERROR: Restart marker not detected");
+                    m_pLog->AddLine(JS_LOGSTR(fmt("  Expect Restart interval elapsed @ 0x%08X.%u", e.a, e.b)));
+                    m_pLog->AddLineErr(JS_LOGSTR("    ERROR: Restart marker not detected"));
                     break;
                 default: break;
                 }
             }
             if (pErr->nevents > JSGPU_MAX_EVENTS)
-                m_pLog->AddLineErr(fmt("    (%u further scan error events not itemised)", pErr->nevents - JSGPU_MAX_EVENTS));
+                m_pLog->AddLineErr(JS_LOGSTR(fmt("    (%u further scan error events not itemised)", pErr->nevents - JSGPU_MAX_EVENTS)));
             m_nRestartRead = pErr->restart_read;
         } else {
             m_bScanBad = true;
-            m_pLog->AddLineErr(fmt("*** ERROR: Bad scan data (device status 0x%08X; error events unavailable: %s) ***", lo.status, jsgpu_last_error(m_pGpu)));
+            m_pLog->AddLineErr(JS_LOGSTR(fmt("*** ERROR: Bad scan data (device status 0x%08X; error events unavailable: %s) ***", lo.status, jsgpu_last_error(m_pGpu))));
         }
         delete pErr;
     } else if (lo.status) {
         m_bScanBad = true;
-        m_pLog->AddLineErr(fmt("*** ERROR: Bad scan data (device status 0x%08X) ***", lo.status));
+        m_pLog->AddLineErr(JS_LOGSTR(fmt("*** ERROR: Bad scan data (device status 0x%08X) ***", lo.status)));
     }
     if (!bQuiet) {
-        m_pLog->AddLine("");
-        if (bDisplay && m_bAvgYValid) { m_pLog->AddLine("  Average Pixel Luminance (Y):"); m_pLog->AddLine(fmt("    Y=[%3u] (range: 0..255)", (unsigned)m_nAvgY)); m_pLog->AddLine(""); }
+        m_pLog->AddLine(JS_LOGSTR(""));
+        if (bDisplay && m_bAvgYValid) { m_pLog->AddLine(JS_LOGSTR("  Average Pixel Luminance (Y):")); m_pLog->AddLine(JS_LOGSTR(fmt("    Y=[%3u] (range: 0..255)", (unsigned)m_nAvgY))); m_pLog->AddLine(JS_LOGSTR("")); }
         if (bDisplay && m_bBrightValid) {
-            m_pLog->AddLine("  Brightest Pixel Search:");
-            m_pLog->AddLine(fmt("    YCC=[%5d,%5d,%5d] RGB=[%3u,%3u,%3u] @ MCU[%3u,%3u]", m_nBrightY, m_nBrightCb, m_nBrightCr, m_nBrightR, m_nBrightG, m_nBrightB, m_nBrightMcuX, m_nBrightMcuY));
-            m_pLog->AddLine("");
+            m_pLog->AddLine(JS_LOGSTR("  Brightest Pixel Search:"));
+            m_pLog->AddLine(JS_LOGSTR(fmt("    YCC=[%5d,%5d,%5d] RGB=[%3u,%3u,%3u] @ MCU[%3u,%3u]", m_nBrightY, m_nBrightCb, m_nBrightCr, m_nBrightR, m_nBrightG, m_nBrightB, m_nBrightMcuX, m_nBrightMcuY)));
+            m_pLog->AddLine(JS_LOGSTR(""));
         }
-        m_pLog->AddLine("  Finished Decoding SCAN Data");
-        m_pLog->AddLine(fmt("    Number of RESTART markers decoded: %u", m_nRestartRead));
-        m_pLog->AddLine("");
+        m_pLog->AddLine(JS_LOGSTR("  Finished Decoding SCAN Data"));
+        m_pLog->AddLine(JS_LOGSTR(fmt("    Number of RESTART markers decoded: %u", m_nRestartRead)));
+        m_pLog->AddLine(JS_LOGSTR(""));
     }
 }
 
 bool CimgDecode::IsPreviewReady() { return m_bPreviewIsJpeg; }
+void CimgDecode::ResetImageContent() {}                       // ref :603-605
 
 // ---- getters ----------------------------------------------------------------------------------
 void CimgDecode::GetPixMapPtrs(short*& pMapY, short*& pMapCb, short*& pMapCr) { pMapY = m_pPixValY; pMapCb = m_pPixValCb; pMapCr = m_pPixValCr; }
 void CimgDecode::GetImageSize(unsigned& nX, unsigned& nY) { nX = m_nImgSizeX; nY = m_nImgSizeY; }
-void CimgDecode::GetBitmapPtr(unsigned char*& pBitmap) { pBitmap = m_pDibBits; }
+void CimgDecode::GetBitmapPtr(unsigned char*& pBitmap)          // ref :4940: the bits of m_pDibTemp — which a JPEG scan keeps in m_pDibBits here
+{ pBitmap = (m_bDibTempReady && !m_bPreviewIsJpeg) ? (unsigned char*)m_pDibTemp.GetDIBBitArray() : m_pDibBits; }
 unsigned CimgDecode::PackFileOffset(unsigned nByte, unsigned nBit) { return (nByte << 4) + nBit; }
 void CimgDecode::UnpackFileOffset(unsigned nPacked, unsigned& nByte, unsigned& nBit) { nBit = nPacked & 0x7; nByte = nPacked >> 4; }
 void CimgDecode::LookupFilePosPix(unsigned nPixX, unsigned nPixY, unsigned& nByte, unsigned& nBit)

@@ -8,26 +8,68 @@
 // status bar, histogram drawing: ImgDecode.h:296-298, 319-329, 346-349, 419-425) are outside
 // the hot path and are not part of this class.
 #pragma once
+// Two build modes.  Stand-alone (default): HostCompat.h supplies small stand-ins for CDocLog / CwindowBuf / CSnoopConfig /
+// CDIB.  Inside JPEGsnoop (-DJSGPU_HOST_EXTERNAL_TYPES): the application's own DocLog.h, WindowBuf.h, SnoopConfig.h and
+// Dib.h are used — this is how oracle/Makefile's `n1` target compiles the reference's unmodified CjfifDecode against this
+// class.
+#ifdef JSGPU_HOST_EXTERNAL_TYPES
+#include "stdafx.h"
+#include "DocLog.h"
+#include "WindowBuf.h"
+#include "SnoopConfig.h"
+#include "Dib.h"
+#else
 #include "HostCompat.h"
+#endif
 #include "../../../include/jsgpu.h"
 #include <string>
 
 // Limits and indices — same meaning as the reference's (ImgDecode.h:62-106)
+#ifndef MAX_DHT_CLASS
 #define MAX_DHT_CLASS     2
+#endif
+#ifndef MAX_DHT_DEST_ID
 #define MAX_DHT_DEST_ID   4
+#endif
+#ifndef DHT_CLASS_DC
 #define DHT_CLASS_DC      0
+#endif
+#ifndef DHT_CLASS_AC
 #define DHT_CLASS_AC      1
+#endif
+#ifndef MAX_DHT_CODES
 #define MAX_DHT_CODES     260
+#endif
+#ifndef MAX_DQT_DEST_ID
 #define MAX_DQT_DEST_ID   4
+#endif
+#ifndef MAX_DQT_COEFF
 #define MAX_DQT_COEFF     64
+#endif
+#ifndef MAX_DQT_COMP
 #define MAX_DQT_COMP      256
+#endif
+#ifndef MAX_SOF_COMP_NF
 #define MAX_SOF_COMP_NF   256
+#endif
+#ifndef MAX_SOS_COMP_NS
 #define MAX_SOS_COMP_NS   4
+#endif
+#ifndef MAX_SAMP_FACT_H
 #define MAX_SAMP_FACT_H   4
+#endif
+#ifndef MAX_SAMP_FACT_V
 #define MAX_SAMP_FACT_V   4
+#endif
+#ifndef NUM_CHAN_GRAYSCALE
 #define NUM_CHAN_GRAYSCALE 1
+#endif
+#ifndef NUM_CHAN_YCC
 #define NUM_CHAN_YCC      3
+#endif
+#ifndef DCT_SZ_ALL
 #define DCT_SZ_ALL        64
+#endif
 
 class CimgDecode
 {
@@ -67,6 +109,8 @@ public:
     void        UnpackFileOffset(unsigned nPacked, unsigned& nByte, unsigned& nBit);                 // ref :5123
     void        ScanErrorsDisable();                                                                 // ref :1014
     void        ScanErrorsEnable();                                                                  // ref :1026
+    void        ResetImageContent();                                                                 // ref :603 (empty there too)
+    void        SetStatusBar(void* /* CStatusBar* */) {}                                              // ref ImgDecode.h:296: GUI only
 
     // Results the reference keeps in private members and reports in its log (ref :3659-3720);
     // exposed read-only so callers and tests do not need `friend` access.
@@ -94,6 +138,8 @@ public:
     int             m_anDqtTblSel[MAX_DQT_COMP];
     bool            m_bDibTempReady;
     bool            m_bPreviewIsJpeg;
+    CDIB            m_pDibTemp;        // public in the reference (ImgDecode.h:384): CjfifDecode hands it to the PSD decoder
+                                       // (JfifDecode.cpp:7369); a JPEG scan's BGRA bits live in m_pDibBits, see GetBitmapPtr()
 
 private:
     void        ResetDqtTables();

@@ -26,6 +26,7 @@ struct Ex {
     bool scan_end, scan_bad, cur_err, restart_flag;
     uint32_t restart_read, restart_last, restart_expect, mcus_left, rst_interval, warn_bad_num, err_max;
     uint32_t precision; bool decode_ac;
+    short css[3][16];                            // m_anDcLumCss / m_anDcChrCbCss / m_anDcChrCrCss: DC sum of block (v,h) of the current MCU
     JsExResult* res;
     uint32_t* histo;                             // [2][4][17] of this image
     const DevTableSet* ts;
@@ -209,7 +210,8 @@ __device__ __noinline__ bool ex_decode_scan_comp(Ex& x, uint32_t tdc, uint32_t t
         const uint32_t saved_pos = x.pos[0], saved_err = x.latch_err, saved_align = x.align;
         int r = ex_read_scan_val(x, bdc ? 0 : 1, bdc ? tdc : tac, zrl, val);
         if (r == EX_RSV_RST_TERM) {                              // :1644-1680: the restart is handled where the marker is met
-            dc_lum = dc_cb = dc_cr = 0;
+            dc_lum = dc_cb = dc_cr = 0;                              // DecodeRestartDcState (:2693-2703) clears the per-block copies too
+            for (int i = 0; i < 16; i++) { x.css[0][i] = 0; x.css[1][i] = 0; x.css[2][i] = 0; }
             x.ptr += 2;
             ex_restart_scan_buf(x, x.ptr);
             x.restart_flag = false;
@@ -257,6 +259,7 @@ __global__ void __launch_bounds__(32) k_huff_exact(DevBatch b, int err_max)
     x.precision = im.precision; x.decode_ac = b.decode_ac != 0;
     x.rst_interval = im.restart_en ? im.ri : 0;                 // m_nRestartInterval (0 when DRI is off: never looked at then)
     x.restart_read = 0; x.restart_last = 0; x.restart_expect = 0;
+    for (int i = 0; i < 16; i++) { x.css[0][i] = 0; x.css[1][i] = 0; x.css[2][i] = 0; }
     ex_restart_scan_buf(x, 0);
     ex_buff_topup(x);
     short dc_lum = 0, dc_cb = 0, dc_cr = 0;
@@ -283,17 +286,24 @@ __global__ void __launch_bounds__(32) k_huff_exact(DevBatch b, int err_max)
                     row[0] = dc;
                     const bool ac = full && x.decode_ac;
                     for (int i = 1; i < 64; i++) row[i] = ac ? x.dct[i] : (short)0;
-                    // block-DC maps, :3524-3608 (the reference's own addressing, overlaps included)
-                    const size_t bi = (size_t)(my * im.ev[c] + v) * im.blk_xmax + (mx * im.eh[c] + h);
-                    if (bi < nb) ((c == 0) ? blk_y : (c == 1) ? blk_cb : blk_cr)[bi] = dc;
+                    x.css[c][v * 4 + h] = dc;                    // :3282, 3357, 3388
                 }
             }
+            // block-DC maps, :3524-3608: written after the MCU from the per-block copies (which a restart inside the MCU has
+            // cleared), with the reference's own addressing, overlaps included
+            for (uint32_t c = 0; c < ns; c++)
+                for (uint32_t v = 0; v < im.V[c]; v++) for (uint32_t h = 0; h < im.H[c]; h++) {
+                    const size_t bi = (size_t)(my * im.ev[c] + v) * im.blk_xmax + (mx * im.eh[c] + h);
+                    if (bi < nb) ((c == 0) ? blk_y : (c == 1) ? blk_cb : blk_cr)[bi] = x.css[c][v * 4 + h];
+                }
             if (im.restart_en) x.mcus_left--;
             if (x.scan_end && x.scan_bad) stop = true;           // :3621-3625
         }
     }
     x.res->scan_bad = x.scan_bad ? 1u : 0u; x.res->restart_read = x.restart_read; x.res->done = 1;
+    x.res->end_pos = x.pos[0]; x.res->end_align = x.align;
     b.stats[(size_t)ii * 16 + 11] = (int32_t)x.restart_read;     // m_nRestartRead
+    b.stats[(size_t)ii * 16 + 12] = (int32_t)x.pos[0]; b.stats[(size_t)ii * 16 + 13] = (int32_t)x.align;
 }
 
 // Before the re-decode: which images need it, and their intermediates back to the state the reference starts from

@@ -95,30 +95,40 @@ JS_HD uint32_t ph_fsl(uint32_t lo, uint32_t hi, uint32_t n)      // high word of
 #endif
 }
 struct PhWin {
-    uint32_t hi, lo, nx, idx; int nb; const uint32_t* base;
+    uint32_t hi, lo, nx0, nx1, idx; int nb; const uint32_t* base;
     // window positioned at absolute bit `bitpos` of the interval; idx stays an absolute word index, so that
-    // pos() is the absolute bit position too
+    // pos() is the absolute bit position too.  Two words are kept in flight behind the window: a refill consumes the word
+    // requested two refills (~10 symbols) earlier, so the L2 latency of these scattered 4-byte loads stays off the chain.
     JS_HD void init(const uint32_t* words, uint32_t bitpos) {
         base = words; idx = bitpos >> 5;
-        hi = ph_ldw(base + idx); lo = ph_ldw(base + idx + 1); nx = ph_ldw(base + idx + 2);
-        idx += 3; nb = 64;
+        hi = ph_ldw(base + idx); lo = ph_ldw(base + idx + 1); nx0 = ph_ldw(base + idx + 2); nx1 = ph_ldw(base + idx + 3);
+        idx += 4; nb = 64;
         consume(bitpos & 31);
     }
     JS_HD void refill_if_low() {               // afterwards >= 33 bits are in the window
-        if (nb <= 32) {
 #if defined(__CUDA_ARCH__)
-            hi |= __funnelshift_rc(nx, 0, nb);
-            lo = __funnelshift_rc(0, nx, nb);
-#else
-            hi |= (nb >= 32) ? 0u : (nx >> nb);
-            lo = (nb >= 32) ? nx : (nx << (32 - nb));
-#endif
+        // predicated in-place reload of the look-ahead word: written as a C++ conditional the compiler loads into a temporary
+        // and copies it at the end of the same step, i.e. waits for the very load that is to be hidden (cf. Win in jsgpu_huff.cu)
+        const uint32_t need = (nb <= 32) ? 1u : 0u;
+        if (need) {
+            hi |= __funnelshift_rc(nx0, 0, nb);
+            lo = __funnelshift_rc(0, nx0, nb);
             nb += 32;
-            nx = ph_ldw(base + idx); idx++;
+            nx0 = nx1;
         }
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.global.nc.u32 %0, [%1];\n\t}" : "+r"(nx1) : "l"(base + idx), "r"(need));
+        idx += need;
+#else
+        if (nb <= 32) {
+            hi |= (nb >= 32) ? 0u : (nx0 >> nb);
+            lo = (nb >= 32) ? nx0 : (nx0 << (32 - nb));
+            nb += 32;
+            nx0 = nx1; nx1 = ph_ldw(base + idx); idx++;
+        }
+#endif
     }
     JS_HD void consume(uint32_t n) { hi = ph_fsl(lo, hi, n); lo = (n >= 32) ? 0u : (lo << n); nb -= (int)n; }
-    JS_HD uint32_t pos() const { return 32u * (idx - 1) - (uint32_t)nb; }
+    JS_HD uint32_t pos() const { return 32u * (idx - 2) - (uint32_t)nb; }
 };
 
 // What a fix run learns about its slot.

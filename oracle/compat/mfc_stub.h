@@ -52,6 +52,11 @@ typedef unsigned long   ULONGLONG_T;
 #define DECLARE_MESSAGE_MAP()
 #define MB_OK 0
 #define MB_ICONSTOP 0
+#define MB_YESNO 0
+#define MB_ICONQUESTION 0
+#define IDNO 7
+#define IDYES 6
+typedef unsigned long long ULONGLONG;
 #define MB_ICONEXCLAMATION 0
 #define TRANSPARENT 1
 #define OPAQUE 2
@@ -66,12 +71,25 @@ typedef unsigned long   ULONGLONG_T;
 #define DT_CALCRECT 0
 #define SRCCOPY 0
 #define BI_RGB 0
+#define _tcscmp strcmp
+#define _tcsnccmp strncmp
+#define _tcsncmp strncmp
+#define _istprint isprint
+template <size_t N> inline void _tcscpy_s(char (&d)[N],const char* s){ strncpy(d,s,N-1); d[N-1]=0; }
+inline void _tcscpy_s(char* d,size_t n,const char* s){ if(n){ strncpy(d,s,n-1); d[n-1]=0; } }
+#define _tcstol strtol
+#define _tstoi atoi
+#define _tcschr strchr
+#define _stprintf_s snprintf
+inline BOOL CopyFile(LPCTSTR,LPCTSTR,BOOL){ return FALSE; }
 #define _tcstoul strtoul
 #define _tcslen strlen
 #define _tcscpy strcpy
 inline wchar_t* lstrcpyW(wchar_t* d,const wchar_t* s){ wchar_t* r=d; while((*d++=*s++)){} return r; }
 inline void OutputDebugString(LPCTSTR){}
 
+class CString;
+typedef CString CStringA;
 class CString {
 public:
 	std::string s;
@@ -123,6 +141,19 @@ public:
 	bool operator==(const CString& o) const { return s==o.s; }
 	bool operator==(const char* p) const { return s==p; }
 	bool operator!=(const char* p) const { return s!=p; }
+	// (the N1 build of the reference's CjfifDecode needs a few more members than the scan decoder does)
+	CString& TrimRight() { while(!s.empty() && isspace((unsigned char)s.back())) s.pop_back(); return *this; }
+	CString& TrimLeft()  { size_t i=0; while(i<s.size() && isspace((unsigned char)s[i])) i++; s.erase(0,i); return *this; }
+	CString& Trim()      { TrimRight(); return TrimLeft(); }
+	int  Replace(const char* a,const char* b) { int n=0; size_t la=strlen(a),lb=strlen(b),p=0; if(!la) return 0; while((p=s.find(a,p))!=std::string::npos){ s.replace(p,la,b); p+=lb; n++; } return n; }
+	int  Replace(char a,char b) { int n=0; for(auto& c:s) if(c==a){c=b;n++;} return n; }
+	int  ReverseFind(char c) const { size_t r=s.rfind(c); return r==std::string::npos?-1:(int)r; }
+	int  CompareNoCase(const char* p) const { return strcasecmp(s.c_str(),p); }
+	void SetAt(int i,char c) { s[(size_t)i]=c; }
+	int  Delete(int i,int n=1) { if(i<(int)s.size()) s.erase((size_t)i,(size_t)n); return (int)s.size(); }
+	int  FindOneOf(const char* set) const { size_t r=s.find_first_of(set); return r==std::string::npos?-1:(int)r; }
+	bool operator!=(const CString& o) const { return s!=o.s; }
+	bool operator<(const CString& o) const { return s<o.s; }
 	LPTSTR GetBuffer(int n=0) { if((int)s.size()<n) s.resize((size_t)n); return &s[0]; }
 	void ReleaseBuffer(int n=-1) { if(n<0) s.resize(strlen(s.c_str())); else s.resize((size_t)n); }
 };
@@ -200,7 +231,14 @@ class CFile { public:
 	uint64_t Seek(int64_t off,UINT from){ int64_t b=(from==begin)?0:(from==current)?(int64_t)m_pos:(int64_t)m_n; int64_t p=b+off; if(p<0)p=0; m_pos=(uint64_t)p; return m_pos; }
 	UINT Read(void* dst,UINT n){ if(m_pos>=m_n) return 0; uint64_t r=std::min<uint64_t>(n,m_n-m_pos); memcpy(dst,m_p+m_pos,(size_t)r); m_pos+=r; return (UINT)r; }
 	uint64_t GetPosition() const { return m_pos; }
+	// write side (N1 build: CjfifDecode's export functions; never reached by the tests): discards
+	enum { modeCreate=1, modeWrite=2, typeBinary=4, shareDenyNone=8, modeRead=16, shareDenyWrite=32, modeNoTruncate=64 };
+	CFile(LPCTSTR,UINT) : m_p(nullptr),m_n(0),m_pos(0) {}
+	BOOL Open(LPCTSTR,UINT,void* =nullptr){ return FALSE; }
+	void Write(const void*,UINT){} void Close(){} void Flush(){}
 };
+class CException { public: virtual ~CException(){} BOOL GetErrorMessage(LPTSTR p,UINT n){ if(n) p[0]=0; return TRUE; } void Delete(){} };
+class CFileException : public CException { public: int m_cause=0; };
 
 inline int AfxMessageBox(LPCTSTR,UINT=0,UINT=0){ return 0; }
 CWinApp* AfxGetApp();
