@@ -133,7 +133,8 @@ typedef struct {
 #define JSGPU_STAT_BRIGHT_MY 10
 #define JSGPU_STAT_NRST      11  /* m_nRestartRead                                              */
 #define JSGPU_STAT_END_POS   12  /* m_anScanBuffPtr_pos[0] / m_nScanBuffPtr_align after the last MCU: the reference's      */
-#define JSGPU_STAT_END_ALIGN 13  /* "Next position in scan buffer" and compression-ratio lines (ImgDecode.cpp:3659-3726)  */
+#define JSGPU_STAT_END_ALIGN 13
+#define JSGPU_STAT_END_MARK  14  /* file position of the marker that ends the scan (BuffAddByte logs it, ImgDecode.cpp:1527-1543) */  /* "Next position in scan buffer" and compression-ratio lines (ImgDecode.cpp:3659-3726)  */
 #define JSGPU_STAT_WORDS     16
 
 /* Output selectors for jsgpu_batch_download */

@@ -18,6 +18,7 @@ static std::string fmt(const char* f, ...)
 // The only places where the two build modes differ: how a line reaches the log, how the scan bytes are fetched, and where
 // the device knobs (which the reference's CSnoopConfig does not have) come from.
 #ifdef JSGPU_HOST_EXTERNAL_TYPES
+#include "JPEGsnoop.h"          // CJPEGsnoopApp::m_pAppConfig, as the reference's constructor reads it (ImgDecode.cpp:146-148)
 #define JS_LOGSTR(x) CString(std::string(x).c_str())
 static void js_copy_scan(CwindowBuf* w, unsigned long off, size_t n, uint8_t* dst) { for (size_t i = 0; i < n; i++) dst[i] = w->Buf(off + (unsigned long)i); }
 #ifdef IDCT_FIXEDPT
@@ -42,7 +43,11 @@ static void js_copy_scan(CwindowBuf* w, unsigned long off, size_t n, uint8_t* ds
 
 CimgDecode::CimgDecode(CDocLog* pLog, CwindowBuf* pWBuf, CSnoopConfig* pConfig)
 {
+#ifdef JSGPU_HOST_EXTERNAL_TYPES
+    m_pAppConfig = pConfig ? pConfig : ((CJPEGsnoopApp*)AfxGetApp())->m_pAppConfig;
+#else
     m_pAppConfig = pConfig ? pConfig : &m_sOwnConfig;
+#endif
     m_pLog = pLog; m_pWBuf = pWBuf; m_pGpu = nullptr;
     m_bDibTempReady = false; m_bPreviewIsJpeg = false;
     m_pMcuFileMap = nullptr;
@@ -423,16 +428,67 @@ void CimgDecode::DecodeScanImg(unsigned nStart, bool bDisplay, bool bQuiet)
         m_bScanBad = true;
         m_pLog->AddLineErr(JS_LOGSTR(fmt("*** ERROR: Bad scan data (device status 0x%08X) ***", lo.status)));
     }
+    if (!(lo.status & JSGPU_ST_EXACT)) {
+        // A healthy scan still leaves one line behind: topping the accumulator up past the last data byte meets the marker
+        // that ends the scan (ref :1527-1543) — EOI normally; anything else also earns an error line there.
+        const unsigned nEndMark = (unsigned)st[JSGPU_STAT_END_MARK];
+        if ((unsigned long)nEndMark + 1 < nEof && m_nWarnBadScanNum < m_nScanErrMax) {
+            const unsigned nMarker = m_pWBuf->Buf(nEndMark + 1);
+            m_pLog->AddLine(JS_LOGSTR(fmt("  Scan Data encountered marker   0xFF%02X @ 0x%08X.0", nMarker, nEndMark)));
+            if (nMarker != 0xD9) m_pLog->AddLineErr(JS_LOGSTR("  NOTE: Marker wasn't EOI (0xFFD9)"));
+            m_nWarnBadScanNum++;
+            if (m_nWarnBadScanNum >= m_nScanErrMax) m_pLog->AddLineErr(JS_LOGSTR(fmt("    Only reported first %u instances of this message...", m_nScanErrMax)));
+        }
+    }
+    const unsigned nEndPos = (unsigned)st[JSGPU_STAT_END_POS], nEndAlign = (unsigned)st[JSGPU_STAT_END_ALIGN];
     if (!bQuiet) {
         m_pLog->AddLine(JS_LOGSTR(""));
-        if (bDisplay && m_bAvgYValid) { m_pLog->AddLine(JS_LOGSTR("  Average Pixel Luminance (Y):")); m_pLog->AddLine(JS_LOGSTR(fmt("    Y=[%3u] (range: 0..255)", (unsigned)m_nAvgY))); m_pLog->AddLine(JS_LOGSTR("")); }
-        if (bDisplay && m_bBrightValid) {
-            m_pLog->AddLine(JS_LOGSTR("  Brightest Pixel Search:"));
-            m_pLog->AddLine(JS_LOGSTR(fmt("    YCC=[%5d,%5d,%5d] RGB=[%3u,%3u,%3u] @ MCU[%3u,%3u]", m_nBrightY, m_nBrightCb, m_nBrightCr, m_nBrightR, m_nBrightG, m_nBrightB, m_nBrightMcuX, m_nBrightMcuY)));
-            m_pLog->AddLine(JS_LOGSTR(""));
-        }
+        // ref :3655-3668 compression statistics: bits of scan data consumed up to where the accumulator stands
+        m_pLog->AddLine(JS_LOGSTR("  Compression stats:"));
+        const float fRatio = (float)(m_nDimX * m_nDimY * m_nNumSosComps * 8) / (float)((nEndPos - nStart) * 8);
+        m_pLog->AddLine(JS_LOGSTR(fmt("    Compression Ratio: %5.2f:1", fRatio)));
+        const float fBpp = (float)((nEndPos - nStart) * 8) / (float)(m_nDimX * m_nDimY);
+        m_pLog->AddLine(JS_LOGSTR(fmt("    Bits per pixel:    %5.2f:1", fBpp)));
+        m_pLog->AddLine(JS_LOGSTR(""));
+        // ref :3670-3691 code-length histogram (m_anDhtHisto, counted on the device)
+        m_pLog->AddLine(JS_LOGSTR("  Huffman code histogram stats:"));
+        for (unsigned nClass = DHT_CLASS_DC; nClass <= DHT_CLASS_AC; nClass++)
+            for (unsigned nDestId = 0; nDestId <= m_anDhtLookupSetMax[nClass]; nDestId++) {
+                unsigned nTotal = 0;
+                for (unsigned nLen = 1; nLen <= 16; nLen++) nTotal += m_anDhtHisto[nClass][nDestId][nLen];
+                m_pLog->AddLine(JS_LOGSTR(fmt("    Huffman Table: (Dest ID: %u, Class: %s)", nDestId, nClass ? "AC" : "DC")));
+                for (unsigned nLen = 1; nLen <= 16; nLen++)
+                    m_pLog->AddLine(JS_LOGSTR(fmt("      # codes of length %02u bits: %8u (%3.0f%%)", nLen, m_anDhtHisto[nClass][nDestId][nLen],
+                                                   (m_anDhtHisto[nClass][nDestId][nLen] * 100.0) / nTotal)));
+                m_pLog->AddLine(JS_LOGSTR(""));
+            }
+        // ref :3764-3837 ReportColorStats with the clip/histogram statistics off (bHistoEn = bStatClipEn = false: the colour
+        // pass is ConvertYCCtoRGBFastFloat, which counts nothing, :4753-4758)
+        m_pLog->AddLine(JS_LOGSTR("  YCC clipping in DC:"));
+        m_pLog->AddLine(JS_LOGSTR(fmt("    Y  component: [<0=%5u] [>255=%5u]", 0u, 0u)));
+        m_pLog->AddLine(JS_LOGSTR(fmt("    Cb component: [<0=%5u] [>255=%5u]", 0u, 0u)));
+        m_pLog->AddLine(JS_LOGSTR(fmt("    Cr component: [<0=%5u] [>255=%5u]", 0u, 0u)));
+        m_pLog->AddLine(JS_LOGSTR(""));
+        m_pLog->AddLine(JS_LOGSTR("  RGB clipping in DC:"));
+        m_pLog->AddLine(JS_LOGSTR(fmt("    R  component: [<0=%5u] [>255=%5u]", 0u, 0u)));
+        m_pLog->AddLine(JS_LOGSTR(fmt("    G  component: [<0=%5u] [>255=%5u]", 0u, 0u)));
+        m_pLog->AddLine(JS_LOGSTR(fmt("    B  component: [<0=%5u] [>255=%5u]", 0u, 0u)));
+        m_pLog->AddLine(JS_LOGSTR(""));
+    }
+    if (bDisplay && m_bAvgYValid) {                              // ref :3702-3708 (also in quiet mode)
+        m_pLog->AddLine(JS_LOGSTR("  Average Pixel Luminance (Y):"));
+        m_pLog->AddLine(JS_LOGSTR(fmt("    Y=[%3u] (range: 0..255)", (unsigned)m_nAvgY)));
+        m_pLog->AddLine(JS_LOGSTR(""));
+    }
+    if (bDisplay && m_bBrightValid) {                            // ref :3710-3718
+        m_pLog->AddLine(JS_LOGSTR("  Brightest Pixel Search:"));
+        m_pLog->AddLine(JS_LOGSTR(fmt("    YCC=[%5d,%5d,%5d] RGB=[%3u,%3u,%3u] @ MCU[%3u,%3u]", m_nBrightY, m_nBrightCb, m_nBrightCr, m_nBrightR, m_nBrightG, m_nBrightB, m_nBrightMcuX, m_nBrightMcuY)));
+        m_pLog->AddLine(JS_LOGSTR(""));
+    }
+    if (!bQuiet) {                                               // ref :3723-3731
         m_pLog->AddLine(JS_LOGSTR("  Finished Decoding SCAN Data"));
         m_pLog->AddLine(JS_LOGSTR(fmt("    Number of RESTART markers decoded: %u", m_nRestartRead)));
+        m_pLog->AddLine(JS_LOGSTR(fmt("    Next position in scan buffer: Offset 0x%08X.%u", nEndPos, nEndAlign)));
         m_pLog->AddLine(JS_LOGSTR(""));
     }
 }

@@ -18,10 +18,11 @@
 #include "WindowBuf.h"
 #include "SnoopConfig.h"
 #include "Dib.h"
+#include "jsgpu.h"                 // found through -I<repo>/include (the application's build decides the include paths)
 #else
 #include "HostCompat.h"
-#endif
 #include "../../../include/jsgpu.h"
+#endif
 #include <string>
 
 // Limits and indices — same meaning as the reference's (ImgDecode.h:62-106)
@@ -69,6 +70,16 @@
 #endif
 #ifndef DCT_SZ_ALL
 #define DCT_SZ_ALL        64
+#endif
+
+// ... and the ones the reference's OTHER translation units take from ImgDecode.h (JfifDecode.cpp:3465, 4959-4965, 7477)
+#ifndef MAX_DHT_CODELEN
+#define MAX_DHT_CODELEN   16      // ImgDecode.h:67
+#endif
+#ifndef SCAN_COMP_Y
+#define SCAN_COMP_Y       1       // ImgDecode.h:112-114: component indices of a YCC scan
+#define SCAN_COMP_CB      2
+#define SCAN_COMP_CR      3
 #endif
 
 class CimgDecode

@@ -252,6 +252,7 @@ __global__ void k_finalize_stats(DevBatch b)
         if ((eb >> 3) < D) pos = im.file_pos + b.seg_start[sidx] + js_raw_of_unstuffed(b, im, k, eb >> 3);
         else pos = im.file_pos + b.scan_end[i] + ((eb >> 3) - D);
         st[12] = (int32_t)pos; st[13] = (int32_t)(eb & 7);
+        st[14] = (int32_t)(im.file_pos + b.scan_end[i]);
     }
 }
 

@@ -16,7 +16,7 @@ ORACLE_DIR = os.path.join(ROOT, "oracle")
 
 def build_oracles(quiet=True):
     """Build the port always; the reference oracle only where /root/reference exists."""
-    out = subprocess.run(["make", "-C", ORACLE_DIR, "port", "ref"], capture_output=True, text=True)
+    out = subprocess.run(["make", "-C", ORACLE_DIR, "port", "ref", "n1"], capture_output=True, text=True)
     if out.returncode != 0:
         raise RuntimeError("oracle build failed:\n" + out.stdout[-2000:] + out.stderr[-2000:])
     return out.stdout if not quiet else ""
