@@ -701,13 +701,15 @@ static inline size_t lane_smem_bytes(uint32_t nl, bool histo)
 }
 
 // Bit window as two 32-bit registers (hi = next 32 bits, lo = the 32 after), funnel-shift consume.
+#ifndef JS_WIN_DEPTH
+#define JS_WIN_DEPTH 1                  // words in flight behind the bit window (2 = requested two refills ahead)
+#endif
 struct Win {
     uint32_t hi, lo; int nb; uint32_t nx; uint32_t idx; const uint32_t* base;
-    __device__ __forceinline__ void init(const uint8_t* b) {
-        base = reinterpret_cast<const uint32_t*>(b);
-        hi = __ldg(base); lo = __ldg(base + 1);
-        nx = __ldg(base + 2); idx = 3; nb = 64;
-    }
+#if JS_WIN_DEPTH == 2
+    uint32_t nx2;
+#endif
+    __device__ __forceinline__ void init(const uint8_t* b) { init_at(b, 0); }
     // start at absolute bit `bitpos` of the interval (virtual restart intervals): idx stays an absolute word index,
     // so consumed() is the absolute bit position
     __device__ __forceinline__ void init_at(const uint8_t* b, uint32_t bitpos) {
@@ -715,6 +717,9 @@ struct Win {
         const uint32_t w = bitpos >> 5;
         hi = __ldg(base + w); lo = __ldg(base + w + 1);
         nx = __ldg(base + w + 2); idx = w + 3; nb = 64;
+#if JS_WIN_DEPTH == 2
+        nx2 = __ldg(base + w + 3); idx = w + 4;
+#endif
         consume(bitpos & 31);
     }
     // Top up when 32 bits or fewer are left (6 <= nb then).  The look-ahead word is reloaded IN PLACE by a
@@ -727,12 +732,19 @@ struct Win {
             hi |= __funnelshift_rc(nx, 0, nb);             // nx >> nb, 0 when nb == 32
             lo = __funnelshift_rc(0, nx, nb);              // nx << (32 - nb), nx when nb == 32
             nb += 32;
+#if JS_WIN_DEPTH == 2
+            nx = nx2;
+#endif
         }
+#if JS_WIN_DEPTH == 2
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.global.nc.u32 %0, [%1];\n\t}" : "+r"(nx2) : "l"(base + idx), "r"(need));
+#else
         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.global.nc.u32 %0, [%1];\n\t}" : "+r"(nx) : "l"(base + idx), "r"(need));
+#endif
         idx += need;
     }
     __device__ __forceinline__ void consume(uint32_t n) { hi = __funnelshift_l(lo, hi, n); lo <<= n; nb -= (int)n; }
-    __device__ __forceinline__ uint32_t consumed() const { return 32u * (idx - 1) - (uint32_t)nb; }
+    __device__ __forceinline__ uint32_t consumed() const { return 32u * (idx - JS_WIN_DEPTH) - (uint32_t)nb; }
 };
 
 // GENERIC = false: the common case compiled without run-time feature checks (AC decode on, 8-bit

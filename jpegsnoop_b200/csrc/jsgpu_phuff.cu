@@ -86,7 +86,7 @@ __device__ __forceinline__ PhSlots ph_slots(const DevBatch& b, const DevImage& i
 // MODE 0: guess.  MODE 1: fix round 1 (every slot).  MODE 2: fix round r >= 2 — only the slots whose predecessor changed in
 // round r-1, taken from the per-image list that round wrote (dense threads instead of one live lane in a warp here and there).
 template <int MODE>
-__global__ void __launch_bounds__(PH_THREADS) k_ph_sync(DevBatch b, uint32_t round)
+__global__ void __launch_bounds__(PH_THREADS, 5) k_ph_sync(DevBatch b, uint32_t round)
 {
     if (MODE == 2 && b.ph_nchg[round - 1] == 0) return;                    // the previous round changed nothing: settled
     extern __shared__ __align__(16) uint8_t ph_smem[];

@@ -151,41 +151,34 @@ JS_HD unsigned long long ph_run(const PhTabs& t, const uint32_t* words, uint32_t
     if (pos >= lim) return ph_pack(pos, blk, zz);
     PhWin s; s.init(words, pos);
     uint32_t dcoff = t.blk_dc[blk], acoff = t.blk_ac[blk], c = t.blk_c[blk];
+    // ONE symbol per iteration, whatever it is: on the device the 32 lanes of a warp walk 32 different slots, and a loop
+    // nest (block / DC / AC) would leave most of them waiting at every level (measured: 16 of 32 lanes active); with a flat
+    // loop and selects instead of branches they stay together until their slots end.
     while (pos < lim) {
-        if (zz == 0) {                                              // ---- DC symbol of a new block ----
-            s.refill_if_low();
-            uint32_t e = t.lutb[dcoff + (s.hi >> (32 - JS_LUT_BITS))];
-            if (e & 0x8000) e = t.lutb[dcoff + JS_LUT_SIZE + (e & 0x7FFF) + ((s.hi >> 16) & ((1u << JS_LUT2_BITS) - 1))];
-            if (e == 0) { s.consume(1); pos += 1; continue; }
-            const uint32_t len = e >> 8, size = e & 15, run = (e >> 4) & 15;
-            if (COUNT) {
-                if (blk == 0) {
-                    if (o.nmcu == 0) { o.fpos = pos; o.bef0 = o.tot0; o.bef1 = o.tot1; o.bef2 = o.tot2; }
-                    o.nmcu++;
-                }
-                const uint32_t tv = ph_fsl(s.lo, s.hi, len);       // value bits follow the code
-                const uint32_t v = size ? (tv >> (32 - size)) : 0u;
-                int val = (int)v - ((((int)~tv) >> 31) & (int)((1u << size) - 1u));      // T.81 F.12 EXTEND (HuffmanDc2Signed, :859-866)
-                if (t.pshift) val /= (1 << t.pshift);
-                const uint32_t q = t.qz[c * 80 + run];
-                if ((q >> 16) == 0) {                               // the coefficient lands in natural position 0: a DC difference
-                    const int d = (int)(short)(val * (int)(q & 0xFFFF));
-                    if (c == 0) o.tot0 += d; else if (c == 1) o.tot1 += d; else o.tot2 += d;
-                }
+        s.refill_if_low();
+        const bool isdc = (zz == 0);
+        const uint32_t off = isdc ? dcoff : acoff;
+        uint32_t e = t.lutb[off + (s.hi >> (32 - JS_LUT_BITS))];
+        if (e & 0x8000) e = t.lutb[off + JS_LUT_SIZE + (e & 0x7FFF) + ((s.hi >> 16) & ((1u << JS_LUT2_BITS) - 1))];
+        if (e == 0) { s.consume(1); pos += 1; continue; }           // rare (see above)
+        const uint32_t len = e >> 8, size = e & 15, run = (e >> 4) & 15;
+        if (COUNT) {
+            if (isdc && blk == 0) {                                  // an MCU starts here
+                if (o.nmcu == 0) { o.fpos = pos; o.bef0 = o.tot0; o.bef1 = o.tot1; o.bef2 = o.tot2; }
+                o.nmcu++;
             }
-            s.consume(len + size); pos += len + size;
-            zz = 1 + run;
+            const uint32_t tv = ph_fsl(s.lo, s.hi, len);           // value bits follow the code
+            const uint32_t v = size ? (tv >> (32 - size)) : 0u;
+            int val = (int)v - ((((int)~tv) >> 31) & (int)((1u << size) - 1u));      // T.81 F.12 EXTEND (HuffmanDc2Signed, :859-866)
+            if (t.pshift) val /= (1 << t.pshift);
+            const uint32_t q = t.qz[c * 80 + run];
+            // a DC symbol whose coefficient lands in natural position 0 is a DC difference (dequantised, short like the reference's)
+            const int d = (isdc && (q >> 16) == 0) ? (int)(short)(val * (int)(q & 0xFFFF)) : 0;
+            o.tot0 += (c == 0) ? d : 0; o.tot1 += (c == 1) ? d : 0; o.tot2 += (c == 2) ? d : 0;
         }
-        while (zz < 64 && pos < lim) {                              // ---- AC symbols ----
-            s.refill_if_low();
-            uint32_t e = t.lutb[acoff + (s.hi >> (32 - JS_LUT_BITS))];
-            if (e & 0x8000) e = t.lutb[acoff + JS_LUT_SIZE + (e & 0x7FFF) + ((s.hi >> 16) & ((1u << JS_LUT2_BITS) - 1))];
-            if (e == 0) { s.consume(1); pos += 1; continue; }
-            const uint32_t n = (e >> 8) + (e & 15);
-            s.consume(n); pos += n;
-            zz = ((e & 0xFF) == 0) ? 64u : zz + ((e >> 4) & 15) + 1;
-        }
-        if (zz >= 64) {
+        s.consume(len + size); pos += len + size;
+        zz = isdc ? 1 + run : (((e & 0xFF) == 0) ? 64u : zz + run + 1);
+        if (zz >= 64) {                                              // block closed
             zz = 0; blk = (blk + 1 == t.bpm) ? 0u : blk + 1;
             dcoff = t.blk_dc[blk]; acoff = t.blk_ac[blk]; c = t.blk_c[blk];
         }
