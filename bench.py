@@ -40,6 +40,9 @@ CONFIGS = {
     "cfg3shard": (2, 512, "batch=512 per GPU of 3840x2160 4:2:0 baseline, q85, RST interval=8 MCUs (BASELINE configs[2] image-sharded: 4096 images at 8 GPUs)"),
     "cfg4": (3, 512, "batch=512 per GPU (2048 at 4 GPUs), mixed 4:2:0/4:2:2/4:4:4, sizes 1080p/720p/4K, q50..95 and optimised DHT per image, DRI in {MCU row,4,8,16}"),
     "cfg5": (4, 512, "batch=512 3840x2160 4:2:0 baseline, q85, NO restart markers (one serial segment per image)"),
+    # the same images as cfg2 decoded with the reference's DEFAULT build arithmetic (float IDCT, ImgDecode.cpp:2372-2392), verified
+    # against the float-IDCT build of the compiled reference
+    "cfg2float": (1, 1024, "batch=1024 1920x1080 4:2:0 baseline, q85, RST interval=4 MCUs, FLOAT-IDCT arithmetic (the reference's shipping default build)"),
 }
 METRIC = "MPixels/s decoded (bit-exact vs ref)"
 UNIT = "MPix/s"
@@ -58,7 +61,7 @@ def specs_for(cfg, rank, nimg=None):
         seed = 1234 + num * 1000 + g
         if cfg == "cfg1":
             s = dict(width=640, height=480, subsampling="444", quality=85, restart_interval=80, optimize=False)
-        elif cfg == "cfg2":
+        elif cfg in ("cfg2", "cfg2float"):
             s = dict(width=1920, height=1080, subsampling="420", quality=85, restart_interval=4, optimize=False)
         elif cfg == "cfg3shard":
             s = dict(width=3840, height=2160, subsampling="420", quality=85, restart_interval=8, optimize=False)
@@ -120,12 +123,12 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def load_oracle():
-    """The compiled reference (oracle/_ref, integer-IDCT build) when present, else the C port (spot checks only)."""
+def load_oracle(fixed=True):
+    """The compiled reference (oracle/_ref; integer-IDCT build unless fixed=False) when present, else the C port (spot checks only)."""
     from oracle_util import Oracle, ref_available
-    if ref_available("fixed"):
-        return Oracle("ref_fixed"), "reference"
-    return Oracle("port", idct_fixed=True), "port"
+    if ref_available("fixed" if fixed else "float"):
+        return Oracle("ref_fixed" if fixed else "ref_float"), "reference"
+    return Oracle("port", idct_fixed=fixed), "port"
 
 
 def verify_all(bd, jpegs, orc, kind, threads, max_images=None):
@@ -171,7 +174,10 @@ def run_config(cfg, args, env, orc, kind, threads, steps, warmup, verify_budget_
     t0 = time.time()
     jpegs, specs = make_batch(cfg, rank, nimg=args.batch if cfg == args.config else (args.side_batch if cfg != "cfg1" else None))
     t_gen = time.time() - t0
-    bd = BatchDecoder(device=local, huff_kernel=args.huff_kernel, idct_kernel=args.idct_kernel, want_histo=not args.no_histo, want_mcu_map=not args.no_mcu_map)
+    if cfg == "cfg2float":
+        orc, kind = load_oracle(fixed=False)
+    bd = BatchDecoder(device=local, idct_fixedpt=(cfg != "cfg2float"), huff_kernel=args.huff_kernel, idct_kernel=args.idct_kernel,
+                      want_histo=not args.no_histo, want_mcu_map=not args.no_mcu_map)
     tarr, darr, bits = BatchDecoder.prepare(jpegs)
     shared_tables = cfg != "cfg4"
     if world > 1 and shared_tables:      # shared Huffman/quant tables: ONE broadcast of rank 0's table blob over NCCL (NVLink)
@@ -229,6 +235,7 @@ def run_config(cfg, args, env, orc, kind, threads, steps, warmup, verify_budget_
                         "idct+colour": round(idct_ms, 3), "finalize": round(float(stage_ms[3]), 3), "step_total": round(float(stage_ms[4]), 3)},
            "k2_frac_of_hbm_peak": round(alg_b / (idct_ms / 1e3) / 1e9 / peak, 4) if idct_ms > 0 else None,
            "bitstream_bytes_per_padded_px": round(bits.size / float(bd.npadded_pixels), 4),
+           "idct": "float (reference default build)" if cfg == "cfg2float" else "integer (-DIDCT_FIXEDPT build)",
            "bit_exact": bad_all == 0 and checked_all > 0, "bit_exact_checked_images": checked_all, "images_all_ranks": nimg_all,
            "mismatching_images": bad_all, "checked_by": "device checksums of all output buffers vs " + ("oracle/_ref (compiled reference) checksums" if kind == "reference" else "C port, spot check"),
            "decoder_status_words": status, "gpu_launches_per_step": launches, "gen_s": round(t_gen, 1),
@@ -487,7 +494,7 @@ def main():
 
     # ---- the other BASELINE configs ------------------------------------------------------------------------------------
     if args.configs == "auto":
-        side = {1: ["cfg1", "cfg5", "cfg3shard", "cfg4"], 2: ["cfg3shard"], 4: ["cfg3shard", "cfg4"], 8: ["cfg3shard"]}.get(world, ["cfg3shard"])
+        side = {1: ["cfg1", "cfg5", "cfg3shard", "cfg4", "cfg2float"], 2: ["cfg3shard"], 4: ["cfg3shard", "cfg4"], 8: ["cfg3shard"]}.get(world, ["cfg3shard"])
     elif args.configs in ("none", ""):
         side = []
     else:

@@ -621,7 +621,7 @@ int jsgpu_batch_decode(jsgpu_ctx* ctx)
         // fused tile kernel: integer IDCT, standard sampling layouts, decomposable table; everything
         // else (float IDCT, exotic sampling, a libm whose table does not decompose) takes the simple kernels
         const bool fused = (ctx->opt.idct_kernel != 1) && ctx->opt.idct_mode == 0 && ctx->sym_ok && b.ntiles > 0;
-        // idct_kernel: 2 = TMA-staged tile kernel, 0/3 = tile kernel with per-lane vector loads (measured faster, profiles/r1_idct.md)
+        // idct_kernel: 2 = TMA-staged tile kernel, 0/3 = tile kernel with per-lane vector loads (measured faster in round 1; shapes of round 2: profiles/r2_k2_variants.md)
         if (fused && ctx->opt.idct_kernel == 2 && ctx->tmap_ok) launches += js_launch_idct_tma(b, (const IdctSym*)ctx->d_sym.p, (const ColorTabs*)ctx->d_ctab.p, ctx->tmap, ctx->sm_count, s);
         else if (fused) launches += js_launch_idct_fused(b, (const IdctSym*)ctx->d_sym.p, (const ColorTabs*)ctx->d_ctab.p, ctx->sm_count, ctx->tab_mode, s);
         // float IDCT (the reference's default build): fused tile kernel with the float table as immediates, when that table

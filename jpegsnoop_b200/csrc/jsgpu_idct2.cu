@@ -5,7 +5,7 @@
 //     swizzle atom) into a per-warp double buffer, completion on a per-warp mbarrier.  A warp issues
 //     the loads of its NEXT 32-block group before it starts computing the current one, so HBM latency
 //     is hidden behind ~2000 instructions of IDCT + colour work instead of being paid at the top of
-//     every group (the long_scoreboard stall of the LDG version, profiles/r1_idct.md).
+//     every group (the long_scoreboard stall of the LDG version in the first round-1 captures).
 //   * SWIZZLE_128B makes "lane l reads 16-byte chunk c of ITS OWN row" bank-conflict free: physical
 //     chunk = c ^ (l & 7), so the 8 lanes of a quarter-warp hit 8 different bank groups while the
 //     logical chunk index stays warp-uniform (static register allocation in the unrolled MAC loop).

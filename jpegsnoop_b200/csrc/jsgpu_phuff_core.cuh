@@ -94,41 +94,31 @@ JS_HD uint32_t ph_fsl(uint32_t lo, uint32_t hi, uint32_t n)      // high word of
     n &= 31; return n ? ((hi << n) | (lo >> (32 - n))) : hi;
 #endif
 }
+// Position-based window: the four words from the one holding bit `pos` onwards.  A peek is ONE funnel shift (its shift count
+// is taken modulo 32, i.e. pos & 31 for free); moving on costs nothing until the position crosses a word boundary (at most once
+// per symbol: code + value <= 31 bits), then the words shift down and the one three words ahead is requested — ~10 symbols
+// before it is looked at, so the L2 latency of these scattered 4-byte loads stays off the dependency chain.
 struct PhWin {
-    uint32_t hi, lo, nx0, nx1, idx; int nb; const uint32_t* base;
-    // window positioned at absolute bit `bitpos` of the interval; idx stays an absolute word index, so that
-    // pos() is the absolute bit position too.  Two words are kept in flight behind the window: a refill consumes the word
-    // requested two refills (~10 symbols) earlier, so the L2 latency of these scattered 4-byte loads stays off the chain.
+    uint32_t w0, w1, w2, w3; const uint32_t* nextp;          // nextp: address of the word after w3
     JS_HD void init(const uint32_t* words, uint32_t bitpos) {
-        base = words; idx = bitpos >> 5;
-        hi = ph_ldw(base + idx); lo = ph_ldw(base + idx + 1); nx0 = ph_ldw(base + idx + 2); nx1 = ph_ldw(base + idx + 3);
-        idx += 4; nb = 64;
-        consume(bitpos & 31);
+        const uint32_t* p = words + (bitpos >> 5);
+        w0 = ph_ldw(p); w1 = ph_ldw(p + 1); w2 = ph_ldw(p + 2); w3 = ph_ldw(p + 3); nextp = p + 4;
     }
-    JS_HD void refill_if_low() {               // afterwards >= 33 bits are in the window
+    JS_HD uint32_t peek(uint32_t pos) const { return ph_fsl(w1, w0, pos); }                     // 32 bits from `pos` (inside w0)
+    // 32 bits from p2, pos <= p2 <= pos + 31 (value bits behind a code)
+    JS_HD uint32_t peek_at(uint32_t pos, uint32_t p2) const { return ((p2 ^ pos) & ~31u) ? ph_fsl(w2, w1, p2) : ph_fsl(w1, w0, p2); }
+    JS_HD void advance(uint32_t pos, uint32_t npos) {       // npos - pos <= 32
 #if defined(__CUDA_ARCH__)
-        // predicated in-place reload of the look-ahead word: written as a C++ conditional the compiler loads into a temporary
-        // and copies it at the end of the same step, i.e. waits for the very load that is to be hidden (cf. Win in jsgpu_huff.cu)
-        const uint32_t need = (nb <= 32) ? 1u : 0u;
-        if (need) {
-            hi |= __funnelshift_rc(nx0, 0, nb);
-            lo = __funnelshift_rc(0, nx0, nb);
-            nb += 32;
-            nx0 = nx1;
-        }
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.global.nc.u32 %0, [%1];\n\t}" : "+r"(nx1) : "l"(base + idx), "r"(need));
-        idx += need;
+        // predicated in-place reload: written as a C++ conditional the compiler loads into a temporary and copies it at the
+        // end of the same step, i.e. waits for the very load that is to be hidden (cf. Win in jsgpu_huff.cu)
+        const uint32_t cross = ((npos ^ pos) >> 5) ? 1u : 0u;
+        if (cross) { w0 = w1; w1 = w2; w2 = w3; }
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.global.nc.u32 %0, [%1];\n\t}" : "+r"(w3) : "l"(nextp), "r"(cross));
+        nextp += cross;
 #else
-        if (nb <= 32) {
-            hi |= (nb >= 32) ? 0u : (nx0 >> nb);
-            lo = (nb >= 32) ? nx0 : (nx0 << (32 - nb));
-            nb += 32;
-            nx0 = nx1; nx1 = ph_ldw(base + idx); idx++;
-        }
+        if ((npos ^ pos) >> 5) { w0 = w1; w1 = w2; w2 = w3; w3 = ph_ldw(nextp); nextp++; }
 #endif
     }
-    JS_HD void consume(uint32_t n) { hi = ph_fsl(lo, hi, n); lo = (n >= 32) ? 0u : (lo << n); nb -= (int)n; }
-    JS_HD uint32_t pos() const { return 32u * (idx - 2) - (uint32_t)nb; }
 };
 
 // What a fix run learns about its slot.
@@ -155,19 +145,19 @@ JS_HD unsigned long long ph_run(const PhTabs& t, const uint32_t* words, uint32_t
     // nest (block / DC / AC) would leave most of them waiting at every level (measured: 16 of 32 lanes active); with a flat
     // loop and selects instead of branches they stay together until their slots end.
     while (pos < lim) {
-        s.refill_if_low();
+        const uint32_t top = s.peek(pos);
         const bool isdc = (zz == 0);
         const uint32_t off = isdc ? dcoff : acoff;
-        uint32_t e = t.lutb[off + (s.hi >> (32 - JS_LUT_BITS))];
-        if (e & 0x8000) e = t.lutb[off + JS_LUT_SIZE + (e & 0x7FFF) + ((s.hi >> 16) & ((1u << JS_LUT2_BITS) - 1))];
-        if (e == 0) { s.consume(1); pos += 1; continue; }           // rare (see above)
+        uint32_t e = t.lutb[off + (top >> (32 - JS_LUT_BITS))];
+        if (e & 0x8000) e = t.lutb[off + JS_LUT_SIZE + (e & 0x7FFF) + ((top >> 16) & ((1u << JS_LUT2_BITS) - 1))];
+        if (e == 0) { s.advance(pos, pos + 1); pos += 1; continue; }           // rare (see above)
         const uint32_t len = e >> 8, size = e & 15, run = (e >> 4) & 15;
         if (COUNT) {
             if (isdc && blk == 0) {                                  // an MCU starts here
                 if (o.nmcu == 0) { o.fpos = pos; o.bef0 = o.tot0; o.bef1 = o.tot1; o.bef2 = o.tot2; }
                 o.nmcu++;
             }
-            const uint32_t tv = ph_fsl(s.lo, s.hi, len);           // value bits follow the code
+            const uint32_t tv = s.peek_at(pos, pos + len);         // value bits follow the code
             const uint32_t v = size ? (tv >> (32 - size)) : 0u;
             int val = (int)v - ((((int)~tv) >> 31) & (int)((1u << size) - 1u));      // T.81 F.12 EXTEND (HuffmanDc2Signed, :859-866)
             if (t.pshift) val /= (1 << t.pshift);
@@ -176,7 +166,8 @@ JS_HD unsigned long long ph_run(const PhTabs& t, const uint32_t* words, uint32_t
             const int d = (isdc && (q >> 16) == 0) ? (int)(short)(val * (int)(q & 0xFFFF)) : 0;
             o.tot0 += (c == 0) ? d : 0; o.tot1 += (c == 1) ? d : 0; o.tot2 += (c == 2) ? d : 0;
         }
-        s.consume(len + size); pos += len + size;
+        const uint32_t npos = pos + len + size;
+        s.advance(pos, npos); pos = npos;
         zz = isdc ? 1 + run : (((e & 0xFF) == 0) ? 64u : zz + run + 1);
         if (zz >= 64) {                                              // block closed
             zz = 0; blk = (blk + 1 == t.bpm) ? 0u : blk + 1;

@@ -273,6 +273,19 @@ def test_random_corpus_matches_oracle(built):
             assert not bad, f"{name} (huff_kernel={huff}): mismatch in {bad}"
 
 
+@pytest.mark.parametrize("tab", [0, 1, 2], ids=["table_in_smem", "table_in_constant_bank", "table_as_immediates"])
+def test_idct_table_sources_match_oracle(built, cases, tab, monkeypatch):
+    """The three sources of the quadrant IDCT table in the fused kernel (JSGPU_IDCT_TABLE: what runs when the host libm's table
+    differs from the build box's, and the default immediates) produce the same pixels."""
+    from jpegsnoop_b200 import BatchDecoder
+    monkeypatch.setenv("JSGPU_IDCT_TABLE", str(tab))
+    orc = _oracle(True)
+    bd = BatchDecoder(huff_kernel=0, idct_kernel=3)
+    bd.set_batch([j for _, j in cases]); bd.decode(); bd.sync()
+    for i, (name, j) in enumerate(cases):
+        assert not JC.compare(orc.decode(j), bd.fetch(i), what=("pix_y", "pix_cb", "pix_cr", "dib")), (name, tab)
+
+
 def test_host_marker_walk_equals_device_marker_scan(built, cases):
     from jpegsnoop_b200 import BatchDecoder
     jpegs = [j for _, j in cases]
