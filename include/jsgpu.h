@@ -261,6 +261,56 @@ int jsgpu_batch_errors(jsgpu_ctx* ctx, uint32_t image, jsgpu_scan_errors* out);
 #define JSGPU_CK_WORDS 12
 int jsgpu_batch_checksums(jsgpu_ctx* ctx, uint64_t* ck, uint32_t n);
 
+/* --- channel preview, colour statistics and histograms -------------------------------------------
+ * CimgDecode::CalcChannelPreviewFull (ImgDecode.cpp:4619-4821) beyond its default: the clipping/histogram colour
+ * conversion ConvertYCCtoRGB/CapYccRange/CapRgbRange (:4229-4601) taken when CSnoopConfig::bHistoEn or bStatClipEn is set,
+ * the channel selection ChannelExtract (:4832-4876) and the YCC level shift from a given MCU on (SetPreviewYccOffset,
+ * :650-659).  With the defaults (all zero, mode 1) jsgpu_batch_decode's fused kernel has produced exactly this already. */
+typedef struct {
+    int32_t hist_en;        /* m_bHistEn  (ImgDecode.cpp:2740)                                                        */
+    int32_t statclip_en;    /* m_bStatClipEn (:2741); either one selects ConvertYCCtoRGB instead of ...FastFloat (:4745) */
+    int32_t mode;           /* m_nPreviewMode: 1 RGB, 2 YCC, 3 R, 4 G, 5 B, 6 Y, 7 Cb, 8 Cr (snoop.h:100-108); 0 = 1 */
+    int32_t shift_y, shift_cb, shift_cr;          /* m_nPreviewShiftY/Cb/Cr                                            */
+    uint32_t shift_mcu_x, shift_mcu_y;            /* m_nPreviewShiftMcuX/Y: applied to MCUs at or after this one (:4735) */
+    uint32_t ycc_warn_budget;                     /* YCC_CLIP_REPORT_MAX - m_nWarnYccClipNum (ImgDecode.h:50): how many
+                                                     "YCC Clipped" notes may still be issued (and counted, :4372-4378)  */
+    uint32_t pad;
+} jsgpu_preview;
+#define JSGPU_CC_HISTO_BINS  128    /* HISTO_BINS (ImgDecode.h:157)      */
+#define JSGPU_Y_HISTO_BINS   2048   /* FULL_HISTO_BINS (ImgDecode.h:162) */
+#define JSGPU_MAX_YCC_WARN   10     /* YCC_CLIP_REPORT_MAX               */
+/* channel order of the range arrays: 0-2 pre-ranged Y,Cb,Cr (nPreclipY.. of PixelCcHisto, ImgDecode.h:236-280), 3-5 ranged
+ * Y,Cb,Cr before the clip (nClipY..), 6-8 R,G,B before the clip (nPreclipR..), 9-11 R,G,B after it (nClipR..).
+ * min/max start at 0 like the reference's memset (ImgDecode.cpp:3147); sums are 64-bit here, the reference's are `int`
+ * (the caller truncates).  clip[]: nClipYUnder, YOver, CbUnder, CbOver, CrUnder, CrOver (counted only while notes are issued:
+ * at most ycc_warn_budget in total), RUnder, ROver, GUnder, GOver, BUnder, BOver. */
+typedef struct { uint32_t mcu_x, mcu_y; int32_t y, cb, cr; uint32_t kind; } jsgpu_ycc_warn;   /* kind: index into clip[0..5] */
+typedef struct {
+    uint32_t cc_histo[3][JSGPU_CC_HISTO_BINS];    /* m_anCcHisto_r/g/b                                                 */
+    uint32_t y_histo[JSGPU_Y_HISTO_BINS];         /* m_anHistoYFull                                                    */
+    int32_t  vmin[12], vmax[12];
+    int64_t  vsum[12];
+    uint64_t count;                               /* m_sHisto.nCount                                                   */
+    uint32_t clip[12];
+    uint32_t nwarn, pad;
+    jsgpu_ycc_warn warn[JSGPU_MAX_YCC_WARN];      /* the notes, in the reference's (raster, Y/Cb/Cr) order             */
+} jsgpu_colour_stats;
+/* Recompute the DIB (and stats[] SUMY/AVGY) of every image of the current batch from its pixel maps with `p`; the statistics
+ * of this pass are kept for jsgpu_batch_colour_stats.  jsgpu_set_preview makes jsgpu_batch_decode do so itself whenever the
+ * settings differ from the defaults. */
+int jsgpu_set_preview(jsgpu_ctx* ctx, const jsgpu_preview* p);
+int jsgpu_batch_preview(jsgpu_ctx* ctx, const jsgpu_preview* p);
+int jsgpu_batch_colour_stats(jsgpu_ctx* ctx, uint32_t image, jsgpu_colour_stats* out);
+
+/* --- Export-to-TIFF consumer ---------------------------------------------------------------------------
+ * The three-samples-per-pixel, top-down array CJPEGsnoopDoc::OnToolsExporttiff (JPEGsnoopDoc.cpp:2061-2180) hands to
+ * FileTiff::WriteFile, packed on the device from image `image` of the current batch and copied to host_out
+ * (img_x * img_y * 3 bytes, 6 for RGB16).  YCC8 needs a three-component scan (the reference reads all three pixel maps). */
+#define JSGPU_EXPORT_RGB8  0   /* the DIB's R,G,B                                    (JPEGsnoopDoc.cpp:2108-2124) */
+#define JSGPU_EXPORT_RGB16 1   /* ... as 16-bit samples value << 8, big-endian       (:2125-2130)                 */
+#define JSGPU_EXPORT_YCC8  2   /* pixel maps clipped to -1024..1023, (0x400 + v) >> 3 (:2133-2170)                 */
+int jsgpu_batch_export(jsgpu_ctx* ctx, uint32_t image, int mode, void* host_out, uint64_t bytes);
+
 /* One-call end-to-end form: host bitstream in, host outputs out (any pointer may be NULL to
  * skip that output).  Output buffers hold the images back to back in batch order using the
  * element offsets of jsgpu_batch_layout.  Small batches run H2D, decode and D2H on the context

@@ -19,6 +19,8 @@ jsimg* jsimg_create(void);
 void   jsimg_destroy(jsimg*);
 /* config (CSnoopConfig fields read at ImgDecode.cpp:2730-2741 + device knobs) */
 void   jsimg_config(jsimg*, int decode_ac, int idct_fixedpt, int cuda_device, int huff_kernel, int idct_kernel, int device_markers);
+/* CSnoopConfig::bHistoEn / bStatClipEn / bDumpHistoY (SnoopConfig.cpp:76-82), read at ImgDecode.cpp:2730-2741 */
+void   jsimg_config_histo(jsimg*, int histo_en, int statclip_en, int dump_histo_y);
 /* byte source: CwindowBuf::BufFileSet equivalent on a memory buffer (caller keeps it alive) */
 void   jsimg_set_file(jsimg*, const uint8_t* data, uint64_t n);
 int    jsimg_overlay_install(jsimg*, uint32_t start, const uint8_t* data, uint32_t n);
@@ -52,6 +54,19 @@ void   jsimg_GetStats(jsimg*, int32_t* out12);   /* avgY, avgValid, brightY,Cb,C
 void   jsimg_GetIdctTables(jsimg*, float* lf /*[64*64]*/, int32_t* li /*[64*64]*/);
 void   jsimg_GetStageMs(jsimg*, float* ms5);
 unsigned jsimg_GetScanStatus(jsimg*);
+/* channel preview and colour statistics (ImgDecode.h:304-312; ImgDecode.cpp:631-677, 3764-4012) */
+void   jsimg_SetPreviewMode(jsimg*, unsigned nMode);
+unsigned jsimg_GetPreviewMode(jsimg*);
+void   jsimg_SetPreviewYccOffset(jsimg*, unsigned nMcuX, unsigned nMcuY, int nY, int nCb, int nCr);
+void   jsimg_GetPreviewYccOffset(jsimg*, unsigned* nMcuX, unsigned* nMcuY, int* nY, int* nCb, int* nCr);
+void   jsimg_GetStatClip(jsimg*, uint32_t* out12);                 /* m_sStatClip: Y/Cb/Cr/R/G/B x under, over     */
+void   jsimg_GetHistoRanges(jsimg*, int32_t* out36, uint32_t* nCount);   /* m_sHisto in PixelCcHisto's member order */
+void   jsimg_GetCcHisto(jsimg*, unsigned nChan, uint32_t* out128); /* m_anCcHisto_r/g/b                            */
+void   jsimg_GetHistoYFull(jsimg*, uint32_t* out2048);             /* m_anHistoYFull                               */
+const uint8_t* jsimg_GetHistoDib(jsimg*, int which /*0 RGB (128x90), 1 Y (512x30)*/, int* ready);   /* m_pDibHistRgb / m_pDibHistY */
+
+/* Export-to-TIFF (CJPEGsnoopDoc::OnToolsExporttiff + FileTiff::WriteFile): mode 0 RGB8, 1 RGB16, 2 YCC8; 1 on success */
+int    jsimg_ExportTiff(jsimg*, const char* path, unsigned mode);
 
 /* log access (error convention: failures are log lines, ImgDecode.cpp:2755-2758 etc.) */
 int    jsimg_log_count(jsimg*, int kind /*0 line,1 hdr,2 warn,3 err,4 good,-1 all*/);

@@ -65,6 +65,23 @@ class jsgpu_host_outputs(C.Structure):
                                           "mcu_map", "dht_histo", "stats")]
 
 
+class jsgpu_preview(C.Structure):
+    """include/jsgpu.h: CalcChannelPreviewFull settings (histogram/clip conversion, preview mode, YCC shift)."""
+    _fields_ = [("hist_en", C.c_int32), ("statclip_en", C.c_int32), ("mode", C.c_int32),
+                ("shift_y", C.c_int32), ("shift_cb", C.c_int32), ("shift_cr", C.c_int32),
+                ("shift_mcu_x", C.c_uint32), ("shift_mcu_y", C.c_uint32), ("ycc_warn_budget", C.c_uint32), ("pad", C.c_uint32)]
+
+
+class jsgpu_ycc_warn(C.Structure):
+    _fields_ = [("mcu_x", C.c_uint32), ("mcu_y", C.c_uint32), ("y", C.c_int32), ("cb", C.c_int32), ("cr", C.c_int32), ("kind", C.c_uint32)]
+
+
+class jsgpu_colour_stats(C.Structure):
+    _fields_ = [("cc_histo", (C.c_uint32 * 128) * 3), ("y_histo", C.c_uint32 * 2048),
+                ("vmin", C.c_int32 * 12), ("vmax", C.c_int32 * 12), ("vsum", C.c_int64 * 12), ("count", C.c_uint64),
+                ("clip", C.c_uint32 * 12), ("nwarn", C.c_uint32), ("pad", C.c_uint32), ("warn", jsgpu_ycc_warn * 10)]
+
+
 OUT_PIX_Y, OUT_PIX_CB, OUT_PIX_CR, OUT_DIB, OUT_BLK_Y, OUT_BLK_CB, OUT_BLK_CR, OUT_MCU_MAP, OUT_HISTO, OUT_STATS = range(10)
 
 # every symbol include/jsgpu.h and include/jsimg.h declare (tests check they are all exported)
@@ -73,7 +90,7 @@ JSGPU_SYMBOLS = [
     "jsgpu_set_idct_tables", "jsgpu_set_options", "jsgpu_get_options", "jsgpu_upload_tables", "jsgpu_bcast_tables",
     "jsgpu_batch_begin", "jsgpu_batch_layout", "jsgpu_batch_pools", "jsgpu_batch_upload", "jsgpu_batch_decode",
     "jsgpu_batch_download", "jsgpu_batch_stage_ms", "jsgpu_timer_start", "jsgpu_timer_stop", "jsgpu_batch_launches", "jsgpu_batch_selfsync_info", "jsgpu_batch_checksums", "jsgpu_batch_errors", "jsgpu_decode_batch_host",
-    "jsgpu_host_alloc", "jsgpu_host_free", "jsgpu_host_copy_rate"]
+    "jsgpu_host_alloc", "jsgpu_host_free", "jsgpu_host_copy_rate", "jsgpu_set_preview", "jsgpu_batch_preview", "jsgpu_batch_colour_stats", "jsgpu_batch_export"]
 JSIMG_SYMBOLS = [
     "jsimg_create", "jsimg_destroy", "jsimg_config", "jsimg_set_file", "jsimg_overlay_install", "jsimg_overlay_remove_all", "jsimg_Reset", "jsimg_ResetState",
     "jsimg_SetDqtEntry", "jsimg_SetDqtTables", "jsimg_GetDqtEntry", "jsimg_SetDhtTables", "jsimg_SetDhtEntry",
@@ -81,7 +98,9 @@ JSIMG_SYMBOLS = [
     "jsimg_DecodeScanImg", "jsimg_IsPreviewReady", "jsimg_GetImageSize", "jsimg_GetPixMapPtrs", "jsimg_GetBitmapPtr",
     "jsimg_LookupFilePosMcu", "jsimg_LookupFilePosPix", "jsimg_LookupBlkYCC", "jsimg_GetMcuFileMap", "jsimg_GetBlkDcMap",
     "jsimg_GetDhtHisto", "jsimg_GetGeometry", "jsimg_GetStats", "jsimg_GetIdctTables", "jsimg_GetStageMs", "jsimg_GetScanStatus",
-    "jsimg_log_count", "jsimg_log_line", "jsimg_log_clear", "jsimg_walk_jpeg", "jsimg_decode_jpeg", "jsimg_parse_jpeg"]
+    "jsimg_log_count", "jsimg_log_line", "jsimg_log_clear", "jsimg_walk_jpeg", "jsimg_decode_jpeg", "jsimg_parse_jpeg",
+    "jsimg_config_histo", "jsimg_SetPreviewMode", "jsimg_GetPreviewMode", "jsimg_SetPreviewYccOffset", "jsimg_GetPreviewYccOffset",
+    "jsimg_GetStatClip", "jsimg_GetHistoRanges", "jsimg_GetCcHisto", "jsimg_GetHistoYFull", "jsimg_GetHistoDib", "jsimg_ExportTiff"]
 
 _lib = None
 
@@ -124,6 +143,21 @@ def load():
     L.jsgpu_host_alloc.argtypes = [u64]; L.jsgpu_host_alloc.restype = vp
     L.jsgpu_host_free.argtypes = [vp]; L.jsgpu_host_free.restype = None
     L.jsgpu_host_copy_rate.argtypes = [vp, i32, u64, i32, C.POINTER(C.c_float)]
+    L.jsgpu_set_preview.argtypes = [vp, C.POINTER(jsgpu_preview)]
+    L.jsgpu_batch_preview.argtypes = [vp, C.POINTER(jsgpu_preview)]
+    L.jsgpu_batch_colour_stats.argtypes = [vp, u32, C.POINTER(jsgpu_colour_stats)]
+    L.jsgpu_batch_export.argtypes = [vp, u32, i32, vp, u64]
+    L.jsimg_ExportTiff.argtypes = [vp, C.c_char_p, u32]
+    L.jsimg_config_histo.argtypes = [vp, i32, i32, i32]; L.jsimg_config_histo.restype = None
+    L.jsimg_SetPreviewMode.argtypes = [vp, u32]; L.jsimg_SetPreviewMode.restype = None
+    L.jsimg_GetPreviewMode.argtypes = [vp]; L.jsimg_GetPreviewMode.restype = u32
+    L.jsimg_SetPreviewYccOffset.argtypes = [vp, u32, u32, i32, i32, i32]; L.jsimg_SetPreviewYccOffset.restype = None
+    L.jsimg_GetPreviewYccOffset.argtypes = [vp] + [C.POINTER(u32)] * 2 + [C.POINTER(i32)] * 3; L.jsimg_GetPreviewYccOffset.restype = None
+    L.jsimg_GetStatClip.argtypes = [vp, vp]; L.jsimg_GetStatClip.restype = None
+    L.jsimg_GetHistoRanges.argtypes = [vp, vp, C.POINTER(u32)]; L.jsimg_GetHistoRanges.restype = None
+    L.jsimg_GetCcHisto.argtypes = [vp, u32, vp]; L.jsimg_GetCcHisto.restype = None
+    L.jsimg_GetHistoYFull.argtypes = [vp, vp]; L.jsimg_GetHistoYFull.restype = None
+    L.jsimg_GetHistoDib.argtypes = [vp, i32, C.POINTER(i32)]; L.jsimg_GetHistoDib.restype = vp
     L.jsimg_create.restype = vp
     L.jsimg_destroy.argtypes = [vp]; L.jsimg_destroy.restype = None
     L.jsimg_config.argtypes = [vp] + [i32] * 6; L.jsimg_config.restype = None

@@ -2,6 +2,7 @@
 // numbers refer to /root/reference/source/ImgDecode.cpp.  Only table keeping, validation,
 // byte shipping and result hosting happen here; all decoding is on the device (jsgpu_*).
 #include "ImgDecode.h"
+#include "FileTiff.h"
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -59,6 +60,14 @@ CimgDecode::CimgDecode(CDocLog* pLog, CwindowBuf* pWBuf, CSnoopConfig* pConfig)
     m_nMcuWidth = m_nMcuHeight = 1;          // ref :189-191 (avoid divide-by-zero before the first decode)
     m_nRestartRead = 0;
     for (float& v : m_afStageMs) v = 0.f;
+    m_bHistEn = m_bStatClipEn = false;
+    m_nPreviewMode = 1;                      // PREVIEW_RGB (ref :220)
+    m_nPreviewShiftY = m_nPreviewShiftCb = m_nPreviewShiftCr = 0; m_nPreviewShiftMcuX = m_nPreviewShiftMcuY = 0;   // ref :226
+    m_nWarnYccClipNum = 0; m_nEndPos = m_nEndAlign = 0; m_bDecodedOnDevice = false;
+    m_bDibHistRgbReady = m_bDibHistYReady = false;
+    memset(m_anStatClip, 0, sizeof m_anStatClip); memset(m_anHistoMin, 0, sizeof m_anHistoMin); memset(m_anHistoMax, 0, sizeof m_anHistoMax);
+    memset(m_anHistoSum, 0, sizeof m_anHistoSum); m_nHistoCount = 0;
+    memset(m_anCcHisto, 0, sizeof m_anCcHisto); memset(m_anHistoYFull, 0, sizeof m_anHistoYFull);
     Reset();
     PrecalcIdct();
     ResetState();
@@ -90,7 +99,9 @@ void CimgDecode::Reset()
     m_bDibTempReady = false;
     m_bScanBad = false; m_nScanStatus = 0;
     FreeOutputs();
+    m_bDecodedOnDevice = false;
     if (!m_bScanErrorsDisable) m_nWarnBadScanNum = 0;
+    m_nWarnYccClipNum = 0;                   // ref :130
 }
 
 // ref :286-306, 343-360, 373-406
@@ -264,6 +275,8 @@ bool CimgDecode::EnsureDevice()
 void CimgDecode::DecodeScanImg(unsigned nStart, bool bDisplay, bool bQuiet)
 {
     bool bDecodeScanAc = bDisplay ? m_pAppConfig->bDecodeScanImgAc : false;        // ref :2735-2739
+    const bool bDumpHistoY = m_pAppConfig->bDumpHistoY;                            // ref :2730
+    m_bHistEn = m_pAppConfig->bHistoEn; m_bStatClipEn = m_pAppConfig->bStatClipEn; // ref :2740-2741
     Reset();
     m_nScanErrMax = m_pAppConfig->nErrMaxDecodeScan;
     m_bDecodeScanAc = bDecodeScanAc;
@@ -319,6 +332,12 @@ void CimgDecode::DecodeScanImg(unsigned nStart, bool bDisplay, bool bQuiet)
         m_pLog->AddLine(JS_LOGSTR(""));
     }
 
+    if (bDisplay) {                                                                // ref :3144-3156
+        memset(m_anStatClip, 0, sizeof m_anStatClip); memset(m_anHistoMin, 0, sizeof m_anHistoMin); memset(m_anHistoMax, 0, sizeof m_anHistoMax);
+        memset(m_anHistoSum, 0, sizeof m_anHistoSum); m_nHistoCount = 0;
+        memset(m_anCcHisto, 0, sizeof m_anCcHisto); memset(m_anHistoYFull, 0, sizeof m_anHistoYFull);
+    }
+
     // ---- device decode (replaces HOT LOOPS 1-4, ref :3164-3630 and :4619-4821) -----------------
     if (!EnsureDevice()) { m_bScanBad = true; return; }
     jsgpu_options opt; jsgpu_get_options(m_pGpu, &opt);
@@ -329,6 +348,12 @@ void CimgDecode::DecodeScanImg(unsigned nStart, bool bDisplay, bool bQuiet)
     opt.want_histo = 1; opt.want_mcu_map = 1;
     opt.scan_err_max = (int32_t)m_nScanErrMax;
     jsgpu_set_options(m_pGpu, &opt);
+    // CalcChannelPreview() at the end of the decode (ref :3641-3643) with this object's preview settings: the device takes the
+    // extra colour pass inside jsgpu_batch_decode only when they differ from the defaults
+    jsgpu_preview pv; PreviewSettings(pv);
+    if (!bDisplay) { memset(&pv, 0, sizeof pv); pv.mode = 1; }
+    jsgpu_set_preview(m_pGpu, &pv);
+    const bool bPreviewPass = pv.hist_en || pv.statclip_en || pv.mode != 1 || pv.shift_y || pv.shift_cb || pv.shift_cr;
 
     jsgpu_tables* pTables = new jsgpu_tables;
     ExportTables(*pTables);
@@ -353,6 +378,7 @@ void CimgDecode::DecodeScanImg(unsigned nStart, bool bDisplay, bool bQuiet)
         m_bScanBad = true;
         return;
     }
+    m_bDecodedOnDevice = true;
     jsgpu_batch_stage_ms(m_pGpu, m_afStageMs);
     jsgpu_batch_download(m_pGpu, JSGPU_OUT_MCU_MAP, 0, m_pMcuFileMap, nMcu * 4);
     jsgpu_batch_download(m_pGpu, JSGPU_OUT_BLK_Y, 0, m_pBlkDcValY, nBlk * 2);
@@ -441,8 +467,10 @@ void CimgDecode::DecodeScanImg(unsigned nStart, bool bDisplay, bool bQuiet)
         }
     }
     const unsigned nEndPos = (unsigned)st[JSGPU_STAT_END_POS], nEndAlign = (unsigned)st[JSGPU_STAT_END_ALIGN];
+    m_nEndPos = nEndPos; m_nEndAlign = nEndAlign;
+    if (!bQuiet) m_pLog->AddLine(JS_LOGSTR(""));                                    // ref :3630-3632
+    if (bDisplay && bPreviewPass) FetchPreviewResults();                           // what CalcChannelPreview left behind (ref :3641-3643)
     if (!bQuiet) {
-        m_pLog->AddLine(JS_LOGSTR(""));
         // ref :3655-3668 compression statistics: bits of scan data consumed up to where the accumulator stands
         m_pLog->AddLine(JS_LOGSTR("  Compression stats:"));
         const float fRatio = (float)(m_nDimX * m_nDimY * m_nNumSosComps * 8) / (float)((nEndPos - nStart) * 8);
@@ -462,19 +490,9 @@ void CimgDecode::DecodeScanImg(unsigned nStart, bool bDisplay, bool bQuiet)
                                                    (m_anDhtHisto[nClass][nDestId][nLen] * 100.0) / nTotal)));
                 m_pLog->AddLine(JS_LOGSTR(""));
             }
-        // ref :3764-3837 ReportColorStats with the clip/histogram statistics off (bHistoEn = bStatClipEn = false: the colour
-        // pass is ConvertYCCtoRGBFastFloat, which counts nothing, :4753-4758)
-        m_pLog->AddLine(JS_LOGSTR("  YCC clipping in DC:"));
-        m_pLog->AddLine(JS_LOGSTR(fmt("    Y  component: [<0=%5u] [>255=%5u]", 0u, 0u)));
-        m_pLog->AddLine(JS_LOGSTR(fmt("    Cb component: [<0=%5u] [>255=%5u]", 0u, 0u)));
-        m_pLog->AddLine(JS_LOGSTR(fmt("    Cr component: [<0=%5u] [>255=%5u]", 0u, 0u)));
-        m_pLog->AddLine(JS_LOGSTR(""));
-        m_pLog->AddLine(JS_LOGSTR("  RGB clipping in DC:"));
-        m_pLog->AddLine(JS_LOGSTR(fmt("    R  component: [<0=%5u] [>255=%5u]", 0u, 0u)));
-        m_pLog->AddLine(JS_LOGSTR(fmt("    G  component: [<0=%5u] [>255=%5u]", 0u, 0u)));
-        m_pLog->AddLine(JS_LOGSTR(fmt("    B  component: [<0=%5u] [>255=%5u]", 0u, 0u)));
-        m_pLog->AddLine(JS_LOGSTR(""));
+        ReportColorStats();                                      // ref :3692-3693
     }
+    if (bDisplay && m_bHistEn) DrawHistogram(bQuiet, bDumpHistoY);  // ref :3700-3703
     if (bDisplay && m_bAvgYValid) {                              // ref :3702-3708 (also in quiet mode)
         m_pLog->AddLine(JS_LOGSTR("  Average Pixel Luminance (Y):"));
         m_pLog->AddLine(JS_LOGSTR(fmt("    Y=[%3u] (range: 0..255)", (unsigned)m_nAvgY)));
@@ -490,6 +508,187 @@ void CimgDecode::DecodeScanImg(unsigned nStart, bool bDisplay, bool bQuiet)
         m_pLog->AddLine(JS_LOGSTR(fmt("    Number of RESTART markers decoded: %u", m_nRestartRead)));
         m_pLog->AddLine(JS_LOGSTR(fmt("    Next position in scan buffer: Offset 0x%08X.%u", nEndPos, nEndAlign)));
         m_pLog->AddLine(JS_LOGSTR(""));
+    }
+    if (bDisplay && m_bHistEn && bDumpHistoY) ReportHistogramY();   // ref :3740-3742
+}
+
+// ---- channel preview, colour statistics, histograms --------------------------------------------------
+void CimgDecode::PreviewSettings(jsgpu_preview& pv) const
+{
+    memset(&pv, 0, sizeof pv);
+    pv.hist_en = m_bHistEn ? 1 : 0; pv.statclip_en = m_bStatClipEn ? 1 : 0;
+    pv.mode = (int32_t)m_nPreviewMode;
+    if (pv.mode < 1 || pv.mode > 8) pv.mode = 1;                    // ChannelExtract's final else (ref :4869-4873); PREVIEW_NONE too
+    pv.shift_y = m_nPreviewShiftY; pv.shift_cb = m_nPreviewShiftCb; pv.shift_cr = m_nPreviewShiftCr;
+    pv.shift_mcu_x = m_nPreviewShiftMcuX; pv.shift_mcu_y = m_nPreviewShiftMcuY;
+    pv.ycc_warn_budget = m_nWarnYccClipNum < JSGPU_MAX_YCC_WARN ? JSGPU_MAX_YCC_WARN - m_nWarnYccClipNum : 0;
+}
+
+void CimgDecode::SetPreviewMode(unsigned nMode) { m_nPreviewMode = nMode; CalcChannelPreview(); }             // ref :631-639
+void CimgDecode::SetPreviewYccOffset(unsigned nMcuX, unsigned nMcuY, int nY, int nCb, int nCr)                  // ref :650-659
+{
+    m_nPreviewShiftY = nY; m_nPreviewShiftCb = nCb; m_nPreviewShiftCr = nCr;
+    m_nPreviewShiftMcuX = nMcuX; m_nPreviewShiftMcuY = nMcuY;
+    CalcChannelPreview();
+}
+void CimgDecode::GetPreviewYccOffset(unsigned& nMcuX, unsigned& nMcuY, int& nY, int& nCb, int& nCr)
+{
+    nY = m_nPreviewShiftY; nCb = m_nPreviewShiftCb; nCr = m_nPreviewShiftCr; nMcuX = m_nPreviewShiftMcuX; nMcuY = m_nPreviewShiftMcuY;
+}
+
+// ref :4967-4990.  No DIB, nothing to do (as there); otherwise the device recomputes it from the pixel maps it still holds.
+void CimgDecode::CalcChannelPreview()
+{
+    if (!m_pDibBits || !m_pGpu || !m_bDecodedOnDevice) return;
+    jsgpu_preview pv; PreviewSettings(pv);
+    int r = jsgpu_batch_preview(m_pGpu, &pv);
+    if (r != JSGPU_OK) {
+        m_pLog->AddLineErr(JS_LOGSTR(fmt("*** ERROR: GPU channel preview failed: %s (%s) ***", jsgpu_strerror(r), jsgpu_last_error(m_pGpu))));
+        return;
+    }
+    FetchPreviewResults();
+}
+
+void CimgDecode::FetchPreviewResults()
+{
+    const size_t nPix = (size_t)m_nImgSizeX * m_nImgSizeY;
+    jsgpu_batch_download(m_pGpu, JSGPU_OUT_DIB, 0, m_pDibBits, nPix * 4);
+    int32_t st[JSGPU_STAT_WORDS]; memset(st, 0, sizeof st);
+    jsgpu_batch_download(m_pGpu, JSGPU_OUT_STATS, 0, st, sizeof st);
+    m_nAvgY = st[JSGPU_STAT_AVGY]; m_bAvgYValid = true;             // ref :4813-4819; the brightest pixel does not depend on the settings
+    m_bBrightValid = true;
+    jsgpu_colour_stats* cs = new jsgpu_colour_stats;
+    if (jsgpu_batch_colour_stats(m_pGpu, 0, cs) == JSGPU_OK) {
+        // CalcChannelPreviewFull does not clear the statistics (only DecodeScanImg does, ref :3144-3156): every pass adds to them
+        for (unsigned k = 0; k < 12; k++) {
+            m_anStatClip[k] += cs->clip[k];
+            if (cs->vmin[k] < m_anHistoMin[k]) m_anHistoMin[k] = cs->vmin[k];
+            if (cs->vmax[k] > m_anHistoMax[k]) m_anHistoMax[k] = cs->vmax[k];
+            m_anHistoSum[k] = (int)((unsigned)m_anHistoSum[k] + (unsigned)(unsigned long long)cs->vsum[k]);     // the reference's sums are `int`
+        }
+        m_nHistoCount += (unsigned)cs->count;
+        for (unsigned c = 0; c < 3; c++) for (unsigned i = 0; i < JSGPU_CC_HISTO_BINS; i++) m_anCcHisto[c][i] += cs->cc_histo[c][i];
+        for (unsigned i = 0; i < JSGPU_Y_HISTO_BINS; i++) m_anHistoYFull[i] += cs->y_histo[i];
+        // CapYccRange's notes (ref :4366-4466)
+        static const char* const kKind[6] = { "Y Underflow", "Y Overflow", "Cb Underflow", "Cb Overflow", "Cr Underflow", "Cr Overflow" };
+        for (unsigned i = 0; i < cs->nwarn && i < JSGPU_MAX_YCC_WARN; i++) {
+            const jsgpu_ycc_warn& w = cs->warn[i];
+            m_pLog->AddLineWarn(JS_LOGSTR(fmt("*** NOTE: YCC Clipped. MCU=(%4u,%4u) YCC=(%5d,%5d,%5d) %s @ Offset 0x%08X.%u",
+                                              w.mcu_x, w.mcu_y, w.y, w.cb, w.cr, kKind[w.kind < 6 ? w.kind : 0], m_nEndPos, m_nEndAlign)));
+            m_nWarnYccClipNum++;
+            if (m_nWarnYccClipNum == JSGPU_MAX_YCC_WARN)
+                m_pLog->AddLineWarn(JS_LOGSTR(fmt("    Only reported first %u instances of this message...", (unsigned)JSGPU_MAX_YCC_WARN)));
+        }
+    }
+    delete cs;
+}
+
+// The reference builds the array from the DIB it displays (whatever the preview mode shows) or from the pixel maps (:2098-2170).
+bool CimgDecode::ExportTiffData(unsigned nMode, std::vector<unsigned char>& data)
+{
+    if (nMode > 2 || !m_pDibBits || !m_pGpu || !m_bDecodedOnDevice) return false;
+    if (nMode == 2 && m_nNumSosComps != NUM_CHAN_YCC) return false;           // the reference dereferences all three pixel maps
+    data.assign((size_t)m_nImgSizeX * m_nImgSizeY * (nMode == 1 ? 6 : 3), 0);
+    const int r = jsgpu_batch_export(m_pGpu, 0, (int)nMode, data.data(), data.size());
+    if (r != JSGPU_OK) { m_pLog->AddLineErr(JS_LOGSTR(fmt("*** ERROR: GPU export failed: %s (%s) ***", jsgpu_strerror(r), jsgpu_last_error(m_pGpu)))); return false; }
+    return true;
+}
+bool CimgDecode::ExportTiff(const char* szFnameOut, unsigned nMode)
+{
+    std::vector<unsigned char> data;
+    if (!szFnameOut || !ExportTiffData(nMode, data)) return false;
+    FileTiff myTiff;
+    return myTiff.WriteFile(szFnameOut, nMode == 2, nMode == 1, data.data(), m_nImgSizeX, m_nImgSizeY);
+}
+
+void CimgDecode::GetHistoRanges(int out[36], unsigned& nCount) const
+{
+    // PixelCcHisto's order (ImgDecode.h:236-280): pre-ranged YCC, ranged YCC, CLIPPED RGB, pre-clip RGB
+    static const int kOrder[12] = { 0, 1, 2, 3, 4, 5, 9, 10, 11, 6, 7, 8 };
+    for (int k = 0; k < 12; k++) { out[k * 3] = m_anHistoMin[kOrder[k]]; out[k * 3 + 1] = m_anHistoMax[kOrder[k]]; out[k * 3 + 2] = m_anHistoSum[kOrder[k]]; }
+    nCount = m_nHistoCount;
+}
+
+// ref :3764-3837
+void CimgDecode::ReportColorStats()
+{
+    static const char* const kYcc[3] = { "Y ", "Cb", "Cr" };
+    static const char* const kRgb[3] = { "R ", "G ", "B " };
+    m_pLog->AddLine(JS_LOGSTR("  YCC clipping in DC:"));
+    for (unsigned c = 0; c < 3; c++) m_pLog->AddLine(JS_LOGSTR(fmt("    %s component: [<0=%5u] [>255=%5u]", kYcc[c], m_anStatClip[c * 2], m_anStatClip[c * 2 + 1])));
+    m_pLog->AddLine(JS_LOGSTR(""));
+    if (m_bHistEn) {
+        struct { const char* title; const char* const* names; unsigned first; } blocks[3] = {
+            { "  YCC histogram in DC (DCT sums : pre-ranged:", kYcc, 0 }, { "  YCC histogram in DC:", kYcc, 3 }, { "  RGB histogram in DC (before clip):", kRgb, 6 } };
+        for (auto& bl : blocks) {
+            m_pLog->AddLine(JS_LOGSTR(bl.title));
+            for (unsigned c = 0; c < 3; c++)
+                m_pLog->AddLine(JS_LOGSTR(fmt("    %s component histo: [min=%5d max=%5d avg=%7.1f]", bl.names[c], m_anHistoMin[bl.first + c], m_anHistoMax[bl.first + c],
+                                              (float)m_anHistoSum[bl.first + c] / (float)m_nHistoCount)));
+            m_pLog->AddLine(JS_LOGSTR(""));
+        }
+    }
+    m_pLog->AddLine(JS_LOGSTR("  RGB clipping in DC:"));
+    for (unsigned c = 0; c < 3; c++) m_pLog->AddLine(JS_LOGSTR(fmt("    %s component: [<0=%5u] [>255=%5u]", kRgb[c], m_anStatClip[6 + c * 2], m_anStatClip[6 + c * 2 + 1])));
+    m_pLog->AddLine(JS_LOGSTR(""));
+}
+
+// ref :3846-3859
+void CimgDecode::ReportHistogramY()
+{
+    m_pLog->AddLine(JS_LOGSTR("  Y Histogram in DC: (DCT sums) Full"));
+    for (unsigned row = 0; row < JSGPU_Y_HISTO_BINS / 8; row++) {
+        std::string strFull = fmt("    Y=%5d..%5d: ", -1024 + (int)(row * 8), -1024 + (int)(row * 8) + 7);
+        for (unsigned col = 0; col < 8; col++) strFull += fmt("0x%06x, ", m_anHistoYFull[col + row * 8]);
+        m_pLog->AddLine(JS_LOGSTR(strFull));
+    }
+}
+
+// ref :3870-4012: the after-clip RGB ranges, then the two histogram bitmaps (bars of HISTO_BIN_HEIGHT_MAX = 30 rows, one pixel
+// per bin: 128 x 90 for R/G/B stacked, 512 x 30 for the luminance sums taken four bins at a time)
+void CimgDecode::DrawHistogram(bool bQuiet, bool bDumpHistoY)
+{
+    if (!bQuiet) {
+        static const char* const kRgb[3] = { "R ", "G ", "B " };
+        m_pLog->AddLine(JS_LOGSTR("  RGB histogram in DC (after clip):"));
+        for (unsigned c = 0; c < 3; c++)
+            m_pLog->AddLine(JS_LOGSTR(fmt("    %s component histo: [min=%5d max=%5d avg=%7.1f]", kRgb[c], m_anHistoMin[9 + c], m_anHistoMax[9 + c],
+                                          (float)m_anHistoSum[9 + c] / (float)m_nHistoCount)));
+        m_pLog->AddLine(JS_LOGSTR(""));
+    }
+    const unsigned kBarMax = 30, kSubset = 512;
+    m_pDibHistRgb.Kill(); m_bDibHistRgbReady = false;
+    m_pDibHistRgb.CreateDIB(JSGPU_CC_HISTO_BINS, 3 * kBarMax, 32);
+    if (unsigned char* pBits = (unsigned char*)m_pDibHistRgb.GetDIBBitArray()) {
+        const unsigned nRowBytes = JSGPU_CC_HISTO_BINS * 4;
+        memset(pBits, 0, (size_t)3 * kBarMax * nRowBytes);
+        unsigned nPeak = 1;                                          // across all three channels (ref :3912-3926)
+        for (unsigned c = 0; c < 3; c++) for (unsigned i = 0; i < JSGPU_CC_HISTO_BINS; i++) if (m_anCcHisto[c][i] > nPeak) nPeak = m_anCcHisto[c][i];
+        for (unsigned c = 0; c < 3; c++) for (unsigned i = 0; i < JSGPU_CC_HISTO_BINS; i++) {
+            const unsigned nHeight = kBarMax * m_anCcHisto[c][i] / nPeak;          // 32-bit product, like the reference's
+            for (unsigned y = 0; y < nHeight; y++) {
+                unsigned char* px = pBits + (size_t)i * 4 + (size_t)((2 - c) * kBarMax + y) * nRowBytes;
+                px[3] = 0; px[2] = (c == 0) ? 255 : 0; px[1] = (c == 1) ? 255 : 0; px[0] = (c == 2) ? 255 : 0;
+            }
+        }
+        m_bDibHistRgbReady = true;
+    }
+    m_bDibHistYReady = false;
+    if (bDumpHistoY) {
+        m_pDibHistY.Kill();
+        m_pDibHistY.CreateDIB(kSubset, kBarMax, 32);
+        if (unsigned char* pBits = (unsigned char*)m_pDibHistY.GetDIBBitArray()) {
+            const unsigned nRowBytes = kSubset * 4;
+            memset(pBits, 0, (size_t)kBarMax * nRowBytes);
+            unsigned nPeak = 1;
+            for (unsigned i = 0; i < kSubset; i++) { const unsigned v = m_anHistoYFull[i * 4] + m_anHistoYFull[i * 4 + 1] + m_anHistoYFull[i * 4 + 2] + m_anHistoYFull[i * 4 + 3]; if (v > nPeak) nPeak = v; }
+            for (unsigned i = 0; i < kSubset; i++) {
+                const unsigned v = m_anHistoYFull[i * 4] + m_anHistoYFull[i * 4 + 1] + m_anHistoYFull[i * 4 + 2] + m_anHistoYFull[i * 4 + 3];
+                const unsigned nHeight = kBarMax * v / nPeak;
+                for (unsigned y = 0; y < nHeight; y++) { unsigned char* px = pBits + (size_t)i * 4 + (size_t)y * nRowBytes; px[3] = 0; px[2] = 255; px[1] = 255; px[0] = 0; }
+            }
+            m_bDibHistYReady = true;
+        }
     }
 }
 

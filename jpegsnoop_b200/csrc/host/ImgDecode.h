@@ -8,6 +8,7 @@
 // status bar, histogram drawing: ImgDecode.h:296-298, 319-329, 346-349, 419-425) are outside
 // the hot path and are not part of this class.
 #pragma once
+#include <vector>
 // Two build modes.  Stand-alone (default): HostCompat.h supplies small stand-ins for CDocLog / CwindowBuf / CSnoopConfig /
 // CDIB.  Inside JPEGsnoop (-DJSGPU_HOST_EXTERNAL_TYPES): the application's own DocLog.h, WindowBuf.h, SnoopConfig.h and
 // Dib.h are used — this is how oracle/Makefile's `n1` target compiles the reference's unmodified CjfifDecode against this
@@ -121,6 +122,18 @@ public:
     void        ScanErrorsDisable();                                                                 // ref :1014
     void        ScanErrorsEnable();                                                                  // ref :1026
     void        ResetImageContent();                                                                 // ref :603 (empty there too)
+    // Channel preview: each setter recomputes the DIB on the device (CalcChannelPreview, ref :4967-4990)
+    void        SetPreviewMode(unsigned nMode);                                                      // ref :631
+    unsigned    GetPreviewMode() const { return m_nPreviewMode; }                                    // ref :600
+    void        SetPreviewYccOffset(unsigned nMcuX, unsigned nMcuY, int nY, int nCb, int nCr);       // ref :650
+    void        GetPreviewYccOffset(unsigned& nMcuX, unsigned& nMcuY, int& nY, int& nCb, int& nCr);  // ref :669
+    void        ReportColorStats();                                                                  // ref :3764
+    void        ReportHistogramY();                                                                  // ref :3846
+    void        DrawHistogram(bool bQuiet, bool bDumpHistoY);                                        // ref :3870
+    // Export-to-TIFF (CJPEGsnoopDoc::OnToolsExporttiff, JPEGsnoopDoc.cpp:2008-2193): nMode 0 RGB 8-bit, 1 RGB 16-bit, 2 YCC 8-bit
+    // (the dialog's m_nCtlFmt); the sample array is packed on the device.  ExportTiffData fills the pixel part only.
+    bool        ExportTiff(const char* szFnameOut, unsigned nMode);
+    bool        ExportTiffData(unsigned nMode, std::vector<unsigned char>& data);
     void        SetStatusBar(void* /* CStatusBar* */) {}                                              // ref ImgDecode.h:296: GUI only
 
     // Results the reference keeps in private members and reports in its log (ref :3659-3720);
@@ -134,6 +147,12 @@ public:
     unsigned    GetRestartRead() const { return m_nRestartRead; }
     bool        GetBrightest(int& nY, int& nCb, int& nCr, unsigned& nR, unsigned& nG, unsigned& nB, unsigned& nMcuX, unsigned& nMcuY) const;
     bool        GetAvgY(long& nAvgY) const { nAvgY = m_nAvgY; return m_bAvgYValid; }
+    // m_sStatClip (12 counters, PixelCcClip order), m_sHisto as [12 channels][min,max,sum] in PixelCcHisto's order of appearance
+    // (pre-ranged YCC, ranged YCC, clipped RGB, pre-clip RGB) + nCount, m_anCcHisto_r/g/b, m_anHistoYFull
+    const unsigned* GetStatClip() const { return m_anStatClip; }
+    void        GetHistoRanges(int out[36], unsigned& nCount) const;
+    const unsigned* GetCcHisto(unsigned nChan) const { return m_anCcHisto[nChan < 3 ? nChan : 0]; }
+    const unsigned* GetHistoYFull() const { return m_anHistoYFull; }
     const float* GetIdctLookupFloat() const { return &m_afIdctLookup[0][0]; }
     const int*   GetIdctLookupFixed() const { return &m_anIdctLookup[0][0]; }
     // Fill the C-ABI structures from the current table / geometry state (used for batching).
@@ -149,6 +168,8 @@ public:
     int             m_anDqtTblSel[MAX_DQT_COMP];
     bool            m_bDibTempReady;
     bool            m_bPreviewIsJpeg;
+    CDIB            m_pDibHistRgb, m_pDibHistY;      // the histogram bitmaps DrawHistogram paints (ref ImgDecode.h:513-517)
+    bool            m_bDibHistRgbReady, m_bDibHistYReady;
     CDIB            m_pDibTemp;        // public in the reference (ImgDecode.h:384): CjfifDecode hands it to the PSD decoder
                                        // (JfifDecode.cpp:7369); a JPEG scan's BGRA bits live in m_pDibBits, see GetBitmapPtr()
 
@@ -158,6 +179,9 @@ private:
     void        PrecalcIdct();                    // ref :2313-2351 — must run on the HOST (libm cosf)
     void        FreeOutputs();
     bool        EnsureDevice();
+    void        CalcChannelPreview();             // ref :4967-4990 -> CalcChannelPreviewFull :4619-4821, on the device
+    void        PreviewSettings(jsgpu_preview& pv) const;
+    void        FetchPreviewResults();            // DIB, average luminance, statistics and "YCC Clipped" notes of the last preview pass
 
     CSnoopConfig*   m_pAppConfig;
     CSnoopConfig    m_sOwnConfig;
@@ -198,4 +222,17 @@ private:
     bool            m_bBrightValid, m_bAvgYValid;
     long            m_nAvgY;
     float           m_afStageMs[5];
+
+    bool            m_bHistEn, m_bStatClipEn;
+    unsigned        m_nPreviewMode;
+    int             m_nPreviewShiftY, m_nPreviewShiftCb, m_nPreviewShiftCr;
+    unsigned        m_nPreviewShiftMcuX, m_nPreviewShiftMcuY;
+    unsigned        m_nWarnYccClipNum;
+    unsigned        m_nEndPos, m_nEndAlign;       // m_anScanBuffPtr_pos[0], m_nScanBuffPtr_align after the scan (GetScanBufPos, ref :2575)
+    bool            m_bDecodedOnDevice;           // the device still holds this object's last decode
+    unsigned        m_anStatClip[12];
+    int             m_anHistoMin[12], m_anHistoMax[12], m_anHistoSum[12];     // jsgpu_colour_stats channel order
+    unsigned        m_nHistoCount;
+    unsigned        m_anCcHisto[3][JSGPU_CC_HISTO_BINS];
+    unsigned        m_anHistoYFull[JSGPU_Y_HISTO_BINS];
 };

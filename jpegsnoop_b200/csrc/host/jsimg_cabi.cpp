@@ -15,6 +15,21 @@ jsimg* jsimg_create(void) { return new jsimg(); }
 void jsimg_destroy(jsimg* h) { delete h; }
 void jsimg_config(jsimg* h, int ac, int fixed, int dev, int hk, int ik, int dm)
 { h->cfg.bDecodeScanImgAc = ac != 0; h->cfg.bIdctFixedPt = fixed != 0; h->cfg.nCudaDevice = dev; h->cfg.nHuffKernel = hk; h->cfg.nIdctKernel = ik; h->cfg.bDeviceMarkers = dm != 0; }
+void jsimg_config_histo(jsimg* h, int he, int sc, int dy) { h->cfg.bHistoEn = he != 0; h->cfg.bStatClipEn = sc != 0; h->cfg.bDumpHistoY = dy != 0; }
+void jsimg_SetPreviewMode(jsimg* h, unsigned m) { h->dec->SetPreviewMode(m); }
+unsigned jsimg_GetPreviewMode(jsimg* h) { return h->dec->GetPreviewMode(); }
+void jsimg_SetPreviewYccOffset(jsimg* h, unsigned mx, unsigned my, int y, int cb, int cr) { h->dec->SetPreviewYccOffset(mx, my, y, cb, cr); }
+void jsimg_GetPreviewYccOffset(jsimg* h, unsigned* mx, unsigned* my, int* y, int* cb, int* cr) { h->dec->GetPreviewYccOffset(*mx, *my, *y, *cb, *cr); }
+void jsimg_GetStatClip(jsimg* h, uint32_t* o) { memcpy(o, h->dec->GetStatClip(), 12 * sizeof(uint32_t)); }
+void jsimg_GetHistoRanges(jsimg* h, int32_t* o, uint32_t* n) { int t[36]; unsigned c = 0; h->dec->GetHistoRanges(t, c); for (int i = 0; i < 36; i++) o[i] = t[i]; *n = c; }
+void jsimg_GetCcHisto(jsimg* h, unsigned c, uint32_t* o) { memcpy(o, h->dec->GetCcHisto(c), JSGPU_CC_HISTO_BINS * sizeof(uint32_t)); }
+void jsimg_GetHistoYFull(jsimg* h, uint32_t* o) { memcpy(o, h->dec->GetHistoYFull(), JSGPU_Y_HISTO_BINS * sizeof(uint32_t)); }
+const uint8_t* jsimg_GetHistoDib(jsimg* h, int which, int* ready)
+{
+    if (ready) *ready = which ? h->dec->m_bDibHistYReady : h->dec->m_bDibHistRgbReady;
+    return (const uint8_t*)(which ? h->dec->m_pDibHistY.GetDIBBitArray() : h->dec->m_pDibHistRgb.GetDIBBitArray());
+}
+int  jsimg_ExportTiff(jsimg* h, const char* path, unsigned mode) { return h->dec->ExportTiff(path, mode) ? 1 : 0; }
 void jsimg_set_file(jsimg* h, const uint8_t* d, uint64_t n) { h->wbuf.BufSet(d, (size_t)n); }
 int  jsimg_overlay_install(jsimg* h, uint32_t start, const uint8_t* d, uint32_t n) { return h->wbuf.OverlayInstall(start, d, n) ? 1 : 0; }
 void jsimg_overlay_remove_all(jsimg* h) { h->wbuf.OverlayRemoveAll(); }

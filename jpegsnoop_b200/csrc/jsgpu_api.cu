@@ -65,6 +65,9 @@ struct jsgpu_ctx {
     bool layout_only = false;                // ... and that is all this context currently holds: upload/decode need a new batch_begin
     bool host_delivered = false;             // the last decode went straight to host buffers: nothing to download from this context
     float ms[5] = {0, 0, 0, 0, 0};
+    // CalcChannelPreviewFull settings (jsgpu_set_preview) and the statistics of the last preview pass
+    jsgpu_preview pv = {0, 0, 1, 0, 0, 0, 0, 0, JSGPU_MAX_YCC_WARN, 0};
+    DevBuf d_cstats, d_rowclip; uint64_t rows_total = 0; uint32_t max_hp = 0; bool pv_done = false;
 };
 
 static int fail(jsgpu_ctx* c, int code, const char* fmt, ...)
@@ -75,6 +78,21 @@ static int fail(jsgpu_ctx* c, int code, const char* fmt, ...)
     return code;
 }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, (e_ == cudaErrorMemoryAllocation) ? JSGPU_ENOMEM : JSGPU_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); } while (0)
+
+static bool preview_is_default(const jsgpu_preview& p)
+{
+    return !p.hist_en && !p.statclip_en && (p.mode == 0 || p.mode == 1) && !p.shift_y && !p.shift_cb && !p.shift_cr;
+}
+static int run_preview(jsgpu_ctx* ctx, const jsgpu_preview& pv, int* launches)
+{
+    const size_t n = ctx->himg.size();
+    CK(ctx->d_cstats.reserve(n * sizeof(jsgpu_colour_stats)));
+    CK(ctx->d_rowclip.reserve((size_t)ctx->rows_total * 4 + 16));
+    *launches += js_launch_preview(ctx->batch, pv, (jsgpu_colour_stats*)ctx->d_cstats.p, (uint32_t*)ctx->d_rowclip.p, ctx->rows_total,
+                                   ctx->max_hp, ctx->sm_count, ctx->stream);
+    ctx->pv_done = true;
+    return JSGPU_OK;
+}
 
 extern "C" {
 
@@ -126,7 +144,7 @@ void jsgpu_free(jsgpu_ctx* ctx)
     ctx->kids.clear();
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = { &ctx->d_ctab, &ctx->d_li, &ctx->d_lf, &ctx->d_sym, &ctx->d_tables, &ctx->d_img, &ctx->d_items, &ctx->d_litems, &ctx->d_tiles, &ctx->d_ubits, &ctx->d_seg64, &ctx->d_ph, &ctx->d_rowtab, &ctx->d_ex, &ctx->d_bits, &ctx->d_seg,
+    DevBuf* bufs[] = { &ctx->d_ctab, &ctx->d_li, &ctx->d_lf, &ctx->d_sym, &ctx->d_tables, &ctx->d_img, &ctx->d_items, &ctx->d_litems, &ctx->d_tiles, &ctx->d_ubits, &ctx->d_seg64, &ctx->d_ph, &ctx->d_rowtab, &ctx->d_ex, &ctx->d_cstats, &ctx->d_rowclip, &ctx->d_bits, &ctx->d_seg,
                        &ctx->d_coef, &ctx->d_mcubits, &ctx->d_pix, &ctx->d_dib, &ctx->d_blk, &ctx->d_mcumap, &ctx->d_histo, &ctx->d_stats, &ctx->d_misc };
     for (auto* b : bufs) b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -345,6 +363,7 @@ int jsgpu_batch_begin(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, 
     uint64_t pix = 0, dib = 0, blk = 0, mcu = 0, rows = 0, max_scan = 0, ub = 0;
     uint32_t seg = 0, n_std = 0, n_nonstd = 0, plane_bytes = 0, seg_np = 0, n_psync = 0;
     uint64_t pht = 0, rtt = 0, cst = 0; uint32_t max_cs = 0;
+    uint64_t rowt = 0; uint32_t max_hp = 0;
     std::vector<uint2> items, litems, items_np, litems_np, vitems;
     std::vector<uint4> tiles, tcls[3];
     for (uint32_t i = 0; i < n; i++) {
@@ -363,6 +382,7 @@ int jsgpu_batch_begin(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, 
         im.pix_off = pix; im.dib_off = dib; im.blk_off = blk; im.mcu_off = mcu; im.seg_first = seg;
         for (uint32_t c = 0; c < im.ns; c++) { im.coef_row[c] = rows; rows += (uint64_t)im.cw[c] * im.ch[c]; }
         uint64_t npx = (uint64_t)im.wp * im.hp;
+        im.row_off = rowt; rowt += im.hp; max_hp = std::max(max_hp, im.hp);
         pix += align_up(npx, 64); dib += align_up(npx * 4, 256); blk += align_up((uint64_t)im.blk_xmax * im.blk_ymax, 64);
         mcu += align_up(im.nmcu, 32); seg += im.nseg;
         max_scan = std::max(max_scan, im.scan_len);
@@ -426,6 +446,7 @@ int jsgpu_batch_begin(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, 
     CK(ctx->d_stats.reserve((size_t)n * 16 * 4));
     CK(ctx->d_misc.reserve((size_t)n * (8 + 8 + 4 + 4) + 64 + 64));
     CK(ctx->d_ex.reserve((size_t)n * sizeof(JsExResult)));
+    ctx->rows_total = rowt; ctx->max_hp = max_hp; ctx->pv_done = false;
     CK(cudaMemcpyAsync(ctx->d_img.p, ctx->himg.data(), sizeof(DevImage) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     const size_t n_it = items.size(), n_lit = litems.size();
     items.insert(items.end(), items_np.begin(), items_np.end());                   // [all | without self-synchronised images]
@@ -640,10 +661,74 @@ int jsgpu_batch_decode(jsgpu_ctx* ctx)
         launches += js_launch_finalize(bf, s);
         if (ctx->opt.want_mcu_map) launches += js_launch_finalize_emptied(bf, s);
     }
+    // CalcChannelPreview() with non-default settings (ImgDecode.cpp:3641-3643): the DIB again, from the pixel maps
+    ctx->pv_done = false;
+    if (!preview_is_default(ctx->pv)) {
+        int rc = run_preview(ctx, ctx->pv, &launches);
+        if (rc != JSGPU_OK) return rc;
+    }
     CK(cudaEventRecord(ctx->ev[4], s));
     CK(cudaGetLastError());
     ctx->launches = launches;
     ctx->decoded = true;
+    return JSGPU_OK;
+}
+
+int jsgpu_set_preview(jsgpu_ctx* ctx, const jsgpu_preview* p)
+{
+    if (!ctx || !p) return JSGPU_EINVAL;
+    if (p->mode < 0 || p->mode > 8) return fail(ctx, JSGPU_EINVAL, "preview mode must be 0..8 (snoop.h:100-108)");
+    ctx->pv = *p;
+    if (ctx->pv.mode == 0) ctx->pv.mode = 1;
+    return JSGPU_OK;
+}
+
+int jsgpu_batch_preview(jsgpu_ctx* ctx, const jsgpu_preview* p)
+{
+    if (!ctx || !p) return JSGPU_EINVAL;
+    if (p->mode < 0 || p->mode > 8) return fail(ctx, JSGPU_EINVAL, "preview mode must be 0..8 (snoop.h:100-108)");
+    if (!ctx->decoded || ctx->host_delivered) return fail(ctx, JSGPU_ESTATE, "no device-resident decode to recolour");
+    cudaSetDevice(ctx->device);
+    jsgpu_preview pv = *p; if (pv.mode == 0) pv.mode = 1;
+    int launches = 0;
+    int rc = run_preview(ctx, pv, &launches);
+    if (rc != JSGPU_OK) return rc;
+    CK(cudaGetLastError());
+    ctx->launches = launches;
+    return JSGPU_OK;
+}
+
+int jsgpu_batch_export(jsgpu_ctx* ctx, uint32_t image, int mode, void* host_out, uint64_t bytes)
+{
+    if (!ctx || !host_out) return JSGPU_EINVAL;
+    if (mode < JSGPU_EXPORT_RGB8 || mode > JSGPU_EXPORT_YCC8) return fail(ctx, JSGPU_EINVAL, "export mode must be 0 (RGB8), 1 (RGB16) or 2 (YCC8)");
+    if (!ctx->decoded || ctx->host_delivered) return fail(ctx, JSGPU_ESTATE, "no device-resident decode to export");
+    if (image >= ctx->himg.size()) return fail(ctx, JSGPU_EINVAL, "image index out of range");
+    const DevImage& im = ctx->himg[image];
+    if (!im.valid) return fail(ctx, JSGPU_EUNSUP, "image %u was skipped", image);
+    if (mode == JSGPU_EXPORT_YCC8 && im.ns != 3) return fail(ctx, JSGPU_EUNSUP, "YCC export needs a three-component scan");
+    const uint64_t npx = (uint64_t)im.wp * im.hp, need = npx * (mode == JSGPU_EXPORT_RGB16 ? 6 : 3);
+    if (bytes < need) return fail(ctx, JSGPU_EINVAL, "export buffer too small: %llu < %llu bytes", (unsigned long long)bytes, (unsigned long long)need);
+    cudaSetDevice(ctx->device);
+    DevBuf tmp;
+    CK(tmp.reserve((size_t)need + 64));
+    js_launch_export(ctx->batch, image, mode, (uint8_t*)tmp.p, npx, ctx->sm_count, ctx->stream);
+    cudaError_t e = cudaMemcpyAsync(host_out, tmp.p, (size_t)need, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    tmp.release();
+    if (e != cudaSuccess) return fail(ctx, JSGPU_ECUDA, "export failed: %s", cudaGetErrorString(e));
+    return JSGPU_OK;
+}
+
+int jsgpu_batch_colour_stats(jsgpu_ctx* ctx, uint32_t image, jsgpu_colour_stats* out)
+{
+    if (!ctx || !out) return JSGPU_EINVAL;
+    if (!ctx->decoded || ctx->host_delivered || !ctx->pv_done) return fail(ctx, JSGPU_ESTATE, "no preview pass has run on this batch (jsgpu_set_preview / jsgpu_batch_preview)");
+    if (image >= ctx->himg.size()) return fail(ctx, JSGPU_EINVAL, "image index out of range");
+    cudaSetDevice(ctx->device);
+    CK(cudaMemcpyAsync(out, (const jsgpu_colour_stats*)ctx->d_cstats.p + image, sizeof *out, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return JSGPU_OK;
 }
 
@@ -813,6 +898,7 @@ int jsgpu_decode_batch_host(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32
         // (re)configure the chunk context like this one
         jsgpu_options o = ctx->opt;
         r = jsgpu_set_options(k, &o); if (r) return fail(ctx, r, "%s", k->err.c_str());
+        k->pv = ctx->pv;
         if (!k->have_idct || k->h_li != ctx->h_li) { r = jsgpu_set_idct_tables(k, ctx->h_li.data(), ctx->h_lf.data()); if (r) return fail(ctx, r, "%s", k->err.c_str()); }
         if (k->h_sets.size() != ctx->h_sets.size() || memcmp(k->h_sets.data(), ctx->h_sets.data(), sizeof(jsgpu_tables) * ctx->h_sets.size()) != 0) {
             r = jsgpu_upload_tables(k, ctx->h_sets.data(), (uint32_t)ctx->h_sets.size()); if (r) return fail(ctx, r, "%s", k->err.c_str());

@@ -80,6 +80,7 @@ struct DevImage {
     uint64_t ph_first;              // ... first entry of this image in the slot arrays
     uint32_t cs_nslots;             // ... 4096-byte chunk slots of k_unstuff_long reserved for this image
     uint64_t cs_first;              // ... first entry of this image in the chunk arrays
+    uint64_t row_off;               // first entry of this image in the per-pixel-row array of the preview pass (jsgpu_preview.cu)
     uint64_t rt_off;                // first entry of this image in the row table (k_unstuff: unstuffed bytes before every 128-byte raw row of a long interval)
 };
 
@@ -178,7 +179,11 @@ int js_upload_idct_constants(const IdctSym* host_sym, cudaStream_t s);
 int js_make_coef_tensor_map(void* out_tmap, void* coef, uint64_t rows);
 int js_launch_idct_tma(const DevBatch& b, const IdctSym* sym, const ColorTabs* ctab, const void* tmap_host, int sm_count, cudaStream_t s);
 int js_launch_exact(const DevBatch& b, int err_max, cudaStream_t s);       // damaged images, again, with the reference's semantics (jsgpu_exact.cu)
+int js_launch_export(const DevBatch& b, uint32_t image, int mode, uint8_t* out, uint64_t npx, int sm_count, cudaStream_t s);   // Export-to-TIFF sample array
 int js_launch_finalize(const DevBatch& b, cudaStream_t s);
+// CalcChannelPreviewFull with non-default settings: clipping/histogram conversion, channel selection, YCC shift (jsgpu_preview.cu)
+int js_launch_preview(const DevBatch& b, const jsgpu_preview& pv, jsgpu_colour_stats* st, uint32_t* rowclip, uint64_t rows_total,
+                      uint32_t max_hp, int sm_count, cudaStream_t s);
 #define JSGPU_CK_WORDS_INTERNAL 12   // == JSGPU_CK_WORDS (include/jsgpu.h)
 int js_launch_checksums(const DevBatch& b, unsigned long long* ck, cudaStream_t s);
 int js_launch_finalize_emptied(const DevBatch& b, cudaStream_t s);   // after js_launch_finalize: drained-interval MCU map entries

@@ -76,6 +76,46 @@ class CimgDecode:
         y, cb, cr = C.c_int(), C.c_int(), C.c_int()
         self.L.jsimg_LookupBlkYCC(self.h, bx, by, C.byref(y), C.byref(cb), C.byref(cr)); return y.value, cb.value, cr.value
 
+    # --- channel preview, colour statistics, histograms (ImgDecode.cpp:631-677, 3764-4012) -------
+    def config_histo(self, histo_en=False, statclip_en=False, dump_histo_y=False):
+        self.L.jsimg_config_histo(self.h, int(histo_en), int(statclip_en), int(dump_histo_y))
+
+    def SetPreviewMode(self, mode): self.L.jsimg_SetPreviewMode(self.h, mode)
+    def GetPreviewMode(self): return int(self.L.jsimg_GetPreviewMode(self.h))
+    def SetPreviewYccOffset(self, mx, my, y, cb, cr): self.L.jsimg_SetPreviewYccOffset(self.h, mx, my, y, cb, cr)
+
+    def GetPreviewYccOffset(self):
+        mx, my = C.c_uint32(), C.c_uint32(); y, cb, cr = C.c_int(), C.c_int(), C.c_int()
+        self.L.jsimg_GetPreviewYccOffset(self.h, C.byref(mx), C.byref(my), C.byref(y), C.byref(cb), C.byref(cr))
+        return mx.value, my.value, y.value, cb.value, cr.value
+
+    def colour_stats(self):
+        """m_sStatClip [12], m_sHisto ([36] min/max/sum in PixelCcHisto order, nCount), m_anCcHisto_r/g/b [3][128], m_anHistoYFull [2048]."""
+        clip = np.zeros(12, np.uint32); self.L.jsimg_GetStatClip(self.h, clip.ctypes.data)
+        rng = np.zeros(36, np.int32); n = C.c_uint32(); self.L.jsimg_GetHistoRanges(self.h, rng.ctypes.data, C.byref(n))
+        cc = np.zeros((3, 128), np.uint32)
+        for c in range(3):
+            self.L.jsimg_GetCcHisto(self.h, c, cc[c].ctypes.data)
+        yh = np.zeros(2048, np.uint32); self.L.jsimg_GetHistoYFull(self.h, yh.ctypes.data)
+        return {"clip": clip, "ranges": rng, "count": int(n.value), "cc_histo": cc, "y_histo": yh}
+
+    def histo_dib(self, which):
+        """The histogram bitmap DrawHistogram painted (0: R/G/B 128x90, 1: Y 512x30), or None when it is not ready."""
+        ready = C.c_int(0); p = self.L.jsimg_GetHistoDib(self.h, which, C.byref(ready))
+        if not ready.value or not p:
+            return None
+        shape = (30, 512, 4) if which else (90, 128, 4)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=shape).copy()
+
+    def ExportTiff(self, path, mode=0):
+        """Export-to-TIFF of the decoded image (mode 0 RGB 8-bit, 1 RGB 16-bit, 2 YCC 8-bit), JPEGsnoopDoc.cpp:2008-2193."""
+        return bool(self.L.jsimg_ExportTiff(self.h, str(path).encode(), mode))
+
+    def bitmap(self):
+        g = np.zeros(8, np.uint32); self.L.jsimg_GetGeometry(self.h, g.ctypes.data)
+        p = self.L.jsimg_GetBitmapPtr(self.h)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(int(g[7]), int(g[6]), 4)).copy() if p else None
+
     def log_lines(self, kind=-1):
         n = self.L.jsimg_log_count(self.h, kind)
         return [self.L.jsimg_log_line(self.h, kind, i).decode() for i in range(n)]
@@ -246,6 +286,29 @@ class BatchDecoder:
     def checksums(self):
         """uint64 [n][12]: device-side checksums of every output buffer of every image (include/jsgpu.h)."""
         a = np.zeros((self.n, 12), np.uint64); self._ck(self.L.jsgpu_batch_checksums(self.ctx, a.ctypes.data, self.n)); return a
+
+    def set_preview(self, **kw):
+        """jsgpu_set_preview: hist_en, statclip_en, mode, shift_y/cb/cr, shift_mcu_x/y, ycc_warn_budget (default 10)."""
+        p = B.jsgpu_preview(); p.mode = 1; p.ycc_warn_budget = 10
+        for k, v in kw.items():
+            setattr(p, k, v)
+        self._ck(self.L.jsgpu_set_preview(self.ctx, C.byref(p)))
+
+    def preview(self, **kw):
+        """jsgpu_batch_preview: recolour the current batch's DIBs with these settings."""
+        p = B.jsgpu_preview(); p.mode = 1; p.ycc_warn_budget = 10
+        for k, v in kw.items():
+            setattr(p, k, v)
+        self._ck(self.L.jsgpu_batch_preview(self.ctx, C.byref(p)))
+
+    def colour_stats(self, i):
+        s = B.jsgpu_colour_stats(); self._ck(self.L.jsgpu_batch_colour_stats(self.ctx, i, C.byref(s))); return s
+
+    def export(self, i, mode=0):
+        """jsgpu_batch_export: the top-down 3-samples-per-pixel array of image i (uint8; RGB16 as big-endian byte pairs)."""
+        lo = self.layout()[i]
+        out = np.zeros(int(lo.img_x) * int(lo.img_y) * (6 if mode == 1 else 3), np.uint8)
+        self._ck(self.L.jsgpu_batch_export(self.ctx, i, mode, out.ctypes.data, out.size)); return out
 
     def selfsync_info(self):
         """(images on the self-synchronising path, slots, [slots changed in fix round 1, 2, ...])"""

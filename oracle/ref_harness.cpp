@@ -56,6 +56,22 @@ void ref_config(int decode_ac,int histo_en,unsigned err_max) {
 	g_cfg.nErrMaxDecodeScan = err_max;
 }
 
+// CSnoopConfig::bHistoEn / bStatClipEn / bDumpHistoY (SnoopConfig.cpp:76-82)
+void ref_config_histo(int histo_en,int statclip_en,int dump_histo_y) {
+	g_cfg.bHistoEn = histo_en!=0; g_cfg.bStatClipEn = statclip_en!=0; g_cfg.bDumpHistoY = dump_histo_y!=0;
+}
+void ref_SetPreviewMode(RefCtx* c,unsigned m) { c->dec->SetPreviewMode(m); }
+void ref_SetPreviewYccOffset(RefCtx* c,unsigned mx,unsigned my,int y,int cb,int cr) { c->dec->SetPreviewYccOffset(mx,my,y,cb,cr); }
+void ref_GetStatClip(RefCtx* c,uint32_t* o /*[12]*/) { memcpy(o,&c->dec->m_sStatClip,12*sizeof(uint32_t)); }
+void ref_GetHistoRanges(RefCtx* c,int32_t* o /*[36]*/,uint32_t* n) { memcpy(o,&c->dec->m_sHisto,36*sizeof(int32_t)); *n = c->dec->m_sHisto.nCount; }
+void ref_GetCcHisto(RefCtx* c,unsigned ch,uint32_t* o /*[128]*/) {
+	memcpy(o, ch==0 ? c->dec->m_anCcHisto_r : ch==1 ? c->dec->m_anCcHisto_g : c->dec->m_anCcHisto_b, HISTO_BINS*sizeof(uint32_t)); }
+void ref_GetHistoYFull(RefCtx* c,uint32_t* o /*[2048]*/) { memcpy(o,c->dec->m_anHistoYFull,FULL_HISTO_BINS*sizeof(uint32_t)); }
+const uint8_t* ref_GetHistoDib(RefCtx* c,int which,int* ready) {
+	if (ready) *ready = which ? c->dec->m_bDibHistYReady : c->dec->m_bDibHistRgbReady;
+	return (const uint8_t*)(which ? c->dec->m_pDibHistY.GetDIBBitArray() : c->dec->m_pDibHistRgb.GetDIBBitArray());
+}
+
 void ref_set_file(RefCtx* c,const uint8_t* data,uint64_t n) {
 	c->file = CFile(data,n);
 	c->wbuf.BufFileSet(&c->file);

@@ -100,8 +100,50 @@ class Oracle:
         self.lib.ref_err_line.restype = C.c_char_p; self.lib.ref_err_line.argtypes = [C.c_void_p, C.c_int]
         return [self.lib.ref_err_line(self.ctx, i).decode("latin-1") for i in range(self._f("num_err_lines")(self.ctx))]
 
-    def decode(self, jpeg_bytes, overlays=()):
-        """Marker walk + DecodeScanImg(start, bDisplay=true, bQuiet=true); returns Decoded.
+    # --- channel preview / colour statistics (compiled reference only) -----------------------------
+    def config_histo(self, histo_en=False, statclip_en=False, dump_histo_y=False):
+        assert self.kind != "port"
+        self.lib.ref_config_histo(int(histo_en), int(statclip_en), int(dump_histo_y))
+
+    def set_preview_mode(self, mode):
+        self.lib.ref_SetPreviewMode.argtypes = [C.c_void_p, C.c_uint]; self.lib.ref_SetPreviewMode(self.ctx, mode)
+
+    def set_ycc_offset(self, mx, my, y, cb, cr):
+        self.lib.ref_SetPreviewYccOffset.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_int]
+        self.lib.ref_SetPreviewYccOffset(self.ctx, mx, my, y, cb, cr)
+
+    def colour_stats(self):
+        L = self.lib
+        clip = np.zeros(12, np.uint32); L.ref_GetStatClip.argtypes = [C.c_void_p, C.c_void_p]; L.ref_GetStatClip(self.ctx, clip.ctypes.data)
+        rng = np.zeros(36, np.int32); n = C.c_uint32()
+        L.ref_GetHistoRanges.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]; L.ref_GetHistoRanges(self.ctx, rng.ctypes.data, C.byref(n))
+        cc = np.zeros((3, 128), np.uint32); L.ref_GetCcHisto.argtypes = [C.c_void_p, C.c_uint, C.c_void_p]
+        for c in range(3):
+            L.ref_GetCcHisto(self.ctx, c, cc[c].ctypes.data)
+        yh = np.zeros(2048, np.uint32); L.ref_GetHistoYFull.argtypes = [C.c_void_p, C.c_void_p]; L.ref_GetHistoYFull(self.ctx, yh.ctypes.data)
+        return {"clip": clip, "ranges": rng, "count": int(n.value), "cc_histo": cc, "y_histo": yh}
+
+    def histo_dib(self, which):
+        L = self.lib; ready = C.c_int(0)
+        L.ref_GetHistoDib.restype = C.POINTER(C.c_uint8); L.ref_GetHistoDib.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        p = L.ref_GetHistoDib(self.ctx, which, C.byref(ready))
+        if not ready.value or not p:
+            return None
+        return np.ctypeslib.as_array(p, shape=(30, 512, 4) if which else (90, 128, 4)).copy()
+
+    def bitmap(self):
+        g = np.zeros(8, np.uint32); self._f("geometry")(self.ctx, g.ctypes.data)
+        p = self._f("dib")(self.ctx)
+        return np.ctypeslib.as_array(p, shape=(int(g[7]), int(g[6]), 4)).copy() if p else None
+
+    def log_lines(self):
+        """Every log line of the last decode, in order — compiled reference only."""
+        assert self.kind != "port"
+        self.lib.ref_line.restype = C.c_char_p; self.lib.ref_line.argtypes = [C.c_void_p, C.c_int]
+        return [self.lib.ref_line(self.ctx, i).decode("latin-1") for i in range(self.lib.ref_num_lines(self.ctx))]
+
+    def decode(self, jpeg_bytes, overlays=(), quiet=True):
+        """Marker walk + DecodeScanImg(start, bDisplay=true, bQuiet=quiet); returns Decoded.
         overlays: [(file offset, bytes)] installed in the reference's CwindowBuf before the decode (reference only)."""
         buf = np.frombuffer(jpeg_bytes, np.uint8).copy()
         self._keep = buf
@@ -112,7 +154,7 @@ class Oracle:
                 ob = np.frombuffer(bytes(data), np.uint8).copy()
                 self.lib.ref_overlay_install.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_uint]
                 self.lib.ref_overlay_install(self.ctx, int(off), ob.ctypes.data, ob.size)
-        r = self._f("decode_jpeg")(self.ctx, buf.ctypes.data, buf.size, 1)
+        r = self._f("decode_jpeg")(self.ctx, buf.ctypes.data, buf.size, 1 if quiet else 0)
         if r < 0:
             raise ValueError(f"marker walk failed ({r})")
         d = Decoded(); d.scan_start = r
