@@ -240,6 +240,21 @@ def run_config(cfg, args, env, orc, kind, threads, steps, warmup, verify_budget_
            "mismatching_images": bad_all, "checked_by": "device checksums of all output buffers vs " + ("oracle/_ref (compiled reference) checksums" if kind == "reference" else "C port, spot check"),
            "decoder_status_words": status, "gpu_launches_per_step": launches, "gen_s": round(t_gen, 1),
            "cpu_reference_mpix_s": round(cpu_px / cpu_s / 1e6, 2) if cpu_s > 0 else None, "cpu_threads": threads, "cpu_err_lines": cpu_errs}
+    if cfg == "cfg2" and not getattr(args, "no_preview", False):
+        # the channel-preview pass over the resident batch, after the verification above: histogram/clip
+        # statistics conversion, then a plain luminance preview; 6 B read + 4 B written per padded pixel
+        try:
+            pv = {}
+            for key, kw in (("histogram+clip_stats", dict(hist_en=1)), ("luminance_preview", dict(mode=6))):
+                bd.preview(**kw); bd.sync()
+                bd.timer_start(); bd.preview(**kw); ms = bd.timer_stop()
+                pv[key] = {"ms": round(ms, 3), "gbs": round(10.0 * bd.npadded_pixels / (ms / 1e3) / 1e9, 1)}
+                if kw.get("hist_en"):
+                    pv[key]["image0_pixels_counted"] = int(bd.colour_stats(0).count)
+            bd.preview(); bd.sync()                                   # back to the default RGB DIB
+            rec["preview_pass"] = pv
+        except Exception as e:                                        # a side figure: never fail the headline over it
+            rec["preview_pass"] = {"error": str(e)[:200]}
     if ss_info and ss_info[0]:
         rec["selfsync"] = {"images": ss_info[0], "slots": ss_info[1], "slots_changed_per_fix_round": ss_info[2]}
     ctx = {"bits": bits, "darr": darr, "ms_max": ms_max, "total_px": total_px, "stage_ms": stage_ms, "alg_b": alg_b, "cpu_s": cpu_s, "cpu_px": cpu_px,

@@ -67,6 +67,8 @@ const uint8_t* jsimg_GetHistoDib(jsimg*, int which /*0 RGB (128x90), 1 Y (512x30
 
 /* Export-to-TIFF (CJPEGsnoopDoc::OnToolsExporttiff + FileTiff::WriteFile): mode 0 RGB8, 1 RGB16, 2 YCC8; 1 on success */
 int    jsimg_ExportTiff(jsimg*, const char* path, unsigned mode);
+/* FileTiff::WriteFile on a caller-made sample array (no device involved); 1 on success */
+int    jsimg_tiff_write(const char* path, int ycc, int b16, const void* data, unsigned w, unsigned h);
 
 /* log access (error convention: failures are log lines, ImgDecode.cpp:2755-2758 etc.) */
 int    jsimg_log_count(jsimg*, int kind /*0 line,1 hdr,2 warn,3 err,4 good,-1 all*/);

@@ -100,7 +100,7 @@ JSIMG_SYMBOLS = [
     "jsimg_GetDhtHisto", "jsimg_GetGeometry", "jsimg_GetStats", "jsimg_GetIdctTables", "jsimg_GetStageMs", "jsimg_GetScanStatus",
     "jsimg_log_count", "jsimg_log_line", "jsimg_log_clear", "jsimg_walk_jpeg", "jsimg_decode_jpeg", "jsimg_parse_jpeg",
     "jsimg_config_histo", "jsimg_SetPreviewMode", "jsimg_GetPreviewMode", "jsimg_SetPreviewYccOffset", "jsimg_GetPreviewYccOffset",
-    "jsimg_GetStatClip", "jsimg_GetHistoRanges", "jsimg_GetCcHisto", "jsimg_GetHistoYFull", "jsimg_GetHistoDib", "jsimg_ExportTiff"]
+    "jsimg_GetStatClip", "jsimg_GetHistoRanges", "jsimg_GetCcHisto", "jsimg_GetHistoYFull", "jsimg_GetHistoDib", "jsimg_ExportTiff", "jsimg_tiff_write"]
 
 _lib = None
 
@@ -148,6 +148,7 @@ def load():
     L.jsgpu_batch_colour_stats.argtypes = [vp, u32, C.POINTER(jsgpu_colour_stats)]
     L.jsgpu_batch_export.argtypes = [vp, u32, i32, vp, u64]
     L.jsimg_ExportTiff.argtypes = [vp, C.c_char_p, u32]
+    L.jsimg_tiff_write.argtypes = [C.c_char_p, i32, i32, vp, u32, u32]
     L.jsimg_config_histo.argtypes = [vp, i32, i32, i32]; L.jsimg_config_histo.restype = None
     L.jsimg_SetPreviewMode.argtypes = [vp, u32]; L.jsimg_SetPreviewMode.restype = None
     L.jsimg_GetPreviewMode.argtypes = [vp]; L.jsimg_GetPreviewMode.restype = u32

@@ -2,7 +2,7 @@
 // numbers refer to /root/reference/source/ImgDecode.cpp.  Only table keeping, validation,
 // byte shipping and result hosting happen here; all decoding is on the device (jsgpu_*).
 #include "ImgDecode.h"
-#include "FileTiff.h"
+#include "TiffExport.h"
 #include <cmath>
 #include <cstdio>
 #include <cstring>

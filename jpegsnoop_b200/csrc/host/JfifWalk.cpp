@@ -84,6 +84,7 @@ int JfifWalk(CimgDecode* pImgDec, const uint8_t* d, uint64_t n)
             if (Ns > MAX_SOS_COMP_NS || q + 2ull * Ns + 3 > e) return JFIFWALK_ETRUNC;
             for (unsigned i = 1; i <= Ns; i++) { q++; unsigned t = d[q++]; pImgDec->SetDhtTables(i, t >> 4, t & 15); }    // :5161
             pImgDec->SetImageDetails(X, Y, Nf, Ns, bRstEn, nRstInterval);                                         // :5291
+            if (e > 0x7FFFFFFFull) return JFIFWALK_ETRUNC;          // the scan start is returned as an int (file positions are 32-bit in the reference too)
             return (int)e;
         }
         default: break;                                             // APPn, COM, ...: skipped

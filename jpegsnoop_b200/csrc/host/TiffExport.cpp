@@ -1,6 +1,6 @@
-// FileTiff.cpp — see FileTiff.h.  The reference emits the IFD twice (a dry run to learn where the out-of-line values and the
+// TiffExport.cpp — see TiffExport.h.  The reference emits the IFD twice (a dry run to learn where the out-of-line values and the
 // pixel data will land, FileTiff.cpp:283-399); here the directory is a table, so the offsets are known before a byte is written.
-#include "FileTiff.h"
+#include "TiffExport.h"
 #include <stdio.h>
 
 namespace {

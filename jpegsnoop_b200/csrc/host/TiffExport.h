@@ -1,4 +1,4 @@
-// FileTiff.h — the Export-to-TIFF consumer of the decoder's outputs: what CJPEGsnoopDoc::OnToolsExporttiff
+// TiffExport.h — class FileTiff: the Export-to-TIFF consumer of the decoder's outputs: what CJPEGsnoopDoc::OnToolsExporttiff
 // (JPEGsnoopDoc.cpp:2008-2193) and FileTiff::WriteFile (FileTiff.cpp:426-537) produce, byte for byte.  The three-samples-per-
 // pixel array is packed ON THE DEVICE from the resident DIB / pixel maps (jsgpu_batch_export); this class only puts the
 // reference's big-endian header and IFD in front of it.

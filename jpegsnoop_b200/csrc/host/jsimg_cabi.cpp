@@ -1,6 +1,7 @@
 // jsimg_cabi.cpp — include/jsimg.h: flat C shim over CimgDecode for FFI callers.
 #include "../../../include/jsimg.h"
 #include "ImgDecode.h"
+#include "TiffExport.h"
 #include "JfifWalk.h"
 #include <cstring>
 
@@ -30,6 +31,7 @@ const uint8_t* jsimg_GetHistoDib(jsimg* h, int which, int* ready)
     return (const uint8_t*)(which ? h->dec->m_pDibHistY.GetDIBBitArray() : h->dec->m_pDibHistRgb.GetDIBBitArray());
 }
 int  jsimg_ExportTiff(jsimg* h, const char* path, unsigned mode) { return h->dec->ExportTiff(path, mode) ? 1 : 0; }
+int  jsimg_tiff_write(const char* path, int ycc, int b16, const void* data, unsigned w, unsigned h) { FileTiff t; return t.WriteFile(path ? path : "", ycc != 0, b16 != 0, data, w, h) ? 1 : 0; }
 void jsimg_set_file(jsimg* h, const uint8_t* d, uint64_t n) { h->wbuf.BufSet(d, (size_t)n); }
 int  jsimg_overlay_install(jsimg* h, uint32_t start, const uint8_t* d, uint32_t n) { return h->wbuf.OverlayInstall(start, d, n) ? 1 : 0; }
 void jsimg_overlay_remove_all(jsimg* h) { h->wbuf.OverlayRemoveAll(); }

@@ -922,15 +922,26 @@ int jsgpu_decode_batch_host(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32
         o2.dht_histo = out->dht_histo ? (uint32_t*)out->dht_histo + (size_t)i0 * 2 * 4 * 17 : nullptr;
         o2.stats     = out->stats     ? (int32_t*)out->stats + (size_t)i0 * 16 : nullptr;
         r = decode_host_single(k, d.data(), i1 - i0, bits + base, end - base, &o2, false);
-        if (r) return fail(ctx, r, "chunk %u: %s", c, k->err.c_str());
+        if (r) {
+            // earlier chunks still have copies in flight into the caller's buffers: let them land before handing control back
+            for (uint32_t c2 = 0; c2 < c; c2++) cudaStreamSynchronize(ctx->kids[c2]->stream);
+            return fail(ctx, r, "chunk %u: %s", c, k->err.c_str());
+        }
     }
     ctx->launches = 0;
     for (uint32_t c = 0; c < JS_HOST_CHUNKS; c++) {
         jsgpu_ctx* k = ctx->kids[c];
-        CK(cudaStreamSynchronize(k->stream));
+        {
+            const cudaError_t e = cudaStreamSynchronize(k->stream);
+            if (e != cudaSuccess) {
+                for (uint32_t c2 = c + 1; c2 < JS_HOST_CHUNKS; c2++) cudaStreamSynchronize(ctx->kids[c2]->stream);
+                return fail(ctx, JSGPU_ECUDA, "chunk %u: %s", c, cudaGetErrorString(e));
+            }
+        }
         const uint32_t i0 = (uint32_t)((uint64_t)n * c / JS_HOST_CHUNKS), i1 = (uint32_t)((uint64_t)n * (c + 1) / JS_HOST_CHUNKS);
         std::vector<jsgpu_image_layout> lo(i1 - i0);
-        r = jsgpu_batch_layout(k, lo.data(), i1 - i0); if (r) return fail(ctx, r, "%s", k->err.c_str());
+        r = jsgpu_batch_layout(k, lo.data(), i1 - i0);
+        if (r) { for (uint32_t c2 = c + 1; c2 < JS_HOST_CHUNKS; c2++) cudaStreamSynchronize(ctx->kids[c2]->stream); return fail(ctx, r, "%s", k->err.c_str()); }
         for (uint32_t i = i0; i < i1; i++) ctx->layout[i].status = lo[i - i0].status;
         ctx->launches += k->launches;
     }

@@ -74,21 +74,27 @@ __device__ __forceinline__ uint32_t pv_extract(int mode, const PvPix& p)
     return b | (g << 8) | (r << 16);
 }
 
+__device__ __forceinline__ bool pv_shifted(const DevImage& im, const jsgpu_preview& pv, uint32_t px, uint32_t py)
+{
+    // nMcuInd >= nMcuShiftInd (:4733-4739); both use m_nImgSizeX / m_nMcuWidth MCUs per row
+    return (py / im.mcu_h) * im.mcu_xmax + px / im.mcu_w >= pv.shift_mcu_y * im.mcu_xmax + pv.shift_mcu_x;
+}
 __device__ __forceinline__ void pv_load(const DevBatch& b, const DevImage& im, const jsgpu_preview& pv, uint32_t px, uint32_t py, PvPix& p)
 {
     const size_t i = im.pix_off + (size_t)py * im.wp + px;
     p.pre_y = b.pix_y[i]; p.pre_cb = 0; p.pre_cr = 0;
     if (im.ns == 3) { p.pre_cb = b.pix_cb[i]; p.pre_cr = b.pix_cr[i]; }
-    // nMcuInd >= nMcuShiftInd (:4733-4739); both use m_nImgSizeX / m_nMcuWidth MCUs per row
-    const uint32_t mcu_ind = (py / im.mcu_h) * im.mcu_xmax + px / im.mcu_w;
-    if (mcu_ind >= pv.shift_mcu_y * im.mcu_xmax + pv.shift_mcu_x) { p.pre_y += pv.shift_y; p.pre_cb += pv.shift_cb; p.pre_cr += pv.shift_cr; }
+    if (pv_shifted(im, pv, px, py)) { p.pre_y += pv.shift_y; p.pre_cb += pv.shift_cb; p.pre_cr += pv.shift_cr; }
 }
 
-struct PvShared {
-    uint32_t cc[3][JSGPU_CC_HISTO_BINS];
+#define PV_CC_COPIES 8               // copies of the 3 x 128-bin colour histograms: neighbouring pixels mostly fall into the same bin,
+struct PvShared {                    // so the lanes of a warp are spread over copies to keep their shared-memory atomics apart
+    uint32_t cc[PV_CC_COPIES][3][JSGPU_CC_HISTO_BINS];
     uint32_t yh[JSGPU_Y_HISTO_BINS];
 };
 
+// Four pixels per thread (the map width is a multiple of 8 and an MCU at least 8 wide, so a group of four never straddles a row or an
+// MCU): 8-byte loads from the three maps, one 16-byte store into the DIB.
 template <bool FULLCONV, bool HIST>
 __global__ void __launch_bounds__(PV_THREADS) k_preview(DevBatch b, jsgpu_preview pv, jsgpu_colour_stats* st, uint32_t* rowclip)
 {
@@ -102,26 +108,39 @@ __global__ void __launch_bounds__(PV_THREADS) k_preview(DevBatch b, jsgpu_previe
     #pragma unroll
     for (int k = 0; k < 6; k++) rgbclip[k] = 0;
     unsigned long long sum_fy = 0, npx = 0;
-    uint32_t* const dib = reinterpret_cast<uint32_t*>(b.dib + im.dib_off);
+    uint32_t (*const mycc)[JSGPU_CC_HISTO_BINS] = sh.cc[threadIdx.x & (PV_CC_COPIES - 1)];
     for (uint32_t py = blockIdx.x; py < im.hp; py += gridDim.x) {
         uint32_t row_events = 0;
-        for (uint32_t px = threadIdx.x; px < im.wp; px += PV_THREADS) {
-            PvPix p; pv_load(b, im, pv, px, py, p);
-            if (FULLCONV) {
-                pv_full(p);
-                row_events += (p.rng_y > 255) + (p.rng_y < 0) + (p.rng_cb > 255) + (p.rng_cb < 0) + (p.rng_cr > 255) + (p.rng_cr < 0);
-                rgbclip[0] += p.pr < 0; rgbclip[1] += p.pr > 255; rgbclip[2] += p.pg < 0; rgbclip[3] += p.pg > 255; rgbclip[4] += p.pb < 0; rgbclip[5] += p.pb > 255;
-                if (HIST) {
-                    const int v[12] = { p.pre_y, p.pre_cb, p.pre_cr, p.rng_y, p.rng_cb, p.rng_cr, p.pr, p.pg, p.pb, (int)p.fr, (int)p.fg, (int)p.fb };
-                    #pragma unroll
-                    for (int k = 0; k < 12; k++) { vmin[k] = min(vmin[k], v[k]); vmax[k] = max(vmax[k], v[k]); vsum[k] += v[k]; }
-                    npx++;
-                    atomicAdd(&sh.yh[max(-1024, min(1023, p.pre_y)) + 1024], 1u);              // m_anHistoYFull (:4251-4260)
-                    atomicAdd(&sh.cc[0][p.fr >> 1], 1u); atomicAdd(&sh.cc[1][p.fg >> 1], 1u); atomicAdd(&sh.cc[2][p.fb >> 1], 1u);   // 256 / HISTO_BINS = 2 (:4313-4321)
-                }
-            } else pv_fast(p);
-            sum_fy += p.fy;
-            dib[(size_t)(im.hp - 1 - py) * im.wp + px] = pv_extract(pv.mode, p);               // bottom-up, [B,G,R,0] (:4786-4789)
+        const size_t row = im.pix_off + (size_t)py * im.wp;
+        uint4* const drow = reinterpret_cast<uint4*>(b.dib + im.dib_off + (size_t)(im.hp - 1 - py) * im.wp * 4);     // bottom-up (:4786-4789)
+        for (uint32_t px = threadIdx.x * 4; px < im.wp; px += PV_THREADS * 4) {
+            const short4 vy = *reinterpret_cast<const short4*>(b.pix_y + row + px);
+            short4 vb = make_short4(0, 0, 0, 0), vr = vb;
+            if (im.ns == 3) { vb = *reinterpret_cast<const short4*>(b.pix_cb + row + px); vr = *reinterpret_cast<const short4*>(b.pix_cr + row + px); }
+            const bool sh_on = pv_shifted(im, pv, px, py);
+            const int sy = sh_on ? pv.shift_y : 0, sb = sh_on ? pv.shift_cb : 0, sr = sh_on ? pv.shift_cr : 0;
+            const int y4[4] = { vy.x, vy.y, vy.z, vy.w }, b4[4] = { vb.x, vb.y, vb.z, vb.w }, r4[4] = { vr.x, vr.y, vr.z, vr.w };
+            uint32_t o[4];
+            #pragma unroll
+            for (int q = 0; q < 4; q++) {
+                PvPix p; p.pre_y = y4[q] + sy; p.pre_cb = b4[q] + sb; p.pre_cr = r4[q] + sr;
+                if (FULLCONV) {
+                    pv_full(p);
+                    row_events += (p.rng_y > 255) + (p.rng_y < 0) + (p.rng_cb > 255) + (p.rng_cb < 0) + (p.rng_cr > 255) + (p.rng_cr < 0);
+                    rgbclip[0] += p.pr < 0; rgbclip[1] += p.pr > 255; rgbclip[2] += p.pg < 0; rgbclip[3] += p.pg > 255; rgbclip[4] += p.pb < 0; rgbclip[5] += p.pb > 255;
+                    if (HIST) {
+                        const int v[12] = { p.pre_y, p.pre_cb, p.pre_cr, p.rng_y, p.rng_cb, p.rng_cr, p.pr, p.pg, p.pb, (int)p.fr, (int)p.fg, (int)p.fb };
+                        #pragma unroll
+                        for (int k = 0; k < 12; k++) { vmin[k] = min(vmin[k], v[k]); vmax[k] = max(vmax[k], v[k]); vsum[k] += v[k]; }
+                        npx++;
+                        atomicAdd(&sh.yh[max(-1024, min(1023, p.pre_y)) + 1024], 1u);              // m_anHistoYFull (:4251-4260)
+                        atomicAdd(&mycc[0][p.fr >> 1], 1u); atomicAdd(&mycc[1][p.fg >> 1], 1u); atomicAdd(&mycc[2][p.fb >> 1], 1u);   // 256 / HISTO_BINS = 2 (:4313-4321)
+                    }
+                } else pv_fast(p);
+                sum_fy += p.fy;
+                o[q] = pv_extract(pv.mode, p);
+            }
+            drow[px >> 2] = make_uint4(o[0], o[1], o[2], o[3]);
         }
         if (FULLCONV) {
             row_events = __reduce_add_sync(FULL, row_events);
@@ -153,7 +172,12 @@ __global__ void __launch_bounds__(PV_THREADS) k_preview(DevBatch b, jsgpu_previe
         for (int d = 16; d; d >>= 1) npx += __shfl_xor_sync(FULL, npx, d);
         if ((threadIdx.x & 31) == 0 && npx) atomicAdd(reinterpret_cast<unsigned long long*>(&o->count), npx);
         __syncthreads();
-        for (uint32_t i = threadIdx.x; i < 3 * JSGPU_CC_HISTO_BINS; i += PV_THREADS) { const uint32_t v = (&sh.cc[0][0])[i]; if (v) atomicAdd(&o->cc_histo[0][0] + i, v); }
+        for (uint32_t i = threadIdx.x; i < 3 * JSGPU_CC_HISTO_BINS; i += PV_THREADS) {
+            uint32_t v = 0;
+            #pragma unroll
+            for (int c = 0; c < PV_CC_COPIES; c++) v += (&sh.cc[c][0][0])[i];
+            if (v) atomicAdd(&o->cc_histo[0][0] + i, v);
+        }
         for (uint32_t i = threadIdx.x; i < JSGPU_Y_HISTO_BINS; i += PV_THREADS) { const uint32_t v = sh.yh[i]; if (v) atomicAdd(&o->y_histo[i], v); }
     }
 }

@@ -306,7 +306,7 @@ class BatchDecoder:
 
     def export(self, i, mode=0):
         """jsgpu_batch_export: the top-down 3-samples-per-pixel array of image i (uint8; RGB16 as big-endian byte pairs)."""
-        lo = self.layout()[i]
+        lo = self.layout[i]
         out = np.zeros(int(lo.img_x) * int(lo.img_y) * (6 if mode == 1 else 3), np.uint8)
         self._ck(self.L.jsgpu_batch_export(self.ctx, i, mode, out.ctypes.data, out.size)); return out
 

@@ -231,11 +231,15 @@ class CFile { public:
 	uint64_t Seek(int64_t off,UINT from){ int64_t b=(from==begin)?0:(from==current)?(int64_t)m_pos:(int64_t)m_n; int64_t p=b+off; if(p<0)p=0; m_pos=(uint64_t)p; return m_pos; }
 	UINT Read(void* dst,UINT n){ if(m_pos>=m_n) return 0; uint64_t r=std::min<uint64_t>(n,m_n-m_pos); memcpy(dst,m_p+m_pos,(size_t)r); m_pos+=r; return (UINT)r; }
 	uint64_t GetPosition() const { return m_pos; }
-	// write side (N1 build: CjfifDecode's export functions; never reached by the tests): discards
+	// write side: a file opened by NAME for writing goes to the file system (FileTiff::WriteFile, FileTiff.cpp:440; the tests
+	// give it a temporary path); CjfifDecode's export functions (N1 build) are never reached by the tests
 	enum { modeCreate=1, modeWrite=2, typeBinary=4, shareDenyNone=8, modeRead=16, shareDenyWrite=32, modeNoTruncate=64 };
-	CFile(LPCTSTR,UINT) : m_p(nullptr),m_n(0),m_pos(0) {}
+	FILE* m_f = nullptr;
+	CFile(LPCTSTR name,UINT flags) : m_p(nullptr),m_n(0),m_pos(0) { if ((flags & modeWrite) && name) m_f = fopen(name,"wb"); }
 	BOOL Open(LPCTSTR,UINT,void* =nullptr){ return FALSE; }
-	void Write(const void*,UINT){} void Close(){} void Flush(){}
+	void Write(const void* p,UINT n){ if (m_f) fwrite(p,1,n,m_f); }
+	void Close(){ if (m_f) { fclose(m_f); m_f = nullptr; } }
+	void Flush(){ if (m_f) fflush(m_f); }
 };
 class CException { public: virtual ~CException(){} BOOL GetErrorMessage(LPTSTR p,UINT n){ if(n) p[0]=0; return TRUE; } void Delete(){} };
 class CFileException : public CException { public: int m_cause=0; };

@@ -18,6 +18,8 @@
 #include "ImgDecode.h"
 #undef private
 #include "JPEGsnoop.h"
+#include "FileTiff.h"
+#include "General.h"
 
 #include <thread>
 #include <atomic>
@@ -70,6 +72,40 @@ void ref_GetHistoYFull(RefCtx* c,uint32_t* o /*[2048]*/) { memcpy(o,c->dec->m_an
 const uint8_t* ref_GetHistoDib(RefCtx* c,int which,int* ready) {
 	if (ready) *ready = which ? c->dec->m_bDibHistYReady : c->dec->m_bDibHistRgbReady;
 	return (const uint8_t*)(which ? c->dec->m_pDibHistY.GetDIBBitArray() : c->dec->m_pDibHistRgb.GetDIBBitArray());
+}
+
+// Export-to-TIFF: the sample array CJPEGsnoopDoc::OnToolsExporttiff builds from the decoder's DIB / pixel maps
+// (JPEGsnoopDoc.cpp:2098-2170 — GUI code that cannot be compiled here, so those three loops are restated) handed to the
+// reference's own FileTiff::WriteFile (FileTiff.cpp, compiled in place).  mode: 0 RGB 8-bit, 1 RGB 16-bit, 2 YCC 8-bit.
+int ref_export_tiff(RefCtx* c,const char* path,int mode) {
+	unsigned nSizeX=0,nSizeY=0; c->dec->GetImageSize(nSizeX,nSizeY);
+	unsigned char* pBitmapRgb=nullptr; c->dec->GetBitmapPtr(pBitmapRgb);
+	short *pY=c->dec->m_pPixValY,*pCb=c->dec->m_pPixValCb,*pCr=c->dec->m_pPixValCr;
+	const bool bModeYcc=(mode==2), bMode16b=(mode==1);
+	if (!pBitmapRgb || !nSizeX || !nSizeY || (bModeYcc && (!pY||!pCb||!pCr))) return 0;
+	std::vector<unsigned char>  sel8(bMode16b ? 0 : (size_t)nSizeX*nSizeY*3);
+	std::vector<unsigned short> sel16(bMode16b ? (size_t)nSizeX*nSizeY*3 : 0);
+	for (unsigned nIndY=0;nIndY<nSizeY;nIndY++) for (unsigned nIndX=0;nIndX<nSizeX;nIndX++) {
+		const size_t nOffsetDst=((size_t)nIndY*nSizeX+nIndX)*3;
+		if (!bModeYcc) {
+			const size_t nOffsetSrc=((size_t)(nSizeY-1-nIndY)*nSizeX+nIndX)*4;           // the DIB is bottom-up (:2112)
+			const unsigned short nValR=pBitmapRgb[nOffsetSrc+2],nValG=pBitmapRgb[nOffsetSrc+1],nValB=pBitmapRgb[nOffsetSrc+0];
+			if (!bMode16b) { sel8[nOffsetDst]=nValR&0xFF; sel8[nOffsetDst+1]=nValG&0xFF; sel8[nOffsetDst+2]=nValB&0xFF; }
+			else { sel16[nOffsetDst]=Swap16(nValR<<8); sel16[nOffsetDst+1]=Swap16(nValG<<8); sel16[nOffsetDst+2]=Swap16(nValB<<8); }
+		} else {
+			const size_t nOffsetSrc=(size_t)nIndY*nSizeX+nIndX;
+			short v[3]={pY[nOffsetSrc],pCb[nOffsetSrc],pCr[nOffsetSrc]};
+			for (int k=0;k<3;k++) { if (v[k]<-1024) v[k]=-1024; if (v[k]>1023) v[k]=1023; sel8[nOffsetDst+k]=(unsigned char)((0x0400+v[k])>>3); }
+		}
+	}
+	FileTiff myTiff;
+	myTiff.WriteFile(CString(path),bModeYcc,bMode16b,bMode16b ? (void*)sel16.data() : (void*)sel8.data(),nSizeX,nSizeY);
+	return 1;
+}
+
+// FileTiff::WriteFile on a caller-made sample array (header/IFD parity without a decode)
+void ref_tiff_write(const char* path,int ycc,int b16,const void* data,unsigned w,unsigned h) {
+	FileTiff myTiff; myTiff.WriteFile(CString(path),ycc!=0,b16!=0,(void*)data,w,h);
 }
 
 void ref_set_file(RefCtx* c,const uint8_t* data,uint64_t n) {

@@ -50,6 +50,13 @@ def mini_cases():
         ("mini_411_dri3", MJ.encode(synth_rgb(200, 72, 23), quality=75, samp=((4, 1), (1, 1), (1, 1)), dri=3)),
         ("mini_440_nodri", MJ.encode(synth_rgb(120, 88, 24), quality=80, samp=((1, 2), (1, 1), (1, 1)))),
         ("mini_gray_longcodes_nodri", MJ.encode(synth_rgb(136, 64, 25)[:, :, 1], quality=95, ac_tabs=[ac_big, ac_big])),
+    ] + [
+        # every sampling factor up to 4 is legal for the reference (ImgDecode.cpp:2819-2828): 32x32-pixel MCUs, factors of 3,
+        # components with 1 < H < Hmax (tiles larger than the fused IDCT kernel's shared memory go to the literal kernels)
+        ("mini_samp_%s" % "_".join("%dx%d" % hv for hv in samp), MJ.encode(synth_rgb(200, 136, 31 + k), quality=80, samp=samp, dri=dri))
+        for k, (samp, dri) in enumerate([(((4, 4), (1, 1), (1, 1)), 2), (((4, 4), (2, 4), (1, 4)), 0), (((1, 3), (1, 1), (1, 1)), 3),
+                                          (((3, 1), (1, 1), (1, 1)), 2), (((2, 3), (1, 1), (1, 1)), 0), (((4, 2), (2, 2), (1, 1)), 5),
+                                          (((2, 4), (2, 2), (2, 1)), 1)])
     ]
 
 

@@ -1,4 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_preview.py -x -q 2>&1 | tail -n 30
-timeout 900 python -m pytest tests -m gpu -x -q --deselect tests/test_gpu_preview.py 2>&1 | tail -n 4
+timeout 600 python -m pytest tests/test_tiff_export.py -x -q -m gpu 2>&1 | tail -n 6
+timeout 1500 python bench.py 2> gpurun_out/bench_full3.err | tail -n 1 > gpurun_out/bench_full3.json
+cut -c1-1500 gpurun_out/bench_full3.json; tail -n 5 gpurun_out/bench_full3.err
