@@ -284,7 +284,7 @@ typedef struct {
  * min/max start at 0 like the reference's memset (ImgDecode.cpp:3147); sums are 64-bit here, the reference's are `int`
  * (the caller truncates).  clip[]: nClipYUnder, YOver, CbUnder, CbOver, CrUnder, CrOver (counted only while notes are issued:
  * at most ycc_warn_budget in total), RUnder, ROver, GUnder, GOver, BUnder, BOver. */
-typedef struct { uint32_t mcu_x, mcu_y; int32_t y, cb, cr; uint32_t kind; } jsgpu_ycc_warn;   /* kind: index into clip[0..5] */
+typedef struct { uint32_t mcu_x, mcu_y; int32_t y, cb, cr; uint32_t kind; uint32_t px, py; } jsgpu_ycc_warn;   /* kind: index into clip[0..5]; px, py: the pixel */
 typedef struct {
     uint32_t cc_histo[3][JSGPU_CC_HISTO_BINS];    /* m_anCcHisto_r/g/b                                                 */
     uint32_t y_histo[JSGPU_Y_HISTO_BINS];         /* m_anHistoYFull                                                    */
@@ -301,6 +301,28 @@ typedef struct {
 int jsgpu_set_preview(jsgpu_ctx* ctx, const jsgpu_preview* p);
 int jsgpu_batch_preview(jsgpu_ctx* ctx, const jsgpu_preview* p);
 int jsgpu_batch_colour_stats(jsgpu_ctx* ctx, uint32_t image, jsgpu_colour_stats* out);
+
+/* --- "Detailed Decode" of chosen MCUs (CimgDecode::SetDetailVlc, ImgDecode.cpp:4898; DecodeScanCompPrint :1859-2090) ------
+ * For `len` MCUs from (mcu_x, mcu_y) of image `image` the reference prints every Huffman symbol (ReportVlc :2152-2232) and each
+ * block's coefficient matrix (ReportDctMatrix :2104-2131).  The serial reference-semantics walk (the one damaged images take)
+ * collects them; jsgpu_batch_detail returns them after jsgpu_batch_decode.  In DC-only mode the printed MCUs are decoded in full
+ * (AC + IDCT), as DecodeScanCompPrint does. */
+typedef struct { int32_t enable; uint32_t image, mcu_x, mcu_y, len; } jsgpu_detail;
+#define JSGPU_DT_MCU    1   /* an MCU of the range starts: the blank separator line (ImgDecode.cpp:3249-3251)                     */
+#define JSGPU_DT_BLOCK  2   /* "    Lum (Tbl #0), MCU=[x,y]": a = DQT table, b = MCU x, c = MCU y (:1873-1889)                     */
+#define JSGPU_DT_VLC    3   /* ReportVlc: a = file position, b = bit alignment, c = ZRL, d = value, e = first coefficient |
+                               last << 8 | bits of code and value << 16, f = 0 "", 1 "EOB", 2 "ERROR", 3 "EOB64"                  */
+#define JSGPU_DT_MATRIX 4   /* ReportDctMatrix: a = index into matrix[]                                                           */
+typedef struct { uint32_t kind, seq, a, b, c, d, e, f; } jsgpu_detail_event;   /* seq: error events (jsgpu_scan_errors.ev) logged before it */
+#define JSGPU_MAX_DETAIL_EVENTS 8192
+#define JSGPU_MAX_DETAIL_BLOCKS 512
+typedef struct {
+    uint32_t nevents, nblocks, pad0, pad1;       /* counted in full; the arrays keep the first JSGPU_MAX_DETAIL_* */
+    jsgpu_detail_event ev[JSGPU_MAX_DETAIL_EVENTS];
+    int16_t matrix[JSGPU_MAX_DETAIL_BLOCKS][64]; /* m_anDctBlock: dequantised, natural order, [0] = the DC difference */
+} jsgpu_detail_dump;
+int jsgpu_set_detail(jsgpu_ctx* ctx, const jsgpu_detail* d);
+int jsgpu_batch_detail(jsgpu_ctx* ctx, jsgpu_detail_dump* out);
 
 /* --- Export-to-TIFF consumer ---------------------------------------------------------------------------
  * The three-samples-per-pixel, top-down array CJPEGsnoopDoc::OnToolsExporttiff (JPEGsnoopDoc.cpp:2061-2180) hands to

@@ -65,6 +65,9 @@ void   jsimg_GetCcHisto(jsimg*, unsigned nChan, uint32_t* out128); /* m_anCcHist
 void   jsimg_GetHistoYFull(jsimg*, uint32_t* out2048);             /* m_anHistoYFull                               */
 const uint8_t* jsimg_GetHistoDib(jsimg*, int which /*0 RGB (128x90), 1 Y (512x30)*/, int* ready);   /* m_pDibHistRgb / m_pDibHistY */
 
+/* "Detailed Decode" of nLen MCUs from (nX,nY): CimgDecode::SetDetailVlc / GetDetailVlc (ImgDecode.cpp:4880-4904) */
+void   jsimg_SetDetailVlc(jsimg*, int bDetail, unsigned nX, unsigned nY, unsigned nLen);
+void   jsimg_GetDetailVlc(jsimg*, unsigned* bDetail, unsigned* nX, unsigned* nY, unsigned* nLen);
 /* Export-to-TIFF (CJPEGsnoopDoc::OnToolsExporttiff + FileTiff::WriteFile): mode 0 RGB8, 1 RGB16, 2 YCC8; 1 on success */
 int    jsimg_ExportTiff(jsimg*, const char* path, unsigned mode);
 /* FileTiff::WriteFile on a caller-made sample array (no device involved); 1 on success */

@@ -73,7 +73,7 @@ class jsgpu_preview(C.Structure):
 
 
 class jsgpu_ycc_warn(C.Structure):
-    _fields_ = [("mcu_x", C.c_uint32), ("mcu_y", C.c_uint32), ("y", C.c_int32), ("cb", C.c_int32), ("cr", C.c_int32), ("kind", C.c_uint32)]
+    _fields_ = [("mcu_x", C.c_uint32), ("mcu_y", C.c_uint32), ("y", C.c_int32), ("cb", C.c_int32), ("cr", C.c_int32), ("kind", C.c_uint32), ("px", C.c_uint32), ("py", C.c_uint32)]
 
 
 class jsgpu_colour_stats(C.Structure):
@@ -90,7 +90,7 @@ JSGPU_SYMBOLS = [
     "jsgpu_set_idct_tables", "jsgpu_set_options", "jsgpu_get_options", "jsgpu_upload_tables", "jsgpu_bcast_tables",
     "jsgpu_batch_begin", "jsgpu_batch_layout", "jsgpu_batch_pools", "jsgpu_batch_upload", "jsgpu_batch_decode",
     "jsgpu_batch_download", "jsgpu_batch_stage_ms", "jsgpu_timer_start", "jsgpu_timer_stop", "jsgpu_batch_launches", "jsgpu_batch_selfsync_info", "jsgpu_batch_checksums", "jsgpu_batch_errors", "jsgpu_decode_batch_host",
-    "jsgpu_host_alloc", "jsgpu_host_free", "jsgpu_host_copy_rate", "jsgpu_set_preview", "jsgpu_batch_preview", "jsgpu_batch_colour_stats", "jsgpu_batch_export"]
+    "jsgpu_host_alloc", "jsgpu_host_free", "jsgpu_host_copy_rate", "jsgpu_set_preview", "jsgpu_batch_preview", "jsgpu_batch_colour_stats", "jsgpu_batch_export", "jsgpu_set_detail", "jsgpu_batch_detail"]
 JSIMG_SYMBOLS = [
     "jsimg_create", "jsimg_destroy", "jsimg_config", "jsimg_set_file", "jsimg_overlay_install", "jsimg_overlay_remove_all", "jsimg_Reset", "jsimg_ResetState",
     "jsimg_SetDqtEntry", "jsimg_SetDqtTables", "jsimg_GetDqtEntry", "jsimg_SetDhtTables", "jsimg_SetDhtEntry",
@@ -100,7 +100,7 @@ JSIMG_SYMBOLS = [
     "jsimg_GetDhtHisto", "jsimg_GetGeometry", "jsimg_GetStats", "jsimg_GetIdctTables", "jsimg_GetStageMs", "jsimg_GetScanStatus",
     "jsimg_log_count", "jsimg_log_line", "jsimg_log_clear", "jsimg_walk_jpeg", "jsimg_decode_jpeg", "jsimg_parse_jpeg",
     "jsimg_config_histo", "jsimg_SetPreviewMode", "jsimg_GetPreviewMode", "jsimg_SetPreviewYccOffset", "jsimg_GetPreviewYccOffset",
-    "jsimg_GetStatClip", "jsimg_GetHistoRanges", "jsimg_GetCcHisto", "jsimg_GetHistoYFull", "jsimg_GetHistoDib", "jsimg_ExportTiff", "jsimg_tiff_write"]
+    "jsimg_GetStatClip", "jsimg_GetHistoRanges", "jsimg_GetCcHisto", "jsimg_GetHistoYFull", "jsimg_GetHistoDib", "jsimg_ExportTiff", "jsimg_tiff_write", "jsimg_SetDetailVlc", "jsimg_GetDetailVlc"]
 
 _lib = None
 
@@ -149,6 +149,10 @@ def load():
     L.jsgpu_batch_export.argtypes = [vp, u32, i32, vp, u64]
     L.jsimg_ExportTiff.argtypes = [vp, C.c_char_p, u32]
     L.jsimg_tiff_write.argtypes = [C.c_char_p, i32, i32, vp, u32, u32]
+    L.jsgpu_set_detail.argtypes = [vp, vp]
+    L.jsgpu_batch_detail.argtypes = [vp, vp]
+    L.jsimg_SetDetailVlc.argtypes = [vp, i32, u32, u32, u32]; L.jsimg_SetDetailVlc.restype = None
+    L.jsimg_GetDetailVlc.argtypes = [vp] + [C.POINTER(u32)] * 4; L.jsimg_GetDetailVlc.restype = None
     L.jsimg_config_histo.argtypes = [vp, i32, i32, i32]; L.jsimg_config_histo.restype = None
     L.jsimg_SetPreviewMode.argtypes = [vp, u32]; L.jsimg_SetPreviewMode.restype = None
     L.jsimg_GetPreviewMode.argtypes = [vp]; L.jsimg_GetPreviewMode.restype = u32

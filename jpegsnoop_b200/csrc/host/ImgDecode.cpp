@@ -60,6 +60,7 @@ CimgDecode::CimgDecode(CDocLog* pLog, CwindowBuf* pWBuf, CSnoopConfig* pConfig)
     m_nMcuWidth = m_nMcuHeight = 1;          // ref :189-191 (avoid divide-by-zero before the first decode)
     m_nRestartRead = 0;
     for (float& v : m_afStageMs) v = 0.f;
+    m_bDetailVlc = false; m_nDetailVlcX = m_nDetailVlcY = 0; m_nDetailVlcLen = 1;      // ref :194-197
     m_bHistEn = m_bStatClipEn = false;
     m_nPreviewMode = 1;                      // PREVIEW_RGB (ref :220)
     m_nPreviewShiftY = m_nPreviewShiftCb = m_nPreviewShiftCr = 0; m_nPreviewShiftMcuX = m_nPreviewShiftMcuY = 0;   // ref :226
@@ -353,6 +354,9 @@ void CimgDecode::DecodeScanImg(unsigned nStart, bool bDisplay, bool bQuiet)
     jsgpu_preview pv; PreviewSettings(pv);
     if (!bDisplay) { memset(&pv, 0, sizeof pv); pv.mode = 1; }
     jsgpu_set_preview(m_pGpu, &pv);
+    jsgpu_detail dtl; memset(&dtl, 0, sizeof dtl);
+    dtl.enable = m_bDetailVlc ? 1 : 0; dtl.image = 0; dtl.mcu_x = m_nDetailVlcX; dtl.mcu_y = m_nDetailVlcY; dtl.len = m_nDetailVlcLen;
+    jsgpu_set_detail(m_pGpu, &dtl);
     const bool bPreviewPass = pv.hist_en || pv.statclip_en || pv.mode != 1 || pv.shift_y || pv.shift_cb || pv.shift_cr;
 
     jsgpu_tables* pTables = new jsgpu_tables;
@@ -405,60 +409,53 @@ void CimgDecode::DecodeScanImg(unsigned nStart, bool bDisplay, bool bQuiet)
         m_bDibTempReady = true; m_bPreviewIsJpeg = true;                           // ref :3646-3649
     }
     m_nScanStatus = lo.status;
-    if (lo.status & JSGPU_ST_EXACT) {
-        // A damaged scan: the device decoded it a second time the way ReadScanVal / BuffAddByte / DecodeScanComp do (one-bit
-        // resynchronisation, stray markers, lazy restarts, error cap: ref :1096-1115, 1166-1187, 1257-1282, 1486-1561,
-        // 1683-1706, 1737-1797, 2605-2660, 3180-3200) and kept what the reference would have logged; here it becomes text.
-        jsgpu_scan_errors* pErr = new jsgpu_scan_errors;
-        if (jsgpu_batch_errors(m_pGpu, 0, pErr) == JSGPU_OK) {
-            m_bScanBad = pErr->scan_bad != 0;
-            const unsigned nEv = pErr->nevents < JSGPU_MAX_EVENTS ? pErr->nevents : JSGPU_MAX_EVENTS;
-            for (unsigned i = 0; i < nEv; i++) {
-                const jsgpu_scan_event& e = pErr->ev[i];
-                switch (e.code) {
-                case JSGPU_EV_OVERREAD_BEFORE:     m_pLog->AddLineErr(JS_LOGSTR(fmt("*** ERROR: Overread scan segment (before nCode)! @ Offset: 0x%08X.%u", e.a, e.b))); break;
-                case JSGPU_EV_OVERREAD_AFTER_CODE: m_pLog->AddLineErr(JS_LOGSTR(fmt("*** ERROR: Overread scan segment (after nCode)! @ Offset: 0x%08X.%u", e.a, e.b))); break;
-                case JSGPU_EV_OVERREAD_AFTER_BITS: m_pLog->AddLineErr(JS_LOGSTR(fmt("*** ERROR: Overread scan segment (after bitstring)! @ Offset: 0x%08X.%u", e.a, e.b))); break;
-                case JSGPU_EV_NOCODE:              m_pLog->AddLineErr(JS_LOGSTR(fmt("*** ERROR: Can't find huffman bitstring @ 0x%08X.%u, table %u, value [0x%08x]", e.a, e.b, e.c, e.d))); break;
-                case JSGPU_EV_CAP:                 m_pLog->AddLineErr(JS_LOGSTR(fmt("    Only reported first %u instances of this message...", e.a))); break;
-                case JSGPU_EV_RST_MISMATCH:        m_pLog->AddLineErr(JS_LOGSTR(fmt("  ERROR: Expected RST marker index RST%u got RST%u @ 0x%08X.0", e.a, e.b, e.c))); break;
-                case JSGPU_EV_MARKER_NOTE:
-                    m_pLog->AddLine(JS_LOGSTR(fmt("  Scan Data encountered marker   0xFF%02X @ 0x%08X.0", e.a, e.b)));
-                    if (e.a != 0xD9) m_pLog->AddLineErr(JS_LOGSTR("  NOTE: Marker wasn't EOI (0xFFD9)"));
-                    break;
-                case JSGPU_EV_BADMARK:             m_pLog->AddLineErr(JS_LOGSTR(fmt("*** ERROR: Bad marker @ 0x%08X.%u", e.a, e.b))); break;
-                case JSGPU_EV_BADCODE:             m_pLog->AddLineErr(JS_LOGSTR(fmt("*** ERROR: Bad huffman code @ 0x%08X.%u", e.a, e.b))); break;
-                case JSGPU_EV_NCOEF:               m_pLog->AddLineErr(JS_LOGSTR(fmt("*** ERROR: @ 0x%08X.%u, nNumCoeffs>64 [%u]", e.a, e.b, e.c))); break;
-                case JSGPU_EV_MCU: {
-                    const unsigned nComp = e.c & 0xFF, nCssH = (e.c >> 8) & 0xFF, nCssV = (e.c >> 16) & 0xFF;
-                    std::string strComp = fmt(nComp == 0 ? "Lum CSS(%u,%u)" : nComp == 1 ? "Chr(Cb) CSS(%u,%u)" : "Chr(Cr) CSS(%u,%u)", nCssH, nCssV);
-                    m_pLog->AddLineErr(JS_LOGSTR(fmt("*** ERROR: Bad scan data in MCU(%u,%u): %s @ Offset 0x%08X.%u", e.a, e.b, strComp.c_str(), e.d, e.e)));
-                    m_pLog->AddLineErr(JS_LOGSTR(fmt("           MCU located at pixel=(%u,%u)", m_nMcuWidth * e.a + nCssH * 8, m_nMcuHeight * e.b + nCssV * 8)));
-                    break; }
-                case JSGPU_EV_RST_MISSING:
-                    m_pLog->AddLine(JS_LOGSTR(fmt("  Expect Restart interval elapsed @ 0x%08X.%u", e.a, e.b)));
-                    m_pLog->AddLineErr(JS_LOGSTR("    ERROR: Restart marker not detected"));
-                    break;
-                default: break;
-                }
+    // What the scan left in the log: the error events of a damaged scan (the device decoded it a second time the way ReadScanVal /
+    // BuffAddByte / DecodeScanComp do — one-bit resynchronisation, stray markers, lazy restarts, error cap: ref :1096-1115, 1166-1187,
+    // 1257-1282, 1486-1561, 1683-1706, 1737-1797, 2605-2660, 3180-3200 — and kept what the reference would have logged) and, when
+    // SetDetailVlc asked for it, the symbol-by-symbol dump of the chosen MCUs, in the order the reference writes them.
+    bool bMarkerNoteLogged = false;
+    {
+        jsgpu_scan_errors* pErr = new jsgpu_scan_errors; memset(pErr, 0, 16);
+        jsgpu_detail_dump* pDet = m_bDetailVlc ? new jsgpu_detail_dump : nullptr;
+        const bool bExact = (lo.status & JSGPU_ST_EXACT) != 0;
+        const bool bHaveDet = pDet && jsgpu_batch_detail(m_pGpu, pDet) == JSGPU_OK;
+        const bool bHaveErr = (bExact || bHaveDet) && jsgpu_batch_errors(m_pGpu, 0, pErr) == JSGPU_OK;
+        const unsigned nEv = bHaveErr ? (pErr->nevents < JSGPU_MAX_EVENTS ? pErr->nevents : JSGPU_MAX_EVENTS) : 0;
+        unsigned iEv = 0;
+        if (bHaveDet) {
+            const unsigned nDet = pDet->nevents < JSGPU_MAX_DETAIL_EVENTS ? pDet->nevents : JSGPU_MAX_DETAIL_EVENTS;
+            for (unsigned i = 0; i < nDet; i++) {
+                for (; iEv < nEv && iEv < pDet->ev[i].seq; iEv++) { if (pErr->ev[iEv].code == JSGPU_EV_MARKER_NOTE) bMarkerNoteLogged = true; LogScanEvent(pErr->ev[iEv]); }
+                LogDetailEvent(pDet->ev[i], *pDet);
             }
-            if (pErr->nevents > JSGPU_MAX_EVENTS)
-                m_pLog->AddLineErr(JS_LOGSTR(fmt("    (%u further scan error events not itemised)", pErr->nevents - JSGPU_MAX_EVENTS)));
-            m_nRestartRead = pErr->restart_read;
-        } else {
-            m_bScanBad = true;
-            m_pLog->AddLineErr(JS_LOGSTR(fmt("*** ERROR: Bad scan data (device status 0x%08X; error events unavailable: %s) ***", lo.status, jsgpu_last_error(m_pGpu))));
+            if (pDet->nevents > JSGPU_MAX_DETAIL_EVENTS)
+                m_pLog->AddLineWarn(JS_LOGSTR(fmt("    (%u further detailed-decode lines not itemised)", pDet->nevents - JSGPU_MAX_DETAIL_EVENTS)));
         }
-        delete pErr;
-    } else if (lo.status) {
-        m_bScanBad = true;
-        m_pLog->AddLineErr(JS_LOGSTR(fmt("*** ERROR: Bad scan data (device status 0x%08X) ***", lo.status)));
+        if (bExact) {
+            if (bHaveErr) {
+                m_bScanBad = pErr->scan_bad != 0;
+                for (; iEv < nEv; iEv++) LogScanEvent(pErr->ev[iEv]);
+                if (pErr->nevents > JSGPU_MAX_EVENTS)
+                    m_pLog->AddLineErr(JS_LOGSTR(fmt("    (%u further scan error events not itemised)", pErr->nevents - JSGPU_MAX_EVENTS)));
+                m_nRestartRead = pErr->restart_read;
+            } else {
+                m_bScanBad = true;
+                m_pLog->AddLineErr(JS_LOGSTR(fmt("*** ERROR: Bad scan data (device status 0x%08X; error events unavailable: %s) ***", lo.status, jsgpu_last_error(m_pGpu))));
+            }
+        } else {
+            // a healthy image walked only for its detailed decode: the walk stops after the printed MCUs; what it met up to there
+            // (the end-of-scan marker, when the range reaches the end of the image) has its place among the dump lines
+            for (; iEv < nEv; iEv++) { if (pErr->ev[iEv].code == JSGPU_EV_MARKER_NOTE) bMarkerNoteLogged = true; LogScanEvent(pErr->ev[iEv]); }
+            if (lo.status) { m_bScanBad = true; m_pLog->AddLineErr(JS_LOGSTR(fmt("*** ERROR: Bad scan data (device status 0x%08X) ***", lo.status))); }
+        }
+        delete pErr; delete pDet;
     }
     if (!(lo.status & JSGPU_ST_EXACT)) {
         // A healthy scan still leaves one line behind: topping the accumulator up past the last data byte meets the marker
         // that ends the scan (ref :1527-1543) — EOI normally; anything else also earns an error line there.
         const unsigned nEndMark = (unsigned)st[JSGPU_STAT_END_MARK];
-        if ((unsigned long)nEndMark + 1 < nEof && m_nWarnBadScanNum < m_nScanErrMax) {
+        if (bMarkerNoteLogged) m_nWarnBadScanNum++;
+        else if ((unsigned long)nEndMark + 1 < nEof && m_nWarnBadScanNum < m_nScanErrMax) {
             const unsigned nMarker = m_pWBuf->Buf(nEndMark + 1);
             m_pLog->AddLine(JS_LOGSTR(fmt("  Scan Data encountered marker   0xFF%02X @ 0x%08X.0", nMarker, nEndMark)));
             if (nMarker != 0xD9) m_pLog->AddLineErr(JS_LOGSTR("  NOTE: Marker wasn't EOI (0xFFD9)"));
@@ -470,6 +467,7 @@ void CimgDecode::DecodeScanImg(unsigned nStart, bool bDisplay, bool bQuiet)
     m_nEndPos = nEndPos; m_nEndAlign = nEndAlign;
     if (!bQuiet) m_pLog->AddLine(JS_LOGSTR(""));                                    // ref :3630-3632
     if (bDisplay && bPreviewPass) FetchPreviewResults();                           // what CalcChannelPreview left behind (ref :3641-3643)
+    else if (bDisplay && m_bDetailVlc) LogDetailRgb(nullptr);
     if (!bQuiet) {
         // ref :3655-3668 compression statistics: bits of scan data consumed up to where the accumulator stands
         m_pLog->AddLine(JS_LOGSTR("  Compression stats:"));
@@ -510,6 +508,87 @@ void CimgDecode::DecodeScanImg(unsigned nStart, bool bDisplay, bool bQuiet)
         m_pLog->AddLine(JS_LOGSTR(""));
     }
     if (bDisplay && m_bHistEn && bDumpHistoY) ReportHistogramY();   // ref :3740-3742
+}
+
+void CimgDecode::LogScanEvent(const jsgpu_scan_event& e)
+{
+    switch (e.code) {
+    case JSGPU_EV_OVERREAD_BEFORE:     m_pLog->AddLineErr(JS_LOGSTR(fmt("*** ERROR: Overread scan segment (before nCode)! @ Offset: 0x%08X.%u", e.a, e.b))); break;
+    case JSGPU_EV_OVERREAD_AFTER_CODE: m_pLog->AddLineErr(JS_LOGSTR(fmt("*** ERROR: Overread scan segment (after nCode)! @ Offset: 0x%08X.%u", e.a, e.b))); break;
+    case JSGPU_EV_OVERREAD_AFTER_BITS: m_pLog->AddLineErr(JS_LOGSTR(fmt("*** ERROR: Overread scan segment (after bitstring)! @ Offset: 0x%08X.%u", e.a, e.b))); break;
+    case JSGPU_EV_NOCODE:              m_pLog->AddLineErr(JS_LOGSTR(fmt("*** ERROR: Can't find huffman bitstring @ 0x%08X.%u, table %u, value [0x%08x]", e.a, e.b, e.c, e.d))); break;
+    case JSGPU_EV_CAP:                 m_pLog->AddLineErr(JS_LOGSTR(fmt("    Only reported first %u instances of this message...", e.a))); break;
+    case JSGPU_EV_RST_MISMATCH:        m_pLog->AddLineErr(JS_LOGSTR(fmt("  ERROR: Expected RST marker index RST%u got RST%u @ 0x%08X.0", e.a, e.b, e.c))); break;
+    case JSGPU_EV_MARKER_NOTE:
+        m_pLog->AddLine(JS_LOGSTR(fmt("  Scan Data encountered marker   0xFF%02X @ 0x%08X.0", e.a, e.b)));
+        if (e.a != 0xD9) m_pLog->AddLineErr(JS_LOGSTR("  NOTE: Marker wasn't EOI (0xFFD9)"));
+        break;
+    case JSGPU_EV_BADMARK:             m_pLog->AddLineErr(JS_LOGSTR(fmt("*** ERROR: Bad marker @ 0x%08X.%u", e.a, e.b))); break;
+    case JSGPU_EV_BADCODE:             m_pLog->AddLineErr(JS_LOGSTR(fmt("*** ERROR: Bad huffman code @ 0x%08X.%u", e.a, e.b))); break;
+    case JSGPU_EV_NCOEF:               m_pLog->AddLineErr(JS_LOGSTR(fmt("*** ERROR: @ 0x%08X.%u, nNumCoeffs>64 [%u]", e.a, e.b, e.c))); break;
+    case JSGPU_EV_MCU: {
+        const unsigned nComp = e.c & 0xFF, nCssH = (e.c >> 8) & 0xFF, nCssV = (e.c >> 16) & 0xFF;
+        std::string strComp = fmt(nComp == 0 ? "Lum CSS(%u,%u)" : nComp == 1 ? "Chr(Cb) CSS(%u,%u)" : "Chr(Cr) CSS(%u,%u)", nCssH, nCssV);
+        m_pLog->AddLineErr(JS_LOGSTR(fmt("*** ERROR: Bad scan data in MCU(%u,%u): %s @ Offset 0x%08X.%u", e.a, e.b, strComp.c_str(), e.d, e.e)));
+        m_pLog->AddLineErr(JS_LOGSTR(fmt("           MCU located at pixel=(%u,%u)", m_nMcuWidth * e.a + nCssH * 8, m_nMcuHeight * e.b + nCssV * 8)));
+        break; }
+    case JSGPU_EV_RST_MISSING:
+        m_pLog->AddLine(JS_LOGSTR(fmt("  Expect Restart interval elapsed @ 0x%08X.%u", e.a, e.b)));
+        m_pLog->AddLineErr(JS_LOGSTR("    ERROR: Restart marker not detected"));
+        break;
+    default: break;
+    }
+}
+
+// ---- "Detailed Decode" (ref :1859-2232, 4880-4904) -----------------------------------------------------------------------------
+void CimgDecode::SetDetailVlc(bool bDetail, unsigned nX, unsigned nY, unsigned nLen) { m_bDetailVlc = bDetail; m_nDetailVlcX = nX; m_nDetailVlcY = nY; m_nDetailVlcLen = nLen; }
+void CimgDecode::GetDetailVlc(bool& bDetail, unsigned& nX, unsigned& nY, unsigned& nLen) { bDetail = m_bDetailVlc; nX = m_nDetailVlcX; nY = m_nDetailVlcY; nLen = m_nDetailVlcLen; }
+
+void CimgDecode::LogDetailEvent(const jsgpu_detail_event& e, const jsgpu_detail_dump& d)
+{
+    switch (e.kind) {
+    case JSGPU_DT_MCU: m_pLog->AddLine(JS_LOGSTR("")); break;                                          // ref :3249-3251
+    case JSGPU_DT_BLOCK: {                                                                             // ref :1873-1889
+        const char* szTbl = e.a == 0 ? "Lum" : e.a == 1 ? "Chr(0)" : e.a == 2 ? "Chr(1)" : "???";
+        m_pLog->AddLine(JS_LOGSTR(fmt("    %s (Tbl #%u), MCU=[%u,%u]", szTbl, e.a, e.b, e.c)));
+        break; }
+    case JSGPU_DT_VLC: {                                                                               // ReportVlc, ref :2152-2232
+        const unsigned nVlcPos = e.a, nVlcAlign = e.b, nZrl = e.c, nCoeffStart = e.e & 0xFF, nCoeffEnd = (e.e >> 8) & 0xFF, nBits = e.e >> 16;
+        const int nVal = (int)(short)e.d;
+        // the four data bytes from the file position on, stuffed zeros skipped the way the reference's look-back does
+        unsigned nBufByte[4]; unsigned nInd = nVlcPos;
+        const unsigned nPre = m_pWBuf->Buf(nInd - 1);
+        nBufByte[0] = m_pWBuf->Buf(nInd++);
+        if (nPre == 0xFF && nBufByte[0] == 0x00) nBufByte[0] = m_pWBuf->Buf(nInd++);
+        for (unsigned k = 1; k < 4; k++) {
+            nBufByte[k] = m_pWBuf->Buf(nInd++);
+            if (nBufByte[k - 1] == 0xFF && nBufByte[k] == 0x00) nBufByte[k] = m_pWBuf->Buf(nInd++);
+        }
+        std::string strBytes;
+        for (unsigned k = 0; k < 4; k++) for (int bit = 7; bit >= 0; bit--) strBytes += ((nBufByte[k] >> bit) & 1) ? '1' : '0';
+        std::string strBin(nVlcAlign < 32 ? nVlcAlign : 32, '-');
+        if (nVlcAlign < 32) strBin += strBytes.substr(nVlcAlign, nBits);
+        for (unsigned i = nVlcAlign + nBits; i < 32; i++) strBin += '-';
+        for (unsigned at : { 24u, 16u, 8u }) if (strBin.size() >= at) strBin.insert(at, " "); else strBin += " ";
+        const std::string strData = fmt("0x %02X %02X %02X %02X = 0b (%s)", nBufByte[0], nBufByte[1], nBufByte[2], nBufByte[3], strBin.c_str());
+        static const char* const kSpecial[4] = { "", "EOB", "ERROR", "EOB64" };
+        if (nCoeffStart == 0 && nCoeffEnd == 0)
+            m_pLog->AddLine(JS_LOGSTR(fmt("      [0x%08X.%u]: ZRL=[%2u] Val=[%5d] Coef=[%02u= DC] Data=[%s] %s", nVlcPos, nVlcAlign, nZrl, nVal, nCoeffStart, strData.c_str(), kSpecial[e.f & 3])));
+        else
+            m_pLog->AddLine(JS_LOGSTR(fmt("      [0x%08X.%u]: ZRL=[%2u] Val=[%5d] Coef=[%02u..%02u] Data=[%s] %s", nVlcPos, nVlcAlign, nZrl, nVal, nCoeffStart, nCoeffEnd, strData.c_str(), kSpecial[e.f & 3])));
+        break; }
+    case JSGPU_DT_MATRIX: {                                                                            // ReportDctMatrix, ref :2104-2131
+        if (e.a >= JSGPU_MAX_DETAIL_BLOCKS) break;
+        for (unsigned nY = 0; nY < 8; nY++) {
+            std::string strLine = nY == 0 ? "                      DCT Matrix=[" : "                                 [";
+            for (unsigned nX = 0; nX < 8; nX++) { strLine += fmt("%5d", (int)d.matrix[e.a][nY * 8 + nX]); if (nX != 7) strLine += " "; }
+            strLine += "]";
+            m_pLog->AddLine(JS_LOGSTR(strLine));
+        }
+        m_pLog->AddLine(JS_LOGSTR(""));
+        break; }
+    default: break;
+    }
 }
 
 // ---- channel preview, colour statistics, histograms --------------------------------------------------
@@ -569,17 +648,9 @@ void CimgDecode::FetchPreviewResults()
         m_nHistoCount += (unsigned)cs->count;
         for (unsigned c = 0; c < 3; c++) for (unsigned i = 0; i < JSGPU_CC_HISTO_BINS; i++) m_anCcHisto[c][i] += cs->cc_histo[c][i];
         for (unsigned i = 0; i < JSGPU_Y_HISTO_BINS; i++) m_anHistoYFull[i] += cs->y_histo[i];
-        // CapYccRange's notes (ref :4366-4466)
-        static const char* const kKind[6] = { "Y Underflow", "Y Overflow", "Cb Underflow", "Cb Overflow", "Cr Underflow", "Cr Overflow" };
-        for (unsigned i = 0; i < cs->nwarn && i < JSGPU_MAX_YCC_WARN; i++) {
-            const jsgpu_ycc_warn& w = cs->warn[i];
-            m_pLog->AddLineWarn(JS_LOGSTR(fmt("*** NOTE: YCC Clipped. MCU=(%4u,%4u) YCC=(%5d,%5d,%5d) %s @ Offset 0x%08X.%u",
-                                              w.mcu_x, w.mcu_y, w.y, w.cb, w.cr, kKind[w.kind < 6 ? w.kind : 0], m_nEndPos, m_nEndAlign)));
-            m_nWarnYccClipNum++;
-            if (m_nWarnYccClipNum == JSGPU_MAX_YCC_WARN)
-                m_pLog->AddLineWarn(JS_LOGSTR(fmt("    Only reported first %u instances of this message...", (unsigned)JSGPU_MAX_YCC_WARN)));
-        }
-    }
+        if (m_bDetailVlc) LogDetailRgb(cs);                            // the notes, with the RGB dump lines in between
+        else for (unsigned i = 0; i < cs->nwarn && i < JSGPU_MAX_YCC_WARN; i++) LogYccNote(cs->warn[i]);
+    } else if (m_bDetailVlc) LogDetailRgb(nullptr);
     delete cs;
 }
 
@@ -599,6 +670,75 @@ bool CimgDecode::ExportTiff(const char* szFnameOut, unsigned nMode)
     if (!szFnameOut || !ExportTiffData(nMode, data)) return false;
     FileTiff myTiff;
     return myTiff.WriteFile(szFnameOut, nMode == 2, nMode == 1, data.data(), m_nImgSizeX, m_nImgSizeY);
+}
+
+// CapYccRange's notes (ref :4366-4466)
+void CimgDecode::LogYccNote(const jsgpu_ycc_warn& w)
+{
+    static const char* const kKind[6] = { "Y Underflow", "Y Overflow", "Cb Underflow", "Cb Overflow", "Cr Underflow", "Cr Overflow" };
+    m_pLog->AddLineWarn(JS_LOGSTR(fmt("*** NOTE: YCC Clipped. MCU=(%4u,%4u) YCC=(%5d,%5d,%5d) %s @ Offset 0x%08X.%u",
+                                      w.mcu_x, w.mcu_y, w.y, w.cb, w.cr, kKind[w.kind < 6 ? w.kind : 0], m_nEndPos, m_nEndAlign)));
+    m_nWarnYccClipNum++;
+    if (m_nWarnYccClipNum == JSGPU_MAX_YCC_WARN)
+        m_pLog->AddLineWarn(JS_LOGSTR(fmt("    Only reported first %u instances of this message...", (unsigned)JSGPU_MAX_YCC_WARN)));
+}
+
+// The RGB triplet CalcChannelPreviewFull prints in its detailed dump is the pixel BEFORE ChannelExtract (ref :4757-4764): the DIB
+// holds it in the RGB preview mode; in the other modes these few log values (one MCU) are recomputed from the pixel maps with the
+// reference's expressions (ConvertYCCtoRGBFastFloat :4086-4139 / ConvertYCCtoRGB :4229-4325) — a formatting aid, not a decode path.
+static void js_dump_pixel_rgb(int nY, int nCb, int nCr, bool bFull, unsigned& nR, unsigned& nG, unsigned& nB)
+{
+    const float fConstRed = 0.299f, fConstGreen = 0.587f, fConstBlue = 0.114f;
+    int y, cb, cr;
+    if (!bFull) {
+        y = nY >> 3; cb = nCb >> 3; cr = nCr >> 3;
+        y = y < -128 ? -128 : y > 127 ? 127 : y; cb = cb < -128 ? -128 : cb > 127 ? 127 : cb; cr = cr < -128 ? -128 : cr > 127 ? 127 : cr;
+    } else {
+        y = (nY + 1024) / 8; cb = (nCb + 1024) / 8; cr = (nCr + 1024) / 8;
+        y = (y < 0 ? 0 : y > 255 ? 255 : y) - 128; cb = (cb < 0 ? 0 : cb > 255 ? 255 : cb) - 128; cr = (cr < 0 ? 0 : cr > 255 ? 255 : cr) - 128;
+    }
+    float fR = cr * (2 - 2 * fConstRed) + y, fB = cb * (2 - 2 * fConstBlue) + y;
+    float fG = (y - fConstBlue * fB - fConstRed * fR) / fConstGreen;
+    fR += 128; fB += 128; fG += 128;
+    if (!bFull) { nR = fR < 0 ? 0 : fR > 255 ? 255 : (unsigned char)fR; nG = fG < 0 ? 0 : fG > 255 ? 255 : (unsigned char)fG; nB = fB < 0 ? 0 : fB > 255 ? 255 : (unsigned char)fB; }
+    else { const int r = (int)fR, g = (int)fG, b = (int)fB; nR = r < 0 ? 0 : r > 255 ? 255 : r; nG = g < 0 ? 0 : g > 255 ? 255 : g; nB = b < 0 ? 0 : b > 255 ? 255 : b; }
+}
+
+// ref :4683-4687, 4757-4780, 4797-4799: header, one line per pixel row of MCU (m_nDetailVlcX, m_nDetailVlcY) — written when the raster
+// walk leaves the MCU's columns, so a row at the right edge closes on the first pixel of the next row, and the last such row never
+// does — then a blank line.  The "YCC Clipped" notes of the same pass appear where the walk met them.
+void CimgDecode::LogDetailRgb(const jsgpu_colour_stats* cs)
+{
+    m_pLog->AddLine(JS_LOGSTR("  Detailed IDCT Dump (RGB):"));
+    m_pLog->AddLine(JS_LOGSTR(fmt("    MCU [%3u,%3u]:", m_nDetailVlcX, m_nDetailVlcY)));
+    const unsigned W = m_nImgSizeX, H = m_nImgSizeY;
+    const unsigned nNotes = cs ? (cs->nwarn < JSGPU_MAX_YCC_WARN ? cs->nwarn : JSGPU_MAX_YCC_WARN) : 0;
+    unsigned iNote = 0;
+    const bool bRgbInDib = (m_nPreviewMode <= 1 || m_nPreviewMode > 8), bFull = m_bHistEn || m_bStatClipEn;
+    const unsigned long long x0 = (unsigned long long)m_nDetailVlcX * m_nMcuWidth, x1 = x0 + m_nMcuWidth;
+    const unsigned long long y0 = (unsigned long long)m_nDetailVlcY * m_nMcuHeight;
+    if (x0 < W) for (unsigned long long py = y0; py < y0 + m_nMcuHeight && py < H; py++) {
+        const unsigned long long nClose = py * W + (x1 < W ? x1 : W);          // raster index of the pixel that closes this row
+        if (nClose >= (unsigned long long)W * H || (nClose / W) / m_nMcuHeight != m_nDetailVlcY) break;   // never closed: not logged
+        for (; iNote < nNotes && (unsigned long long)cs->warn[iNote].py * W + cs->warn[iNote].px <= nClose; iNote++) LogYccNote(cs->warn[iNote]);
+        std::string strLine = "      [ ";
+        for (unsigned long long px = x0; px < x1 && px < W; px++) {
+            unsigned nR, nG, nB;
+            if (bRgbInDib) { const unsigned char* q = m_pDibBits + ((size_t)(H - 1 - py) * W + px) * 4; nR = q[2]; nG = q[1]; nB = q[0]; }
+            else {
+                const size_t i = (size_t)py * W + px;
+                int nY = m_pPixValY[i], nCb = m_pPixValCb ? m_pPixValCb[i] : 0, nCr = m_pPixValCr ? m_pPixValCr[i] : 0;
+                const unsigned nMcuInd = (unsigned)(py / m_nMcuHeight) * (W / m_nMcuWidth) + (unsigned)(px / m_nMcuWidth);
+                if (nMcuInd >= m_nPreviewShiftMcuY * (W / m_nMcuWidth) + m_nPreviewShiftMcuX) { nY += m_nPreviewShiftY; nCb += m_nPreviewShiftCb; nCr += m_nPreviewShiftCr; }
+                js_dump_pixel_rgb(nY, nCb, nCr, bFull, nR, nG, nB);
+            }
+            strLine += fmt("x%02X%02X%02X ", nR, nG, nB);
+        }
+        strLine += " ]";
+        m_pLog->AddLine(JS_LOGSTR(strLine));
+    }
+    for (; iNote < nNotes; iNote++) LogYccNote(cs->warn[iNote]);
+    m_pLog->AddLine(JS_LOGSTR(""));
 }
 
 void CimgDecode::GetHistoRanges(int out[36], unsigned& nCount) const

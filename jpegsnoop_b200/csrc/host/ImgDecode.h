@@ -130,6 +130,9 @@ public:
     void        ReportColorStats();                                                                  // ref :3764
     void        ReportHistogramY();                                                                  // ref :3846
     void        DrawHistogram(bool bQuiet, bool bDumpHistoY);                                        // ref :3870
+    // "Detailed Decode": every Huffman symbol and coefficient matrix of nLen MCUs from (nX,nY) goes to the log (ref :4880-4904)
+    void        SetDetailVlc(bool bDetail, unsigned nX, unsigned nY, unsigned nLen);
+    void        GetDetailVlc(bool& bDetail, unsigned& nX, unsigned& nY, unsigned& nLen);
     // Export-to-TIFF (CJPEGsnoopDoc::OnToolsExporttiff, JPEGsnoopDoc.cpp:2008-2193): nMode 0 RGB 8-bit, 1 RGB 16-bit, 2 YCC 8-bit
     // (the dialog's m_nCtlFmt); the sample array is packed on the device.  ExportTiffData fills the pixel part only.
     bool        ExportTiff(const char* szFnameOut, unsigned nMode);
@@ -181,7 +184,11 @@ private:
     bool        EnsureDevice();
     void        CalcChannelPreview();             // ref :4967-4990 -> CalcChannelPreviewFull :4619-4821, on the device
     void        PreviewSettings(jsgpu_preview& pv) const;
-    void        FetchPreviewResults();            // DIB, average luminance, statistics and "YCC Clipped" notes of the last preview pass
+    void        FetchPreviewResults();
+    void        LogScanEvent(const jsgpu_scan_event& e);          // one error event of a damaged scan -> the reference's line(s)
+    void        LogDetailEvent(const jsgpu_detail_event& e, const jsgpu_detail_dump& d);   // ReportVlc / ReportDctMatrix lines
+    void        LogYccNote(const jsgpu_ycc_warn& w);
+    void        LogDetailRgb(const jsgpu_colour_stats* cs);       // "Detailed IDCT Dump (RGB)" of CalcChannelPreviewFull, with the YCC notes in between            // DIB, average luminance, statistics and "YCC Clipped" notes of the last preview pass
 
     CSnoopConfig*   m_pAppConfig;
     CSnoopConfig    m_sOwnConfig;
@@ -223,6 +230,7 @@ private:
     long            m_nAvgY;
     float           m_afStageMs[5];
 
+    bool            m_bDetailVlc; unsigned m_nDetailVlcX, m_nDetailVlcY, m_nDetailVlcLen;
     bool            m_bHistEn, m_bStatClipEn;
     unsigned        m_nPreviewMode;
     int             m_nPreviewShiftY, m_nPreviewShiftCb, m_nPreviewShiftCr;

@@ -32,6 +32,8 @@ const uint8_t* jsimg_GetHistoDib(jsimg* h, int which, int* ready)
 }
 int  jsimg_ExportTiff(jsimg* h, const char* path, unsigned mode) { return h->dec->ExportTiff(path, mode) ? 1 : 0; }
 int  jsimg_tiff_write(const char* path, int ycc, int b16, const void* data, unsigned w, unsigned h) { FileTiff t; return t.WriteFile(path ? path : "", ycc != 0, b16 != 0, data, w, h) ? 1 : 0; }
+void jsimg_SetDetailVlc(jsimg* h, int d, unsigned x, unsigned y, unsigned n) { h->dec->SetDetailVlc(d != 0, x, y, n); }
+void jsimg_GetDetailVlc(jsimg* h, unsigned* d, unsigned* x, unsigned* y, unsigned* n) { bool b; h->dec->GetDetailVlc(b, *x, *y, *n); *d = b ? 1u : 0u; }
 void jsimg_set_file(jsimg* h, const uint8_t* d, uint64_t n) { h->wbuf.BufSet(d, (size_t)n); }
 int  jsimg_overlay_install(jsimg* h, uint32_t start, const uint8_t* d, uint32_t n) { return h->wbuf.OverlayInstall(start, d, n) ? 1 : 0; }
 void jsimg_overlay_remove_all(jsimg* h) { h->wbuf.OverlayRemoveAll(); }

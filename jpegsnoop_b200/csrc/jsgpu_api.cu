@@ -68,6 +68,8 @@ struct jsgpu_ctx {
     // CalcChannelPreviewFull settings (jsgpu_set_preview) and the statistics of the last preview pass
     jsgpu_preview pv = {0, 0, 1, 0, 0, 0, 0, 0, JSGPU_MAX_YCC_WARN, 0};
     DevBuf d_cstats, d_rowclip; uint64_t rows_total = 0; uint32_t max_hp = 0; bool pv_done = false;
+    // "Detailed Decode" request (jsgpu_set_detail) and the dump of the last decode
+    jsgpu_detail dtl = {0, 0, 0, 0, 0}; DevBuf d_detail; bool dt_done = false;
 };
 
 static int fail(jsgpu_ctx* c, int code, const char* fmt, ...)
@@ -144,7 +146,7 @@ void jsgpu_free(jsgpu_ctx* ctx)
     ctx->kids.clear();
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = { &ctx->d_ctab, &ctx->d_li, &ctx->d_lf, &ctx->d_sym, &ctx->d_tables, &ctx->d_img, &ctx->d_items, &ctx->d_litems, &ctx->d_tiles, &ctx->d_ubits, &ctx->d_seg64, &ctx->d_ph, &ctx->d_rowtab, &ctx->d_ex, &ctx->d_cstats, &ctx->d_rowclip, &ctx->d_bits, &ctx->d_seg,
+    DevBuf* bufs[] = { &ctx->d_ctab, &ctx->d_li, &ctx->d_lf, &ctx->d_sym, &ctx->d_tables, &ctx->d_img, &ctx->d_items, &ctx->d_litems, &ctx->d_tiles, &ctx->d_ubits, &ctx->d_seg64, &ctx->d_ph, &ctx->d_rowtab, &ctx->d_ex, &ctx->d_cstats, &ctx->d_rowclip, &ctx->d_detail, &ctx->d_bits, &ctx->d_seg,
                        &ctx->d_coef, &ctx->d_mcubits, &ctx->d_pix, &ctx->d_dib, &ctx->d_blk, &ctx->d_mcumap, &ctx->d_histo, &ctx->d_stats, &ctx->d_misc };
     for (auto* b : bufs) b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -605,6 +607,9 @@ int jsgpu_batch_decode(jsgpu_ctx* ctx)
     CK(cudaMemsetAsync(b.bright_key, 0, (size_t)b.nimg * (8 + 8 + 4) + 4, s));      // + ovf_count
     CK(cudaMemsetAsync(b.mcu_map, 0, ctx->mcu_total * 4, s));
     CK(cudaMemsetAsync(b.blk_y, 0, ctx->blk_total * 2 * 3, s));
+    // exotic sampling layouts leave pixels of a component unwritten (a component with 1 < H < Hmax covers only part of the MCU): they
+    // read as the 0 the reference's memset left there (ImgDecode.cpp:2924-2928); standard layouts write every pixel
+    if (ctx->n_nonstd) CK(cudaMemsetAsync(b.pix_y, 0, ctx->pix_total * 2 * 3, s));
     if (ctx->opt.device_markers) launches += js_launch_marker_scan(b, ctx->max_scan_len, s);
     else {
         std::vector<uint8_t> hb(ctx->bits_len);
@@ -635,7 +640,16 @@ int jsgpu_batch_decode(jsgpu_ctx* ctx)
             launches += js_launch_huffman_lane_vseg(bh, ctx->sm_count, s);
         }
         // damaged images (status word != 0) are decoded again with the reference's semantics; returns at once for the others
-        launches += js_launch_exact(b, ctx->opt.scan_err_max > 0 ? ctx->opt.scan_err_max : 20, s);
+        ctx->dt_done = false;
+        jsgpu_detail dtl = ctx->dtl;
+        if (dtl.enable && dtl.image < b.nimg) {
+            CK(ctx->d_detail.reserve(sizeof(jsgpu_detail_dump) + 2 * 4 * 17 * 4));
+            CK(cudaMemsetAsync(ctx->d_detail.p, 0, 16, s));
+            ctx->dt_done = true;
+        } else dtl.enable = 0;
+        jsgpu_detail_dump* dump = (jsgpu_detail_dump*)ctx->d_detail.p;
+        launches += js_launch_exact(b, ctx->opt.scan_err_max > 0 ? ctx->opt.scan_err_max : 20, dtl, dump,
+                                    dump ? (uint32_t*)((uint8_t*)dump + sizeof(jsgpu_detail_dump)) : nullptr, s);
     }
     CK(cudaEventRecord(ctx->ev[2], s));
     {
@@ -695,6 +709,23 @@ int jsgpu_batch_preview(jsgpu_ctx* ctx, const jsgpu_preview* p)
     if (rc != JSGPU_OK) return rc;
     CK(cudaGetLastError());
     ctx->launches = launches;
+    return JSGPU_OK;
+}
+
+int jsgpu_set_detail(jsgpu_ctx* ctx, const jsgpu_detail* d)
+{
+    if (!ctx || !d) return JSGPU_EINVAL;
+    ctx->dtl = *d;
+    return JSGPU_OK;
+}
+
+int jsgpu_batch_detail(jsgpu_ctx* ctx, jsgpu_detail_dump* out)
+{
+    if (!ctx || !out) return JSGPU_EINVAL;
+    if (!ctx->decoded || ctx->host_delivered || !ctx->dt_done) return fail(ctx, JSGPU_ESTATE, "the last decode collected no detailed decode (jsgpu_set_detail)");
+    cudaSetDevice(ctx->device);
+    CK(cudaMemcpyAsync(out, ctx->d_detail.p, sizeof *out, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return JSGPU_OK;
 }
 
@@ -760,7 +791,8 @@ int jsgpu_batch_errors(jsgpu_ctx* ctx, uint32_t image, jsgpu_scan_errors* out)
     uint32_t flag = 0;
     CK(cudaMemcpyAsync(&flag, ctx->batch.ex_flag + image, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (!flag) return fail(ctx, JSGPU_ESTATE, "image %u did not take the serial error path", image);
+    const bool detail_walk = ctx->dt_done && ctx->dtl.enable && ctx->dtl.image == image;      // a healthy image walked for its detailed decode
+    if (!flag && !detail_walk) return fail(ctx, JSGPU_ESTATE, "image %u did not take the serial error path", image);
     CK(cudaMemcpyAsync(out, ctx->batch.ex_res + image, sizeof *out, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return JSGPU_OK;

@@ -31,7 +31,20 @@ struct Ex {
     uint32_t* histo;                             // [2][4][17] of this image
     const DevTableSet* ts;
     short dct[64];
+    uint32_t bits_used;                          // m_nScanBitsUsed1 + m_nScanBitsUsed2 of the last ReadScanVal
+    jsgpu_detail_dump* dt;                       // "Detailed Decode" of the chosen MCUs (DecodeScanCompPrint), or nullptr
 };
+
+// one line of the detailed decode; seq = error events issued so far, so the host can interleave both lists as the reference's log does
+__device__ __forceinline__ void ex_detail(Ex& x, uint32_t kind, uint32_t a = 0, uint32_t b = 0, uint32_t c = 0, uint32_t d = 0, uint32_t e = 0, uint32_t f = 0)
+{
+    jsgpu_detail_dump* t = x.dt;
+    if (t->nevents < JSGPU_MAX_DETAIL_EVENTS) {
+        jsgpu_detail_event& ev = t->ev[t->nevents];
+        ev.kind = kind; ev.seq = x.res->nevents; ev.a = a; ev.b = b; ev.c = c; ev.d = d; ev.e = e; ev.f = f;
+    }
+    t->nevents++;
+}
 
 __device__ __forceinline__ void ex_event(Ex& x, uint32_t code, uint32_t lines, uint32_t a = 0, uint32_t b = 0, uint32_t c = 0, uint32_t d = 0, uint32_t e = 0)
 {
@@ -146,7 +159,7 @@ __device__ __forceinline__ uint32_t ex_find_code(const Ex& x, uint32_t slot, uin
 // ImgDecode.cpp:1072-1286
 __device__ __noinline__ int ex_read_scan_val(Ex& x, uint32_t cls, uint32_t tbl, uint32_t& zrl, int& val)
 {
-    zrl = 0; val = 0;
+    zrl = 0; val = 0; x.bits_used = 0;
     if (x.vacant == 32 && x.restart_flag) return EX_RSV_RST_TERM;
     if (x.vacant >= 32) {
         ex_warn(x, JS_EX_OVERREAD_BEFORE, 1, x.pos[0], x.align);
@@ -162,6 +175,7 @@ __device__ __noinline__ int ex_read_scan_val(Ex& x, uint32_t cls, uint32_t tbl, 
         bits1 = 1; code = 0xFFFFFFFFu;                       // :1178-1187: move one bit and let the caller try again
     }
     if (bits1 < 17) x.histo[(cls * 4 + tbl) * 17 + bits1]++;
+    x.bits_used = bits1;
     ex_scanbuf_consume(x, bits1);
     if (x.vacant > 32) {
         ex_event(x, JS_EX_OVERREAD_AFTER_CODE, 1, x.pos[0], x.align);
@@ -172,6 +186,7 @@ __device__ __noinline__ int ex_read_scan_val(Ex& x, uint32_t cls, uint32_t tbl, 
     if (code != 0xFFFFFFFFu) {
         zrl = (code & 0xF0) >> 4;
         const uint32_t bits2 = code & 0x0F;
+        x.bits_used += bits2;
         if (zrl == 0 && bits2 == 0) return EX_RSV_EOB;
         if (bits2 == 0) { val = 0; return EX_RSV_OK; }
         const uint32_t v = x.buff >> (32 - bits2);                                            // ExtractBits, :898-903
@@ -199,12 +214,16 @@ __device__ __forceinline__ void ex_idct_set(Ex& x, uint32_t dqt, uint32_t ncoef,
     x.dct[q >> 16] = (short)(val * (int)(q & 0xFFFF));
 }
 
-// DecodeScanComp, ImgDecode.cpp:1604-1835.  Returns false when the block ended in an underflow (no IDCT is run for it:
-// its samples are the DC alone).
-__device__ __noinline__ bool ex_decode_scan_comp(Ex& x, uint32_t tdc, uint32_t tac, uint32_t tdqt, short& dc_lum, short& dc_cb, short& dc_cr)
+// DecodeScanComp, ImgDecode.cpp:1604-1835, and — print = true — its verbose twin DecodeScanCompPrint (:1859-2090), which differs
+// in three ways: every symbol becomes a ReportVlc line, AC coefficients are kept even in DC-only mode, and the IDCT always runs.
+// Returns false when the block ended in an underflow (no IDCT is run for it: its samples are the DC alone).
+__device__ __noinline__ bool ex_decode_scan_comp(Ex& x, uint32_t tdc, uint32_t tac, uint32_t tdqt, short& dc_lum, short& dc_cb, short& dc_cr,
+                                                  bool print, uint32_t mx, uint32_t my)
 {
     uint32_t zrl; int val; bool done = false, bdc = true; uint32_t ncoef = 0;
+    uint32_t special = 0;                                        // strSpecial: 0 "", 1 EOB, 2 ERROR, 3 EOB64 (keeps its value across symbols)
     for (int i = 0; i < 64; i++) x.dct[i] = 0;
+    if (print) ex_detail(x, JSGPU_DT_BLOCK, tdqt, mx, my);
     while (!done) {
         ex_buff_topup(x);
         const uint32_t saved_pos = x.pos[0], saved_err = x.latch_err, saved_align = x.align;
@@ -223,42 +242,63 @@ __device__ __noinline__ bool ex_decode_scan_comp(Ex& x, uint32_t tdc, uint32_t t
             ex_warn(x, JS_EX_BADMARK, 1, saved_pos, saved_align);
             x.latch_err = EX_SCANBUF_OK;
         }
+        const uint32_t coef_start = ncoef, coef_end = ncoef + zrl;
         const short v2 = (short)(val & 0xFFFF);
         if (r == EX_RSV_OK) {
+            if (print) special = 0;
             if (bdc) { ex_idct_set(x, tdqt, ncoef, zrl, v2); bdc = false; }
-            else if (x.decode_ac) ex_idct_set(x, tdqt, ncoef, zrl, v2);
+            else if (x.decode_ac || print) ex_idct_set(x, tdqt, ncoef, zrl, v2);
         } else if (r == EX_RSV_EOB) {
             if (bdc) { ex_idct_set(x, tdqt, ncoef, zrl, v2); bdc = false; } else done = true;
+            special = 1;
         } else if (r == EX_RSV_UNDERFLOW) {                      // :1737-1760
+            if (x.warn_bad_num < x.err_max) special = 2;
             ex_warn(x, JS_EX_BADCODE, 1, saved_pos, saved_align);
             x.cur_err = true;
+            if (print) ex_detail(x, JSGPU_DT_VLC, saved_pos, saved_align, zrl, (uint32_t)(int)v2, coef_start | (coef_end << 8) | (x.bits_used << 16), special);
             return false;
         }
         ncoef += 1 + zrl;
-        if (ncoef == 64) done = true;
+        if (ncoef == 64) { special = 3; done = true; }
         else if (ncoef > 64) {                                   // :1776-1797
             ex_warn(x, JS_EX_NCOEF, 1, saved_pos, saved_align, ncoef);
             x.cur_err = true; x.scan_bad = true; done = true; ncoef = 64;
         }
+        if (print) ex_detail(x, JSGPU_DT_VLC, saved_pos, saved_align, zrl, (uint32_t)(int)v2, coef_start | (coef_end << 8) | (x.bits_used << 16), special);
+    }
+    if (print) {                                                 // ReportDctMatrix (:2104-2131): the dequantised block, natural order
+        jsgpu_detail_dump* t = x.dt;
+        if (t->nblocks < JSGPU_MAX_DETAIL_BLOCKS) { for (int i = 0; i < 64; i++) t->matrix[t->nblocks][i] = x.dct[i]; }
+        ex_detail(x, JSGPU_DT_MATRIX, t->nblocks);
+        t->nblocks++;
     }
     return true;
 }
 
 // One thread re-decodes one damaged image.  grid = images, 32 threads per CTA (lane 0 works).
-__global__ void __launch_bounds__(32) k_huff_exact(DevBatch b, int err_max)
+// The same walk serves the "Detailed Decode" of chosen MCUs (m_bDetailVlc, SetDetailVlc :4898): for the image it is asked for, the
+// walk runs even when the image is healthy — then without touching any output (the fast path has produced them) except the
+// coefficient rows of the printed MCUs in DC-only mode, which the reference decodes in full — and ends after the last MCU of the range.
+__global__ void __launch_bounds__(32) k_huff_exact(DevBatch b, int err_max, jsgpu_detail dtl, jsgpu_detail_dump* dump, uint32_t* scratch_histo)
 {
     const uint32_t ii = blockIdx.x;
-    if (threadIdx.x != 0 || !b.ex_flag[ii]) return;
+    if (threadIdx.x != 0) return;
+    const bool wr = b.ex_flag[ii] != 0;                          // damaged: this walk produces the outputs
+    const bool detail = dtl.enable && dtl.image == ii && b.img[ii].valid;
+    if (!wr && !detail) return;
     const DevImage& im = b.img[ii];
     Ex x;
     x.data = b.bits + im.scan_off; x.n = (uint32_t)im.scan_len; x.file_pos = im.file_pos;
     x.ts = b.tables + im.table_set;
-    x.res = b.ex_res + ii; x.histo = b.histo + (size_t)ii * 2 * 4 * 17;
+    x.res = b.ex_res + ii; x.histo = wr ? b.histo + (size_t)ii * 2 * 4 * 17 : scratch_histo;
     x.res->nerr_lines = 0; x.res->nevents = 0; x.res->scan_bad = 0; x.res->restart_read = 0; x.res->done = 0;
     x.err_max = (uint32_t)err_max; x.warn_bad_num = 0;
     x.precision = im.precision; x.decode_ac = b.decode_ac != 0;
     x.rst_interval = im.restart_en ? im.ri : 0;                 // m_nRestartInterval (0 when DRI is off: never looked at then)
-    x.restart_read = 0; x.restart_last = 0; x.restart_expect = 0;
+    x.restart_read = 0; x.restart_last = 0; x.restart_expect = 0; x.bits_used = 0;
+    x.dt = detail ? dump : nullptr;
+    if (detail) { dump->nevents = 0; dump->nblocks = 0; }
+    const uint32_t dt_base = dtl.mcu_y * im.mcu_xmax + dtl.mcu_x;
     for (int i = 0; i < 16; i++) { x.css[0][i] = 0; x.css[1][i] = 0; x.css[2][i] = 0; }
     ex_restart_scan_buf(x, 0);
     ex_buff_topup(x);
@@ -266,15 +306,20 @@ __global__ void __launch_bounds__(32) k_huff_exact(DevBatch b, int err_max)
     const uint32_t ns = im.ns;
     int16_t* const blk_y = b.blk_y + im.blk_off; int16_t* const blk_cb = b.blk_cb + im.blk_off; int16_t* const blk_cr = b.blk_cr + im.blk_off;
     const size_t nb = (size_t)im.blk_xmax * im.blk_ymax;
-    for (uint32_t my = 0; my < im.mcu_ymax; my++) {
+    bool all_done = false;
+    for (uint32_t my = 0; my < im.mcu_ymax && !all_done; my++) {
         bool stop = false;
         for (uint32_t mx = 0; mx < im.mcu_xmax && !stop; mx++) {
+            const uint32_t mcu = my * im.mcu_xmax + mx;
+            if (!wr && (unsigned long long)mcu >= (unsigned long long)dt_base + dtl.len) { all_done = true; break; }     // nothing left to print
             if (im.restart_en && x.mcus_left == 0 && !x.restart_flag) ex_event(x, JS_EX_RST_MISSING, 1, x.pos[0], x.align);     // :3180-3200
-            b.mcu_map[im.mcu_off + my * im.mcu_xmax + mx] = (x.pos[0] << 4) + x.align;                                             // :3229
+            if (wr) b.mcu_map[im.mcu_off + mcu] = (x.pos[0] << 4) + x.align;                                                       // :3229
+            const bool print = detail && mcu >= dt_base && (unsigned long long)mcu < (unsigned long long)dt_base + dtl.len;        // :3235-3241
+            if (print) ex_detail(x, JSGPU_DT_MCU);
             for (uint32_t c = 0; c < ns; c++) {
                 const uint32_t tdc = im.slot_dc[c], tac = im.slot_ac[c] - 4, tdqt = im.dqt[c];
                 for (uint32_t v = 0; v < im.V[c]; v++) for (uint32_t h = 0; h < im.H[c]; h++) {
-                    const bool full = ex_decode_scan_comp(x, tdc, tac, tdqt, dc_lum, dc_cb, dc_cr);
+                    const bool full = ex_decode_scan_comp(x, tdc, tac, tdqt, dc_lum, dc_cb, dc_cr, print, mx, my);
                     if (x.cur_err) {                             // CheckScanErrors, :2605-2660 (two lines per instance)
                         ex_warn(x, JS_EX_MCU, 2, mx, my, c | (h << 8) | (v << 16), x.pos[0], x.align);
                         x.cur_err = false;
@@ -282,16 +327,18 @@ __global__ void __launch_bounds__(32) k_huff_exact(DevBatch b, int err_max)
                     short& dc = (c == 0) ? dc_lum : (c == 1) ? dc_cb : dc_cr;
                     dc = (short)(dc + x.dct[0]);                 // :3280, 3355, 3386
                     // the coefficient row the IDCT kernels read: slot 0 = DC sum; AC only when the IDCT ran for this block
-                    int16_t* row = b.coef + (im.coef_row[c] + (size_t)(my * im.V[c] + v) * im.cw[c] + (mx * im.H[c] + h)) * 64;
-                    row[0] = dc;
-                    const bool ac = full && x.decode_ac;
-                    for (int i = 1; i < 64; i++) row[i] = ac ? x.dct[i] : (short)0;
+                    const bool ac = full && (x.decode_ac || print);
+                    if (wr || (print && !x.decode_ac)) {
+                        int16_t* row = b.coef + (im.coef_row[c] + (size_t)(my * im.V[c] + v) * im.cw[c] + (mx * im.H[c] + h)) * 64;
+                        row[0] = dc;
+                        for (int i = 1; i < 64; i++) row[i] = ac ? x.dct[i] : (short)0;
+                    }
                     x.css[c][v * 4 + h] = dc;                    // :3282, 3357, 3388
                 }
             }
             // block-DC maps, :3524-3608: written after the MCU from the per-block copies (which a restart inside the MCU has
             // cleared), with the reference's own addressing, overlaps included
-            for (uint32_t c = 0; c < ns; c++)
+            if (wr) for (uint32_t c = 0; c < ns; c++)
                 for (uint32_t v = 0; v < im.V[c]; v++) for (uint32_t h = 0; h < im.H[c]; h++) {
                     const size_t bi = (size_t)(my * im.ev[c] + v) * im.blk_xmax + (mx * im.eh[c] + h);
                     if (bi < nb) ((c == 0) ? blk_y : (c == 1) ? blk_cb : blk_cr)[bi] = x.css[c][v * 4 + h];
@@ -300,6 +347,7 @@ __global__ void __launch_bounds__(32) k_huff_exact(DevBatch b, int err_max)
             if (x.scan_end && x.scan_bad) stop = true;           // :3621-3625
         }
     }
+    if (!wr) return;
     x.res->scan_bad = x.scan_bad ? 1u : 0u; x.res->restart_read = x.restart_read; x.res->done = 1;
     x.res->end_pos = x.pos[0]; x.res->end_align = x.align;
     b.stats[(size_t)ii * 16 + 11] = (int32_t)x.restart_read;     // m_nRestartRead
@@ -326,10 +374,10 @@ __global__ void __launch_bounds__(256) k_exact_prepare(DevBatch b)
     for (uint32_t i = threadIdx.x; i < 2 * 4 * 17; i += blockDim.x) b.histo[(size_t)ii * 2 * 4 * 17 + i] = 0;
 }
 
-int js_launch_exact(const DevBatch& b, int err_max, cudaStream_t s)
+int js_launch_exact(const DevBatch& b, int err_max, const jsgpu_detail& dtl, jsgpu_detail_dump* dump, uint32_t* scratch_histo, cudaStream_t s)
 {
     if (b.nimg == 0) return 0;
     k_exact_prepare<<<b.nimg, 256, 0, s>>>(b);
-    k_huff_exact<<<b.nimg, 32, 0, s>>>(b, err_max);
+    k_huff_exact<<<b.nimg, 32, 0, s>>>(b, err_max, dtl, dump, scratch_histo);
     return 2;
 }

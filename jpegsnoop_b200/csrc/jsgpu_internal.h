@@ -178,7 +178,7 @@ int js_launch_build_color_tables(ColorTabs* t, cudaStream_t s);
 int js_upload_idct_constants(const IdctSym* host_sym, cudaStream_t s);
 int js_make_coef_tensor_map(void* out_tmap, void* coef, uint64_t rows);
 int js_launch_idct_tma(const DevBatch& b, const IdctSym* sym, const ColorTabs* ctab, const void* tmap_host, int sm_count, cudaStream_t s);
-int js_launch_exact(const DevBatch& b, int err_max, cudaStream_t s);       // damaged images, again, with the reference's semantics (jsgpu_exact.cu)
+int js_launch_exact(const DevBatch& b, int err_max, const jsgpu_detail& dtl, jsgpu_detail_dump* dump, uint32_t* scratch_histo, cudaStream_t s);       // damaged images, again, with the reference's semantics (jsgpu_exact.cu)
 int js_launch_export(const DevBatch& b, uint32_t image, int mode, uint8_t* out, uint64_t npx, int sm_count, cudaStream_t s);   // Export-to-TIFF sample array
 int js_launch_finalize(const DevBatch& b, cudaStream_t s);
 // CalcChannelPreviewFull with non-default settings: clipping/histogram conversion, channel selection, YCC shift (jsgpu_preview.cu)

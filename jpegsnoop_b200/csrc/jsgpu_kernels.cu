@@ -58,6 +58,8 @@ __global__ void __launch_bounds__(MS_THREADS) k_marker_scan(DevBatch b)
         for (int c = 0; c < 4; c++) {
             // FF bytes are rare (~1/200): test a whole word for "any byte == FF" first and only then look at its bytes
             const uint32_t ws[5] = {v[c].x, v[c].y, v[c].z, v[c].w, (c < 3) ? v[c < 3 ? c + 1 : 3].x : nextb};
+            // ... and a whole 16-byte group first: 9 in 10 hold no FF at all
+            if ((__vcmpeq4(v[c].x, 0xFFFFFFFFu) | __vcmpeq4(v[c].y, 0xFFFFFFFFu) | __vcmpeq4(v[c].z, 0xFFFFFFFFu) | __vcmpeq4(v[c].w, 0xFFFFFFFFu)) == 0) continue;
             #pragma unroll
             for (int wi = 0; wi < 4; wi++) {
                 const uint32_t w = ws[wi];
@@ -163,8 +165,13 @@ __global__ void __launch_bounds__(256) k_idct_simple(DevBatch b, const int32_t* 
         uint32_t px0 = mx * im.mcu_w + h * 8 + x * im.eh[c];
         uint32_t py0 = my * im.mcu_h + v * 8 + y * im.ev[c];
         int16_t* map = ((c == 0) ? b.pix_y : (c == 1) ? b.pix_cb : b.pix_cr) + im.pix_off;
+        // A component with 1 < H < Hmax (or V) replicates each of its blocks over 8*eh x 8*ev pixels but places them only 8 apart, so
+        // inside an MCU its blocks OVERLAP; the reference writes them one after the other (v outer, h inner, :3340-3400), the later
+        // block wins.  Here every pixel is written by exactly that block: the last one in (v,h) order that covers it.
         for (uint32_t iv = 0; iv < im.ev[c]; iv++) for (uint32_t ih = 0; ih < im.eh[c]; ih++) {
             uint32_t px = px0 + ih, py = py0 + iv;
+            const uint32_t dx = px - mx * im.mcu_w, dy = py - my * im.mcu_h;
+            if (h != min(im.H[c] - 1, dx >> 3) || v != min(im.V[c] - 1, dy >> 3)) continue;
             if (px < im.wp && py < im.hp) map[(size_t)py * im.wp + px] = (int16_t)out;
         }
     }

@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(32) k_preview_warn(DevBatch b, jsgpu_preview p
                         if (over ? (cur > 255) : (cur < 0)) {
                             if (nwarn < budget) {
                                 jsgpu_ycc_warn& w = o->warn[nwarn++];
-                                w.mcu_x = px / im.mcu_w; w.mcu_y = py / im.mcu_h; w.y = cy; w.cb = ccb; w.cr = ccr;
+                                w.mcu_x = px / im.mcu_w; w.mcu_y = py / im.mcu_h; w.y = cy; w.cb = ccb; w.cr = ccr; w.px = px; w.py = py;
                                 w.kind = (uint32_t)((k & ~1) + (over ? 1 : 0));                // clip[]: under, over per channel
                                 o->clip[w.kind]++;
                             }

@@ -107,6 +107,8 @@ class CimgDecode:
         shape = (30, 512, 4) if which else (90, 128, 4)
         return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=shape).copy()
 
+    def SetDetailVlc(self, detail, x=0, y=0, n=1): self.L.jsimg_SetDetailVlc(self.h, int(detail), x, y, n)
+
     def ExportTiff(self, path, mode=0):
         """Export-to-TIFF of the decoded image (mode 0 RGB 8-bit, 1 RGB 16-bit, 2 YCC 8-bit), JPEGsnoopDoc.cpp:2008-2193."""
         return bool(self.L.jsimg_ExportTiff(self.h, str(path).encode(), mode))

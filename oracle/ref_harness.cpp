@@ -62,6 +62,7 @@ void ref_config(int decode_ac,int histo_en,unsigned err_max) {
 void ref_config_histo(int histo_en,int statclip_en,int dump_histo_y) {
 	g_cfg.bHistoEn = histo_en!=0; g_cfg.bStatClipEn = statclip_en!=0; g_cfg.bDumpHistoY = dump_histo_y!=0;
 }
+void ref_SetDetailVlc(RefCtx* c,int d,unsigned x,unsigned y,unsigned n) { c->dec->SetDetailVlc(d!=0,x,y,n); }
 void ref_SetPreviewMode(RefCtx* c,unsigned m) { c->dec->SetPreviewMode(m); }
 void ref_SetPreviewYccOffset(RefCtx* c,unsigned mx,unsigned my,int y,int cb,int cr) { c->dec->SetPreviewYccOffset(mx,my,y,cb,cr); }
 void ref_GetStatClip(RefCtx* c,uint32_t* o /*[12]*/) { memcpy(o,&c->dec->m_sStatClip,12*sizeof(uint32_t)); }

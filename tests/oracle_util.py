@@ -105,6 +105,9 @@ class Oracle:
         assert self.kind != "port"
         self.lib.ref_config_histo(int(histo_en), int(statclip_en), int(dump_histo_y))
 
+    def set_detail_vlc(self, detail, x=0, y=0, n=1):
+        self.lib.ref_SetDetailVlc.argtypes = [C.c_void_p, C.c_int, C.c_uint, C.c_uint, C.c_uint]; self.lib.ref_SetDetailVlc(self.ctx, int(detail), x, y, n)
+
     def set_preview_mode(self, mode):
         self.lib.ref_SetPreviewMode.argtypes = [C.c_void_p, C.c_uint]; self.lib.ref_SetPreviewMode(self.ctx, mode)
 
