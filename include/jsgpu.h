@@ -274,6 +274,8 @@ typedef struct {
     uint32_t shift_mcu_x, shift_mcu_y;            /* m_nPreviewShiftMcuX/Y: applied to MCUs at or after this one (:4735) */
     uint32_t ycc_warn_budget;                     /* YCC_CLIP_REPORT_MAX - m_nWarnYccClipNum (ImgDecode.h:50): how many
                                                      "YCC Clipped" notes may still be issued (and counted, :4372-4378)  */
+    uint32_t detail_en;                           /* m_bDetailVlc: also keep the RGB of MCU (detail_mcu_x, detail_mcu_y) BEFORE the    */
+    uint32_t detail_mcu_x, detail_mcu_y;          /* channel selection, for the "Detailed IDCT Dump (RGB)" (ImgDecode.cpp:4757-4764)   */
     uint32_t pad;
 } jsgpu_preview;
 #define JSGPU_CC_HISTO_BINS  128    /* HISTO_BINS (ImgDecode.h:157)      */
@@ -294,6 +296,7 @@ typedef struct {
     uint32_t clip[12];
     uint32_t nwarn, pad;
     jsgpu_ycc_warn warn[JSGPU_MAX_YCC_WARN];      /* the notes, in the reference's (raster, Y/Cb/Cr) order             */
+    uint32_t detail_rgb[32][32];                  /* [row][column] inside the detail MCU: R << 16 | G << 8 | B         */
 } jsgpu_colour_stats;
 /* Recompute the DIB (and stats[] SUMY/AVGY) of every image of the current batch from its pixel maps with `p`; the statistics
  * of this pass are kept for jsgpu_batch_colour_stats.  jsgpu_set_preview makes jsgpu_batch_decode do so itself whenever the

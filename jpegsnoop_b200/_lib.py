@@ -69,7 +69,8 @@ class jsgpu_preview(C.Structure):
     """include/jsgpu.h: CalcChannelPreviewFull settings (histogram/clip conversion, preview mode, YCC shift)."""
     _fields_ = [("hist_en", C.c_int32), ("statclip_en", C.c_int32), ("mode", C.c_int32),
                 ("shift_y", C.c_int32), ("shift_cb", C.c_int32), ("shift_cr", C.c_int32),
-                ("shift_mcu_x", C.c_uint32), ("shift_mcu_y", C.c_uint32), ("ycc_warn_budget", C.c_uint32), ("pad", C.c_uint32)]
+                ("shift_mcu_x", C.c_uint32), ("shift_mcu_y", C.c_uint32), ("ycc_warn_budget", C.c_uint32),
+                ("detail_en", C.c_uint32), ("detail_mcu_x", C.c_uint32), ("detail_mcu_y", C.c_uint32), ("pad", C.c_uint32)]
 
 
 class jsgpu_ycc_warn(C.Structure):
@@ -79,7 +80,8 @@ class jsgpu_ycc_warn(C.Structure):
 class jsgpu_colour_stats(C.Structure):
     _fields_ = [("cc_histo", (C.c_uint32 * 128) * 3), ("y_histo", C.c_uint32 * 2048),
                 ("vmin", C.c_int32 * 12), ("vmax", C.c_int32 * 12), ("vsum", C.c_int64 * 12), ("count", C.c_uint64),
-                ("clip", C.c_uint32 * 12), ("nwarn", C.c_uint32), ("pad", C.c_uint32), ("warn", jsgpu_ycc_warn * 10)]
+                ("clip", C.c_uint32 * 12), ("nwarn", C.c_uint32), ("pad", C.c_uint32), ("warn", jsgpu_ycc_warn * 10),
+                ("detail_rgb", (C.c_uint32 * 32) * 32)]
 
 
 OUT_PIX_Y, OUT_PIX_CB, OUT_PIX_CR, OUT_DIB, OUT_BLK_Y, OUT_BLK_CB, OUT_BLK_CR, OUT_MCU_MAP, OUT_HISTO, OUT_STATS = range(10)

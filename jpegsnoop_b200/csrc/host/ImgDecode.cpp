@@ -601,6 +601,7 @@ void CimgDecode::PreviewSettings(jsgpu_preview& pv) const
     pv.shift_y = m_nPreviewShiftY; pv.shift_cb = m_nPreviewShiftCb; pv.shift_cr = m_nPreviewShiftCr;
     pv.shift_mcu_x = m_nPreviewShiftMcuX; pv.shift_mcu_y = m_nPreviewShiftMcuY;
     pv.ycc_warn_budget = m_nWarnYccClipNum < JSGPU_MAX_YCC_WARN ? JSGPU_MAX_YCC_WARN - m_nWarnYccClipNum : 0;
+    pv.detail_en = m_bDetailVlc ? 1u : 0u; pv.detail_mcu_x = m_nDetailVlcX; pv.detail_mcu_y = m_nDetailVlcY;
 }
 
 void CimgDecode::SetPreviewMode(unsigned nMode) { m_nPreviewMode = nMode; CalcChannelPreview(); }             // ref :631-639
@@ -683,27 +684,6 @@ void CimgDecode::LogYccNote(const jsgpu_ycc_warn& w)
         m_pLog->AddLineWarn(JS_LOGSTR(fmt("    Only reported first %u instances of this message...", (unsigned)JSGPU_MAX_YCC_WARN)));
 }
 
-// The RGB triplet CalcChannelPreviewFull prints in its detailed dump is the pixel BEFORE ChannelExtract (ref :4757-4764): the DIB
-// holds it in the RGB preview mode; in the other modes these few log values (one MCU) are recomputed from the pixel maps with the
-// reference's expressions (ConvertYCCtoRGBFastFloat :4086-4139 / ConvertYCCtoRGB :4229-4325) — a formatting aid, not a decode path.
-static void js_dump_pixel_rgb(int nY, int nCb, int nCr, bool bFull, unsigned& nR, unsigned& nG, unsigned& nB)
-{
-    const float fConstRed = 0.299f, fConstGreen = 0.587f, fConstBlue = 0.114f;
-    int y, cb, cr;
-    if (!bFull) {
-        y = nY >> 3; cb = nCb >> 3; cr = nCr >> 3;
-        y = y < -128 ? -128 : y > 127 ? 127 : y; cb = cb < -128 ? -128 : cb > 127 ? 127 : cb; cr = cr < -128 ? -128 : cr > 127 ? 127 : cr;
-    } else {
-        y = (nY + 1024) / 8; cb = (nCb + 1024) / 8; cr = (nCr + 1024) / 8;
-        y = (y < 0 ? 0 : y > 255 ? 255 : y) - 128; cb = (cb < 0 ? 0 : cb > 255 ? 255 : cb) - 128; cr = (cr < 0 ? 0 : cr > 255 ? 255 : cr) - 128;
-    }
-    float fR = cr * (2 - 2 * fConstRed) + y, fB = cb * (2 - 2 * fConstBlue) + y;
-    float fG = (y - fConstBlue * fB - fConstRed * fR) / fConstGreen;
-    fR += 128; fB += 128; fG += 128;
-    if (!bFull) { nR = fR < 0 ? 0 : fR > 255 ? 255 : (unsigned char)fR; nG = fG < 0 ? 0 : fG > 255 ? 255 : (unsigned char)fG; nB = fB < 0 ? 0 : fB > 255 ? 255 : (unsigned char)fB; }
-    else { const int r = (int)fR, g = (int)fG, b = (int)fB; nR = r < 0 ? 0 : r > 255 ? 255 : r; nG = g < 0 ? 0 : g > 255 ? 255 : g; nB = b < 0 ? 0 : b > 255 ? 255 : b; }
-}
-
 // ref :4683-4687, 4757-4780, 4797-4799: header, one line per pixel row of MCU (m_nDetailVlcX, m_nDetailVlcY) — written when the raster
 // walk leaves the MCU's columns, so a row at the right edge closes on the first pixel of the next row, and the last such row never
 // does — then a blank line.  The "YCC Clipped" notes of the same pass appear where the walk met them.
@@ -714,7 +694,9 @@ void CimgDecode::LogDetailRgb(const jsgpu_colour_stats* cs)
     const unsigned W = m_nImgSizeX, H = m_nImgSizeY;
     const unsigned nNotes = cs ? (cs->nwarn < JSGPU_MAX_YCC_WARN ? cs->nwarn : JSGPU_MAX_YCC_WARN) : 0;
     unsigned iNote = 0;
-    const bool bRgbInDib = (m_nPreviewMode <= 1 || m_nPreviewMode > 8), bFull = m_bHistEn || m_bStatClipEn;
+    // the triplet is the pixel BEFORE ChannelExtract (ref :4757-4764): the preview pass kept it for this MCU; without a pass (default
+    // settings) the DIB holds exactly it
+    const bool bRgbInDib = (cs == nullptr);
     const unsigned long long x0 = (unsigned long long)m_nDetailVlcX * m_nMcuWidth, x1 = x0 + m_nMcuWidth;
     const unsigned long long y0 = (unsigned long long)m_nDetailVlcY * m_nMcuHeight;
     if (x0 < W) for (unsigned long long py = y0; py < y0 + m_nMcuHeight && py < H; py++) {
@@ -725,13 +707,7 @@ void CimgDecode::LogDetailRgb(const jsgpu_colour_stats* cs)
         for (unsigned long long px = x0; px < x1 && px < W; px++) {
             unsigned nR, nG, nB;
             if (bRgbInDib) { const unsigned char* q = m_pDibBits + ((size_t)(H - 1 - py) * W + px) * 4; nR = q[2]; nG = q[1]; nB = q[0]; }
-            else {
-                const size_t i = (size_t)py * W + px;
-                int nY = m_pPixValY[i], nCb = m_pPixValCb ? m_pPixValCb[i] : 0, nCr = m_pPixValCr ? m_pPixValCr[i] : 0;
-                const unsigned nMcuInd = (unsigned)(py / m_nMcuHeight) * (W / m_nMcuWidth) + (unsigned)(px / m_nMcuWidth);
-                if (nMcuInd >= m_nPreviewShiftMcuY * (W / m_nMcuWidth) + m_nPreviewShiftMcuX) { nY += m_nPreviewShiftY; nCb += m_nPreviewShiftCb; nCr += m_nPreviewShiftCr; }
-                js_dump_pixel_rgb(nY, nCb, nCr, bFull, nR, nG, nB);
-            }
+            else { const unsigned v = cs->detail_rgb[py - y0][px - x0]; nR = (v >> 16) & 0xFF; nG = (v >> 8) & 0xFF; nB = v & 0xFF; }
             strLine += fmt("x%02X%02X%02X ", nR, nG, nB);
         }
         strLine += " ]";

@@ -66,7 +66,7 @@ struct jsgpu_ctx {
     bool host_delivered = false;             // the last decode went straight to host buffers: nothing to download from this context
     float ms[5] = {0, 0, 0, 0, 0};
     // CalcChannelPreviewFull settings (jsgpu_set_preview) and the statistics of the last preview pass
-    jsgpu_preview pv = {0, 0, 1, 0, 0, 0, 0, 0, JSGPU_MAX_YCC_WARN, 0};
+    jsgpu_preview pv = {0, 0, 1, 0, 0, 0, 0, 0, JSGPU_MAX_YCC_WARN, 0, 0, 0, 0};
     DevBuf d_cstats, d_rowclip; uint64_t rows_total = 0; uint32_t max_hp = 0; bool pv_done = false;
     // "Detailed Decode" request (jsgpu_set_detail) and the dump of the last decode
     jsgpu_detail dtl = {0, 0, 0, 0, 0}; DevBuf d_detail; bool dt_done = false;

@@ -139,14 +139,138 @@ __global__ void __launch_bounds__(128) k_unstuff(DevBatch b)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// unstuff, one LANE per restart interval (the default for short intervals): with a restart marker every few MCUs an interval is
+// ~300 bytes, i.e. 2-3 of k_unstuff's 128-byte rows plus as much fixed work per interval again (measured: 490 warp instructions per
+// interval, the kernel ALU-bound at 0.8 TB/s).  Here 32 intervals advance together, one 32-bit word per lane and step: the
+// stuffed-zero test, the PRMT that packs the kept bytes and a 64-bit shift register are per lane and branch-free, raw bytes come in
+// as 16-byte loads (one per four steps), output words go to a per-lane ring in shared memory and leave as 64-byte runs of 16-byte
+// stores.  Output format and side tables (seg_ulen / seg_uoff / seg_nstuff / seg_stuff / ovf_list) are exactly k_unstuff's.
+// ------------------------------------------------------------------------------------------------
+#define UN_WARPS 8
+#define UN_PITCH 36                         // words per lane row: a 32-word ring + 4 (keeps rows 16-byte aligned)
+__global__ void __launch_bounds__(UN_WARPS * 32) k_unstuff_lane(DevBatch b)
+{
+    __shared__ __align__(16) uint32_t s_rows[UN_WARPS][32][UN_PITCH];
+    __shared__ uint32_t s_selbe[16];        // PRMT selector: the kept bytes of a word, first one most significant, packed to the low end
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x < 16) {
+        uint32_t kept[4], n = 0, sel = 0;
+        for (uint32_t j = 0; j < 4; j++) if (!(threadIdx.x >> j & 1)) kept[n++] = j;
+        for (uint32_t i = 0; i < 4; i++) sel |= ((i < n) ? kept[n - 1 - i] : 4u) << (4 * i);       // result byte i = kept byte n-1-i; 4 = a zero byte
+        s_selbe[threadIdx.x] = sel;
+    }
+    __syncthreads();
+    uint32_t* const myrow = s_rows[wid][lane];
+    uint32_t (*const rows)[UN_PITCH] = s_rows[wid];
+    for (uint32_t ii = blockIdx.y; ii < b.nimg; ii += gridDim.y) {
+        const DevImage& im = b.img[ii];
+        if (!im.valid || im.psync) continue;
+        const uint32_t nseg = im.nseg, seg_first = im.seg_first;
+        const uint8_t* const scan = b.bits + im.scan_off;
+        for (uint32_t k0 = (blockIdx.x * UN_WARPS + wid) * 32; k0 < nseg; k0 += gridDim.x * UN_WARPS * 32) {
+            const uint32_t k = k0 + lane; const bool live = k < nseg;
+            const uint32_t gw = seg_first + (live ? k : k0);
+            const uint32_t s0 = b.seg_start[gw], len = live ? b.seg_end[gw] - s0 : 0u;
+            const uint64_t dst0 = im.ubits_off + (uint64_t)(s0 & ~15u) + (unsigned long long)JS_USLACK * (live ? k : k0);
+            const uint8_t* const seg = scan + s0;
+            const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(seg) & 15);
+            const uint4* const abase = reinterpret_cast<const uint4*>(seg - mis);
+            const uint32_t nwords = live ? (mis + len + 3) >> 2 : 0u;             // aligned words this lane walks
+            const uint32_t nmax = __reduce_max_sync(FULL, nwords);
+            unsigned long long acc = 0; uint32_t nacc = 0;                          // bytes waiting for a full output word (low end of acc)
+            uint32_t wr = 0, nstuff = 0, wpos = 0, fpos = 0, prevw = 0;
+            // flush: every lane whose ring holds `n` ready 16-byte pieces (0..4) gets them written behind what it has flushed so far
+            auto flush = [&](uint32_t n) {
+                const unsigned long long a = (unsigned long long)(uintptr_t)(b.ubits + dst0) + (unsigned long long)fpos * 4;
+                const uint32_t off = fpos & 31;
+                __syncwarp();
+                #pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    const int src = r * 8 + (lane >> 2); const uint32_t piece = lane & 3;
+                    const unsigned long long sa = __shfl_sync(FULL, a, src);
+                    const uint32_t sn = __shfl_sync(FULL, n, src), so = __shfl_sync(FULL, off, src);
+                    if (piece < sn) *reinterpret_cast<uint4*>(sa + piece * 16) = *reinterpret_cast<const uint4*>(&rows[src][(so + piece * 4) & 31]);
+                }
+                __syncwarp();
+                fpos += n * 4;
+            };
+            auto emit = [&](uint32_t w) { myrow[wpos & 31] = w; wpos++; };
+            uint4 nxt = make_uint4(0, 0, 0, 0);
+            if (nwords) nxt = __ldg(abase);
+            auto step = [&](uint32_t j, uint32_t word) {
+                if (j >= nwords) return;
+                const int rel0 = (int)(4 * j) - (int)mis;                           // interval offset of this word's byte 0
+                const int vlo = max(0, -rel0), vhi = min(4, (int)len - rel0);
+                const uint32_t vn = (vhi > vlo) ? (((1u << vhi) - 1u) & ~((1u << vlo) - 1u)) : 0u;         // bytes inside the interval
+                const uint32_t an = (rel0 <= 0 && rel0 > -4) ? (vn & ~(1u << (-rel0))) : vn;               // ... that may be a stuffed zero (not the first)
+                const uint32_t pw = __byte_perm(prevw, word, 0x6543);               // byte i = the byte before word's byte i
+                const uint32_t npw = ~pw;
+                const uint32_t z = ~(((word & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | word | 0x7F7F7F7Fu);          // byte == 0x00 (flag in bit 7)
+                const uint32_t f = ~(((npw & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | npw | 0x7F7F7F7Fu);            // previous byte == 0xFF
+                const uint32_t dn = ((((z & f) >> 7) * 0x00204081u) >> 21) & an;                           // stuffed zeros, as a nibble
+                const uint32_t rm = dn | (vn ^ 15u);
+                const uint32_t cnt = 4 - __popc(rm);
+                if (dn) {                                   // where bytes were dropped (MCU file map): unstuffed index of the FF before each
+                    uint32_t d = dn;
+                    while (d) {
+                        const uint32_t jj = __ffs(d) - 1; d &= d - 1;
+                        if (nstuff < JS_STUFF_LIST) b.seg_stuff[(size_t)gw * JS_STUFF_LIST + nstuff] = wr + __popc(~rm & ((1u << jj) - 1u)) - 1;
+                        nstuff++;
+                    }
+                }
+                acc = (acc << (8 * cnt)) | __byte_perm(word, 0, s_selbe[rm]);
+                nacc += cnt; wr += cnt;
+                if (nacc >= 4) { emit((uint32_t)(acc >> (8 * (nacc - 4)))); nacc -= 4; }
+                prevw = word;
+            };
+            for (uint32_t j = 0; j < nmax; j += 4) {
+                const uint4 cur = nxt;
+                if (j + 4 < nwords) nxt = __ldg(abase + (j >> 2) + 1);              // the next 16 bytes, one group ahead
+                if (j && (j & 15) == 0) flush((wpos - fpos >= 16) ? 4u : 0u);
+                step(j, cur.x); step(j + 1, cur.y); step(j + 2, cur.z); step(j + 3, cur.w);
+            }
+            flush((wpos - fpos >= 16) ? 4u : 0u);               // room for the padding: fewer than 16 words stay behind
+            // 16 bytes of 1-bits behind the data (the JPEG pad value; no valid code is all ones) so readers can over-fetch, zeros up
+            // to the next 16-byte boundary
+            if (live) {
+                const uint32_t total_words = ((wr + 16 + 15) & ~15u) >> 2;
+                uint32_t pad_left = 16;
+                while (wpos < total_words) {
+                    const uint32_t n = min(4u, pad_left);
+                    const uint32_t v = (n == 4) ? 0xFFFFFFFFu : (n == 0) ? 0u : (0xFFFFFFFFu << (8 * (4 - n)));
+                    pad_left -= n;
+                    acc = (acc << 32) | v; nacc += 4;
+                    emit((uint32_t)(acc >> (8 * (nacc - 4)))); nacc -= 4;
+                }
+            }
+            // what is left in the rings: at most 7 pieces per lane
+            { const uint32_t pend = (wpos - fpos) >> 2; flush(min(pend, 4u)); }
+            { const uint32_t pend = (wpos - fpos) >> 2; flush(min(pend, 4u)); }
+            if (live) {
+                b.seg_ulen[gw] = wr; b.seg_uoff[gw] = dst0; b.seg_nstuff[gw] = nstuff;
+                if (nstuff > JS_STUFF_LIST) b.ovf_list[atomicAdd(b.ovf_count, 1u)] = gw;     // rare: the MCU map of this interval needs the raw re-walk
+            }
+        }
+    }
+}
+
 int js_launch_unstuff(const DevBatch& b, cudaStream_t s)
 {
     if (b.nseg_total == 0 || b.max_nseg == 0) return 0;
-    dim3 grid((b.max_nseg + 3) / 4, b.nimg < 65535u ? b.nimg : 65535u);
-    // persistent over an image's intervals: enough CTAs to fill the GPU ~8x, at most one warp per interval
-    const uint32_t want = (148u * 16u * 8u + grid.y - 1) / grid.y;
+    static const int mode = [] { const char* e = getenv("JSGPU_UNSTUFF"); return e ? atoi(e) : 1; }();   // 0 = warp per interval (k_unstuff)
+    if (mode == 0 || b.max_nseg < 256) {           // few intervals per image: a warp per interval keeps more lanes busy
+        dim3 grid((b.max_nseg + 3) / 4, b.nimg < 65535u ? b.nimg : 65535u);
+        // persistent over an image's intervals: enough CTAs to fill the GPU ~8x, at most one warp per interval
+        const uint32_t want = (148u * 16u * 8u + grid.y - 1) / grid.y;
+        if (grid.x > want) grid.x = want < 1 ? 1 : want;
+        k_unstuff<<<grid, 128, 0, s>>>(b);
+        return 1;
+    }
+    dim3 grid((b.max_nseg + UN_WARPS * 32 - 1) / (UN_WARPS * 32), b.nimg < 65535u ? b.nimg : 65535u);
+    const uint32_t want = (148u * 8u * 4u + grid.y - 1) / grid.y;
     if (grid.x > want) grid.x = want < 1 ? 1 : want;
-    k_unstuff<<<grid, 128, 0, s>>>(b);
+    k_unstuff_lane<<<grid, UN_WARPS * 32, 0, s>>>(b);
     return 1;
 }
 

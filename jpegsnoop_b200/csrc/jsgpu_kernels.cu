@@ -58,8 +58,6 @@ __global__ void __launch_bounds__(MS_THREADS) k_marker_scan(DevBatch b)
         for (int c = 0; c < 4; c++) {
             // FF bytes are rare (~1/200): test a whole word for "any byte == FF" first and only then look at its bytes
             const uint32_t ws[5] = {v[c].x, v[c].y, v[c].z, v[c].w, (c < 3) ? v[c < 3 ? c + 1 : 3].x : nextb};
-            // ... and a whole 16-byte group first: 9 in 10 hold no FF at all
-            if ((__vcmpeq4(v[c].x, 0xFFFFFFFFu) | __vcmpeq4(v[c].y, 0xFFFFFFFFu) | __vcmpeq4(v[c].z, 0xFFFFFFFFu) | __vcmpeq4(v[c].w, 0xFFFFFFFFu)) == 0) continue;
             #pragma unroll
             for (int wi = 0; wi < 4; wi++) {
                 const uint32_t w = ws[wi];

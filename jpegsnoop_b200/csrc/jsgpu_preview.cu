@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(PV_THREADS) k_preview(DevBatch b, jsgpu_previe
             short4 vb = make_short4(0, 0, 0, 0), vr = vb;
             if (im.ns == 3) { vb = *reinterpret_cast<const short4*>(b.pix_cb + row + px); vr = *reinterpret_cast<const short4*>(b.pix_cr + row + px); }
             const bool sh_on = pv_shifted(im, pv, px, py);
+            const bool det = pv.detail_en && px / im.mcu_w == pv.detail_mcu_x && py / im.mcu_h == pv.detail_mcu_y;
             const int sy = sh_on ? pv.shift_y : 0, sb = sh_on ? pv.shift_cb : 0, sr = sh_on ? pv.shift_cr : 0;
             const int y4[4] = { vy.x, vy.y, vy.z, vy.w }, b4[4] = { vb.x, vb.y, vb.z, vb.w }, r4[4] = { vr.x, vr.y, vr.z, vr.w };
             uint32_t o[4];
@@ -139,6 +140,7 @@ __global__ void __launch_bounds__(PV_THREADS) k_preview(DevBatch b, jsgpu_previe
                 } else pv_fast(p);
                 sum_fy += p.fy;
                 o[q] = pv_extract(pv.mode, p);
+                if (det) st[blockIdx.y].detail_rgb[py - pv.detail_mcu_y * im.mcu_h][px + q - pv.detail_mcu_x * im.mcu_w] = (p.fr << 16) | (p.fg << 8) | p.fb;   // sPixSrc.nFinalR/G/B (:4763)
             }
             drow[px >> 2] = make_uint4(o[0], o[1], o[2], o[3]);
         }

@@ -1,17 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_detail.py -q 2>&1 | tail -n 25
-timeout 900 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "unusual" 2>&1 | tail -n 12
-PYTHONPATH=/root/repo:/root/repo/tests python - <<'P'
-import numpy as np, jpeg_cases as JC
-from oracle_util import Oracle
-from jpegsnoop_b200 import CimgDecode
-orc=Oracle("ref_fixed"); dec=CimgDecode()
-for name,j in JC.mini_cases()[5:]:
-    want=orc.decode(j); got=dec.decode(j); bad=JC.compare(want,got)
-    print(name, bad)
-    for k in ("pix_cb","pix_cr"):
-        a=getattr(want,k); b=getattr(got,k)
-        if a is not None and not np.array_equal(a,b):
-            ys,xs=np.nonzero(a!=b); print("   ",k,len(ys),"cols mod mcu", sorted(set((xs%int(want.geom[0])).tolist()))[:40], "rows mod", sorted(set((ys%int(want.geom[1])).tolist()))[:40])
-P
+timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -n 8
+(timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/r2e_launches_cfg2_bench.csv python bench.py --configs none --no-e2e --no-cpu --steps 2 --warmup 1 > gpurun_out/ncu_a.log 2>&1)
+(timeout 600 ncu --set full --clock-control none -c 12 -o gpurun_out/r2e_cfg2_full -f python bench.py --configs none --no-e2e --no-cpu --steps 1 --warmup 0 > gpurun_out/ncu_b.log 2>&1)
+(timeout 400 ncu --set full --clock-control none -k regex:k_preview -c 4 -o gpurun_out/r2e_preview -f python bench.py --configs none --no-e2e --no-cpu --steps 1 --warmup 0 > gpurun_out/ncu_c.log 2>&1)
+(timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/r2e_launches_cfg5.csv python bench.py --config cfg5 --configs none --no-e2e --no-cpu --steps 1 --warmup 1 > gpurun_out/ncu_d.log 2>&1)
+ls -la gpurun_out/*.ncu-rep gpurun_out/r2e_*.csv
+tail -n 2 gpurun_out/ncu_b.log | cut -c1-200
