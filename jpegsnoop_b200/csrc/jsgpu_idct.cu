@@ -35,6 +35,9 @@
 #ifndef IDCT_MIN_CTAS
 #define IDCT_MIN_CTAS 5
 #endif
+#ifndef IDCT_STAGE
+#define IDCT_STAGE 0           // 1: the next tile's coefficient rows are copied into shared memory with cp.async while this tile is in phase 2 (measured SLOWER: 7.11 vs 6.51 ms, profiles/r2_k2_variants.md)
+#endif
 #ifndef IDCT_PREFETCH
 #define IDCT_PREFETCH 0        // 1: the next tile's coefficient rows are requested into registers before phase 2 (32 registers)
 #endif
@@ -100,6 +103,34 @@ __global__ void __launch_bounds__(IDCT_THREADS, IDCT_MIN_CTAS) k_idct_tile(DevBa
     // coefficient rows and output rows advance sequentially).
     const uint32_t t_begin = (uint32_t)(((unsigned long long)tile_count * blockIdx.x) / gridDim.x);
     const uint32_t t_end = (uint32_t)(((unsigned long long)tile_count * (blockIdx.x + 1)) / gridDim.x);
+#if IDCT_STAGE
+    // Shared-memory staging of the coefficient rows (no registers, unlike IDCT_PREFETCH): every thread copies, with cp.async, exactly
+    // the rows it will itself read in phase 1 of the next tile — block idx of the tile -> 128 bytes at idx*128, 16-byte chunk k at
+    // position k ^ (idx & 7) so that the 32 lanes' LDS.128 fall into different banks — so no barrier is needed, only its own
+    // cp.async.wait_group; rows of blocks that do not exist are zero-filled.
+    uint8_t* const stage = planes0 + 2 * (size_t)b.tile_plane_bytes;
+    const uint32_t stage_blocks = ((b.tile_plane_bytes >> 7) + 31u) & ~31u;        // whole 32-block groups: phase 1 reads a row for every lane
+    auto stage_tile = [&](uint32_t tnext, uint32_t img_now) {
+        const uint4 nt = b.tiles[tile_first + tnext];
+        for (uint32_t g = wid; g * 32 < stage_blocks; g += (blockDim.x >> 5)) {
+            const uint32_t idx = g * 32 + lane;
+            size_t nrow;
+            const bool ok = (nt.x == img_now) ? tile_block_row(G, nt, idx, nrow) : tile_block_row(b.img[nt.x], nt, idx, nrow);
+            uint8_t* const dst = stage + (size_t)idx * 128;
+            if (ok) {
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(b.coef + nrow * 64);
+                #pragma unroll
+                for (int k = 0; k < 8; k++)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(dst + ((k ^ (idx & 7)) << 4))), "l"(src + k * 16) : "memory");
+            } else {
+                #pragma unroll
+                for (int k = 0; k < 8; k++) *reinterpret_cast<uint4*>(dst + k * 16) = make_uint4(0, 0, 0, 0);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (t_begin < t_end) stage_tile(t_begin, 0xffffffffu);
+#endif
 #if IDCT_PREFETCH
     uint4 nx4[8];
     #pragma unroll
@@ -144,6 +175,9 @@ __global__ void __launch_bounds__(IDCT_THREADS, IDCT_MIN_CTAS) k_idct_tile(DevBa
         const uint32_t ppitch0 = hu0 * 16, ppitch1 = hu1 * 16, ppitch2 = hu2 * 16;
         const uint32_t nblk = cnt0 + cnt1 + cnt2;
         // ---------------- phase 1: one block per lane ----------------
+#if IDCT_STAGE
+        asm volatile("cp.async.wait_group 0;" ::: "memory");       // this thread's own copies of this tile's rows have landed
+#endif
         for (uint32_t g = wid; g * 32 < nblk; g += (blockDim.x >> 5)) {
             uint32_t i = g * 32 + lane;
             uint32_t c = 0;
@@ -161,6 +195,14 @@ __global__ void __launch_bounds__(IDCT_THREADS, IDCT_MIN_CTAS) k_idct_tile(DevBa
             if (g == wid) {                                        // prefetched while the previous tile was in phase 2
                 #pragma unroll
                 for (int k = 0; k < 8; k++) cw4[k] = nx4[k];
+            } else
+#endif
+#if IDCT_STAGE
+            if (true) {
+                const uint32_t idx = g * 32 + lane;
+                const uint8_t* const srow = stage + (size_t)idx * 128;
+                #pragma unroll
+                for (int k = 0; k < 8; k++) cw4[k] = *reinterpret_cast<const uint4*>(srow + ((k ^ (idx & 7)) << 4));
             } else
 #endif
             if (valid) {
@@ -245,6 +287,9 @@ __global__ void __launch_bounds__(IDCT_THREADS, IDCT_MIN_CTAS) k_idct_tile(DevBa
         }
 #undef JS_COEF
         __syncthreads();
+#if IDCT_STAGE
+        if (ti + 1 < t_end) stage_tile(ti + 1, tile.x);            // lands during phase 2
+#endif
 #if IDCT_PREFETCH
         #pragma unroll
         for (int k = 0; k < 8; k++) nx4[k] = make_uint4(0, 0, 0, 0);
@@ -329,7 +374,7 @@ static int launch_tab(const DevBatch& b, const IdctSym* sym, const ColorTabs* ct
     static bool attr_set_dev[JS_MAX_DEVICES] = {};       // the attribute is per device
     int dev_ = 0; cudaGetDevice(&dev_); if (dev_ < 0 || dev_ >= JS_MAX_DEVICES) dev_ = 0;
     bool& attr_set = attr_set_dev[dev_];
-    const int mx = (int)(sizeof(Idct2Tables) + sizeof(TileGeo) + 48 * 1024);
+    const int mx = (int)(sizeof(Idct2Tables) + sizeof(TileGeo) + 48 * 1024 + (IDCT_STAGE ? 24 * 1024 : 0));
     if (!attr_set) {
         cudaFuncSetAttribute(k_idct_tile<TAB, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         cudaFuncSetAttribute(k_idct_tile<TAB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
@@ -342,7 +387,7 @@ static int launch_tab(const DevBatch& b, const IdctSym* sym, const ColorTabs* ct
 #if IDCT_FORCE_WARPS
     threads = 32 * IDCT_FORCE_WARPS;          // extra warps only take part in phase 2 (its row groups split evenly over 4 warps at 4:2:0)
 #endif
-    const size_t smem = sizeof(Idct2Tables) + sizeof(TileGeo) + 2 * (size_t)b.tile_plane_bytes;
+    const size_t smem = sizeof(Idct2Tables) + sizeof(TileGeo) + 2 * (size_t)b.tile_plane_bytes + (IDCT_STAGE ? (size_t)(((b.tile_plane_bytes >> 7) + 31u) & ~31u) * 128 : 0);
     int n = 0;
     for (int cls = 0; cls < 3; cls++) {
         const uint32_t cnt = b.tcls_count[cls];
