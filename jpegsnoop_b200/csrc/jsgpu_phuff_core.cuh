@@ -152,19 +152,20 @@ JS_HD unsigned long long ph_run(const PhTabs& t, const uint32_t* words, uint32_t
         if (e & 0x8000) e = t.lutb[off + JS_LUT_SIZE + (e & 0x7FFF) + ((top >> 16) & ((1u << JS_LUT2_BITS) - 1))];
         if (e == 0) { s.advance(pos, pos + 1); pos += 1; continue; }           // rare (see above)
         const uint32_t len = e >> 8, size = e & 15, run = (e >> 4) & 15;
-        if (COUNT) {
-            if (isdc && blk == 0) {                                  // an MCU starts here
+        if (COUNT && isdc) {                                         // one symbol in ~20: worth a branch, the lanes rejoin at once
+            if (blk == 0) {                                          // an MCU starts here
                 if (o.nmcu == 0) { o.fpos = pos; o.bef0 = o.tot0; o.bef1 = o.tot1; o.bef2 = o.tot2; }
                 o.nmcu++;
             }
-            const uint32_t tv = s.peek_at(pos, pos + len);         // value bits follow the code
-            const uint32_t v = size ? (tv >> (32 - size)) : 0u;
-            int val = (int)v - ((((int)~tv) >> 31) & (int)((1u << size) - 1u));      // T.81 F.12 EXTEND (HuffmanDc2Signed, :859-866)
-            if (t.pshift) val /= (1 << t.pshift);
             const uint32_t q = t.qz[c * 80 + run];
-            // a DC symbol whose coefficient lands in natural position 0 is a DC difference (dequantised, short like the reference's)
-            const int d = (isdc && (q >> 16) == 0) ? (int)(short)(val * (int)(q & 0xFFFF)) : 0;
-            o.tot0 += (c == 0) ? d : 0; o.tot1 += (c == 1) ? d : 0; o.tot2 += (c == 2) ? d : 0;
+            if ((q >> 16) == 0) {        // a DC symbol whose coefficient lands in natural position 0 is a DC difference
+                const uint32_t tv = s.peek_at(pos, pos + len);     // value bits follow the code
+                const uint32_t v = size ? (tv >> (32 - size)) : 0u;
+                int val = (int)v - ((((int)~tv) >> 31) & (int)((1u << size) - 1u));      // T.81 F.12 EXTEND (HuffmanDc2Signed, :859-866)
+                if (t.pshift) val /= (1 << t.pshift);
+                const int d = (int)(short)(val * (int)(q & 0xFFFF));                      // dequantised, short like the reference's
+                o.tot0 += (c == 0) ? d : 0; o.tot1 += (c == 1) ? d : 0; o.tot2 += (c == 2) ? d : 0;
+            }
         }
         const uint32_t npos = pos + len + size;
         s.advance(pos, npos); pos = npos;
