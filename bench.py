@@ -240,6 +240,18 @@ def run_config(cfg, args, env, orc, kind, threads, steps, warmup, verify_budget_
            "mismatching_images": bad_all, "checked_by": "device checksums of all output buffers vs " + ("oracle/_ref (compiled reference) checksums" if kind == "reference" else "C port, spot check"),
            "decoder_status_words": status, "gpu_launches_per_step": launches, "gen_s": round(t_gen, 1),
            "cpu_reference_mpix_s": round(cpu_px / cpu_s / 1e6, 2) if cpu_s > 0 else None, "cpu_threads": threads, "cpu_err_lines": cpu_errs}
+    if cfg == args.config:
+        # K2 with the device to itself: in the product the MCU-file-map kernels run on a second stream NEXT TO it (the step is
+        # shorter, K2's own span a little longer); without the map they are not launched.  Outside the timed region.
+        try:
+            bd.set_options(want_mcu_map=0)
+            for _ in range(3):
+                bd.decode()
+            bd.sync()
+            rec["k2_alone_ms"] = round(float(bd.stage_ms()[2]), 3)
+            bd.set_options(want_mcu_map=1); bd.decode(); bd.sync()
+        except Exception as e:
+            rec["k2_alone_ms"] = None; rec["k2_alone_error"] = str(e)[:200]
     if cfg == "cfg2" and not getattr(args, "no_preview", False):
         # the channel-preview pass over the resident batch, after the verification above: histogram/clip
         # statistics conversion, then a plain luminance preview; 6 B read + 4 B written per padded pixel
@@ -544,6 +556,11 @@ def main():
                 "algorithmic_bytes_per_padded_px": round(bpp_img, 3), "ms_per_launch": round(idct_ms, 3),
                 "stage_ms": head["stage_ms"], "huffman_achieved_gbs": round(huff_gbs, 1),
                 "whole_step_frac_of_hbm_peak": round((bits_size + npad * (bpp_img - 10.0) + ctx["alg_b"]) / (float(sm[4]) / 1e3) / 1e9 / peak, 4)}
+        if head.get("k2_alone_ms"):
+            roof["ms_per_launch_kernel_alone"] = head["k2_alone_ms"]
+            roof["frac_kernel_alone"] = round(ctx["alg_b"] / (head["k2_alone_ms"] / 1e3) / 1e9 / peak, 4)
+            roof["note"] = ("`frac` is K2's span inside the timed steps, where the MCU-file-map kernels share the device with it on a second stream; "
+                            "`frac_kernel_alone` is the same kernel without them (want_mcu_map=0, measured after the timed region)")
         if traffic_rw:        # read-only and write-only rates of the same launch
             roof["dram_read_gbs"] = round(traffic_rw[0] / (idct_ms / 1e3), 1); roof["dram_write_gbs"] = round(traffic_rw[1] / (idct_ms / 1e3), 1)
         line = {"metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -35,6 +35,8 @@ struct DevBuf {
 struct jsgpu_ctx {
     int device = 0, sm_count = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;          // MCU-file-map kernels run here, next to the IDCT kernel
+    cudaEvent_t evx[2] = {};
     cudaEvent_t ev[6] = {};
     cudaEvent_t tev[2] = {};
     std::string err;
@@ -130,6 +132,8 @@ int jsgpu_init(int device, jsgpu_ctx** out)
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return JSGPU_ENODEV; }
     ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return JSGPU_ECUDA; }
+    if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess) { cudaStreamDestroy(ctx->stream); delete ctx; return JSGPU_ECUDA; }
+    for (auto& ev : ctx->evx) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     for (auto& ev : ctx->ev) cudaEventCreate(&ev);
     for (auto& ev : ctx->tev) cudaEventCreate(&ev);
     memset(&ctx->opt, 0, sizeof ctx->opt);
@@ -151,6 +155,8 @@ void jsgpu_free(jsgpu_ctx* ctx)
     for (auto* b : bufs) b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->tev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->evx) if (ev) cudaEventDestroy(ev);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -651,6 +657,17 @@ int jsgpu_batch_decode(jsgpu_ctx* ctx)
         launches += js_launch_exact(b, ctx->opt.scan_err_max > 0 ? ctx->opt.scan_err_max : 20, dtl, dump,
                                     dump ? (uint32_t*)((uint8_t*)dump + sizeof(jsgpu_detail_dump)) : nullptr, s);
     }
+    // The MCU file map depends on the Huffman stage only: its kernels run on a second stream while the IDCT kernel has the device
+    // (they are short and latency-bound, 0.37 ms serial on cfg2); the scalar statistics below wait for both.
+    bool maps_forked = false;
+    if (ctx->opt.want_mcu_map) {
+        CK(cudaEventRecord(ctx->evx[0], s));
+        CK(cudaStreamWaitEvent(ctx->stream2, ctx->evx[0], 0));
+        launches += js_launch_finalize_maps(b, ctx->stream2);
+        launches += js_launch_finalize_emptied(b, ctx->stream2);
+        CK(cudaEventRecord(ctx->evx[1], ctx->stream2));
+        maps_forked = true;
+    }
     CK(cudaEventRecord(ctx->ev[2], s));
     {
         // fused tile kernel: integer IDCT, standard sampling layouts, decomposable table; everything
@@ -669,12 +686,8 @@ int jsgpu_batch_decode(jsgpu_ctx* ctx)
         }
     }
     CK(cudaEventRecord(ctx->ev[3], s));
-    {
-        DevBatch bf = b;
-        if (!ctx->opt.want_mcu_map) bf.mcu_map = nullptr;
-        launches += js_launch_finalize(bf, s);
-        if (ctx->opt.want_mcu_map) launches += js_launch_finalize_emptied(bf, s);
-    }
+    if (maps_forked) CK(cudaStreamWaitEvent(s, ctx->evx[1], 0));
+    launches += js_launch_finalize_stats(b, s);
     // CalcChannelPreview() with non-default settings (ImgDecode.cpp:3641-3643): the DIB again, from the pixel maps
     ctx->pv_done = false;
     if (!preview_is_default(ctx->pv)) {

@@ -180,7 +180,8 @@ int js_make_coef_tensor_map(void* out_tmap, void* coef, uint64_t rows);
 int js_launch_idct_tma(const DevBatch& b, const IdctSym* sym, const ColorTabs* ctab, const void* tmap_host, int sm_count, cudaStream_t s);
 int js_launch_exact(const DevBatch& b, int err_max, const jsgpu_detail& dtl, jsgpu_detail_dump* dump, uint32_t* scratch_histo, cudaStream_t s);       // damaged images, again, with the reference's semantics (jsgpu_exact.cu)
 int js_launch_export(const DevBatch& b, uint32_t image, int mode, uint8_t* out, uint64_t npx, int sm_count, cudaStream_t s);   // Export-to-TIFF sample array
-int js_launch_finalize(const DevBatch& b, cudaStream_t s);
+int js_launch_finalize_maps(const DevBatch& b, cudaStream_t s);     // MCU file map (independent of the IDCT)
+int js_launch_finalize_stats(const DevBatch& b, cudaStream_t s);    // brightest pixel / average luma / end-of-scan position (after the IDCT)
 // CalcChannelPreviewFull with non-default settings: clipping/histogram conversion, channel selection, YCC shift (jsgpu_preview.cu)
 int js_launch_preview(const DevBatch& b, const jsgpu_preview& pv, jsgpu_colour_stats* st, uint32_t* rowclip, uint64_t rows_total,
                       uint32_t max_hp, int sm_count, cudaStream_t s);

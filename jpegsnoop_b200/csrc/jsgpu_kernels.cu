@@ -385,17 +385,21 @@ __global__ void __launch_bounds__(256) k_finalize_mcumap_fast(DevBatch b)
     }
 }
 
-int js_launch_finalize(const DevBatch& b, cudaStream_t s)
+// The MCU file map needs nothing from the IDCT: its kernels go on a second stream next to K2 (jsgpu_api.cu), only the scalar
+// statistics (brightest pixel, luma sum) wait for it.
+int js_launch_finalize_maps(const DevBatch& b, cudaStream_t s)
+{
+    if (b.nimg == 0 || !b.mcu_map || !b.nseg_total) return 0;
+    dim3 grid(32, b.nimg);
+    k_finalize_mcumap_fast<<<grid, 256, 0, s>>>(b);
+    k_finalize_mcumap<<<std::min<uint32_t>((b.nseg_total + 3) / 4, 148 * 8), 128, 0, s>>>(b);      // walks the overflow list only
+    return 2;
+}
+int js_launch_finalize_stats(const DevBatch& b, cudaStream_t s)
 {
     if (b.nimg == 0) return 0;
-    int n = 0;
-    k_finalize_stats<<<(b.nimg + 127) / 128, 128, 0, s>>>(b); n++;
-    if (b.mcu_map && b.nseg_total) {
-        dim3 grid(32, b.nimg);
-        k_finalize_mcumap_fast<<<grid, 256, 0, s>>>(b); n++;
-        k_finalize_mcumap<<<std::min<uint32_t>((b.nseg_total + 3) / 4, 148 * 8), 128, 0, s>>>(b); n++;      // walks the overflow list only
-    }
-    return n;
+    k_finalize_stats<<<(b.nimg + 127) / 128, 128, 0, s>>>(b);
+    return 1;
 }
 
 // ------------------------------------------------------------------------------------------------
