@@ -262,13 +262,13 @@ int js_launch_unstuff(const DevBatch& b, cudaStream_t s)
     if (mode == 0 || b.max_nseg < 256) {           // few intervals per image: a warp per interval keeps more lanes busy
         dim3 grid((b.max_nseg + 3) / 4, b.nimg < 65535u ? b.nimg : 65535u);
         // persistent over an image's intervals: enough CTAs to fill the GPU ~8x, at most one warp per interval
-        const uint32_t want = (148u * 16u * 8u + grid.y - 1) / grid.y;
+        const uint32_t want = (JS_B200_SMS * 16u * 8u + grid.y - 1) / grid.y;
         if (grid.x > want) grid.x = want < 1 ? 1 : want;
         k_unstuff<<<grid, 128, 0, s>>>(b);
         return 1;
     }
     dim3 grid((b.max_nseg + UN_WARPS * 32 - 1) / (UN_WARPS * 32), b.nimg < 65535u ? b.nimg : 65535u);
-    const uint32_t want = (148u * 8u * 4u + grid.y - 1) / grid.y;
+    const uint32_t want = (JS_B200_SMS * 8u * 4u + grid.y - 1) / grid.y;
     if (grid.x > want) grid.x = want < 1 ? 1 : want;
     k_unstuff_lane<<<grid, UN_WARPS * 32, 0, s>>>(b);
     return 1;
@@ -457,7 +457,7 @@ int js_launch_unstuff_long(const DevBatch& b, uint32_t max_cs, cudaStream_t s)
 {
     if (max_cs == 0) return 0;
     dim3 grid((max_cs + UL_WARPS - 1) / UL_WARPS, b.nimg < 65535u ? b.nimg : 65535u);
-    const uint32_t want = (148u * 8u * 4u + grid.y - 1) / grid.y;
+    const uint32_t want = (JS_B200_SMS * 8u * 4u + grid.y - 1) / grid.y;
     if (grid.x > want) grid.x = want < 1 ? 1 : want;
     k_unstuff_count<<<grid, UL_WARPS * 32, 0, s>>>(b);
     k_unstuff_scan<<<b.nimg < 65535u ? b.nimg : 65535u, 128, 0, s>>>(b);

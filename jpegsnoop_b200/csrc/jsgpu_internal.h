@@ -13,6 +13,7 @@
 #define JS_USLACK     48                 // bytes of slack per restart interval in the unstuffed pool (16 pad + flush rounding + alignment)
 #define JS_STUFF_LIST 6                  // stuffed-byte positions recorded per restart interval
 #define JS_MAX_DEVICES 64                // per-device "function attribute set" flags of the launchers
+#define JS_B200_SMS   148u               // grid-size heuristics of the small helper kernels (the main kernels take the device's SM count)
 #define JS_NSLOT      8                  // (class,Th) pairs: slot = class*4 + Th
 
 // serial reference-semantics path (jsgpu_exact.cu): per-image result = the public jsgpu_scan_errors

@@ -392,7 +392,7 @@ int js_launch_finalize_maps(const DevBatch& b, cudaStream_t s)
     if (b.nimg == 0 || !b.mcu_map || !b.nseg_total) return 0;
     dim3 grid(32, b.nimg);
     k_finalize_mcumap_fast<<<grid, 256, 0, s>>>(b);
-    k_finalize_mcumap<<<std::min<uint32_t>((b.nseg_total + 3) / 4, 148 * 8), 128, 0, s>>>(b);      // walks the overflow list only
+    k_finalize_mcumap<<<std::min<uint32_t>((b.nseg_total + 3) / 4, JS_B200_SMS * 8), 128, 0, s>>>(b);      // walks the overflow list only
     return 2;
 }
 int js_launch_finalize_stats(const DevBatch& b, cudaStream_t s)
