@@ -34,6 +34,22 @@ def test_struct_layouts_match_the_header(built):
     assert C.sizeof(B.jsgpu_image_desc) == 136 and C.sizeof(B.jsgpu_image_layout) == 72 and C.sizeof(B.jsgpu_options) == 32
 
 
+def test_ctypes_structs_have_the_compilers_sizes(built, tmp_path):
+    """The ctypes mirrors of the larger C-ABI structures against what gcc makes of include/jsgpu.h."""
+    import subprocess
+    from jpegsnoop_b200 import _lib as B
+    names = ["jsgpu_tables", "jsgpu_image_desc", "jsgpu_image_layout", "jsgpu_options", "jsgpu_pools", "jsgpu_host_outputs",
+             "jsgpu_scan_errors", "jsgpu_preview", "jsgpu_ycc_warn", "jsgpu_colour_stats"]
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "jsgpu.h"\nint main(void){' +
+                   "".join('printf("%s %%zu\\n", sizeof(%s));' % (n, n) for n in names) + "return 0;}\n")
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for n in names:
+        assert C.sizeof(getattr(B, n)) == int(out[n]), (n, C.sizeof(getattr(B, n)), out[n])
+
+
 def _no_gpu():
     try:
         import torch
