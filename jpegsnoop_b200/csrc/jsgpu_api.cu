@@ -69,6 +69,7 @@ struct jsgpu_ctx {
     float ms[5] = {0, 0, 0, 0, 0};
     // CalcChannelPreviewFull settings (jsgpu_set_preview) and the statistics of the last preview pass
     jsgpu_preview pv = {0, 0, 1, 0, 0, 0, 0, 0, JSGPU_MAX_YCC_WARN, 0, 0, 0, 0};
+    DevBuf d_mc; uint32_t mc_total = 0;      // marker-scan chunk arrays
     DevBuf d_cstats, d_rowclip; uint64_t rows_total = 0; uint32_t max_hp = 0; bool pv_done = false;
     // "Detailed Decode" request (jsgpu_set_detail) and the dump of the last decode
     jsgpu_detail dtl = {0, 0, 0, 0, 0}; DevBuf d_detail; bool dt_done = false;
@@ -150,7 +151,7 @@ void jsgpu_free(jsgpu_ctx* ctx)
     ctx->kids.clear();
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = { &ctx->d_ctab, &ctx->d_li, &ctx->d_lf, &ctx->d_sym, &ctx->d_tables, &ctx->d_img, &ctx->d_items, &ctx->d_litems, &ctx->d_tiles, &ctx->d_ubits, &ctx->d_seg64, &ctx->d_ph, &ctx->d_rowtab, &ctx->d_ex, &ctx->d_cstats, &ctx->d_rowclip, &ctx->d_detail, &ctx->d_bits, &ctx->d_seg,
+    DevBuf* bufs[] = { &ctx->d_ctab, &ctx->d_li, &ctx->d_lf, &ctx->d_sym, &ctx->d_tables, &ctx->d_img, &ctx->d_items, &ctx->d_litems, &ctx->d_tiles, &ctx->d_ubits, &ctx->d_seg64, &ctx->d_ph, &ctx->d_rowtab, &ctx->d_ex, &ctx->d_cstats, &ctx->d_rowclip, &ctx->d_detail, &ctx->d_mc, &ctx->d_bits, &ctx->d_seg,
                        &ctx->d_coef, &ctx->d_mcubits, &ctx->d_pix, &ctx->d_dib, &ctx->d_blk, &ctx->d_mcumap, &ctx->d_histo, &ctx->d_stats, &ctx->d_misc };
     for (auto* b : bufs) b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -372,6 +373,7 @@ int jsgpu_batch_begin(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, 
     uint32_t seg = 0, n_std = 0, n_nonstd = 0, plane_bytes = 0, seg_np = 0, n_psync = 0;
     uint64_t pht = 0, rtt = 0, cst = 0; uint32_t max_cs = 0;
     uint64_t rowt = 0; uint32_t max_hp = 0;
+    std::vector<uint32_t> mc_img;              // image of every 4096-byte chunk (marker scan)
     std::vector<uint2> items, litems, items_np, litems_np, vitems;
     std::vector<uint4> tiles, tcls[3];
     for (uint32_t i = 0; i < n; i++) {
@@ -391,6 +393,8 @@ int jsgpu_batch_begin(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, 
         for (uint32_t c = 0; c < im.ns; c++) { im.coef_row[c] = rows; rows += (uint64_t)im.cw[c] * im.ch[c]; }
         uint64_t npx = (uint64_t)im.wp * im.hp;
         im.row_off = rowt; rowt += im.hp; max_hp = std::max(max_hp, im.hp);
+        im.mc_first = mc_img.size(); im.mc_n = (uint32_t)((im.scan_len + 4095) >> 12); if (im.mc_n == 0) im.mc_n = 1;
+        mc_img.insert(mc_img.end(), im.mc_n, i);
         pix += align_up(npx, 64); dib += align_up(npx * 4, 256); blk += align_up((uint64_t)im.blk_xmax * im.blk_ymax, 64);
         mcu += align_up(im.nmcu, 32); seg += im.nseg;
         max_scan = std::max(max_scan, im.scan_len);
@@ -455,6 +459,9 @@ int jsgpu_batch_begin(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, 
     CK(ctx->d_misc.reserve((size_t)n * (8 + 8 + 4 + 4) + 64 + 64));
     CK(ctx->d_ex.reserve((size_t)n * sizeof(JsExResult)));
     ctx->rows_total = rowt; ctx->max_hp = max_hp; ctx->pv_done = false;
+    CK(ctx->d_mc.reserve(mc_img.size() * 4 + (mc_img.size() + 2) * 8 + 64));
+    if (!mc_img.empty()) CK(cudaMemcpyAsync(ctx->d_mc.p, mc_img.data(), mc_img.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->mc_total = (uint32_t)mc_img.size();
     CK(cudaMemcpyAsync(ctx->d_img.p, ctx->himg.data(), sizeof(DevImage) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     const size_t n_it = items.size(), n_lit = litems.size();
     items.insert(items.end(), items_np.begin(), items_np.end());                   // [all | without self-synchronised images]
@@ -497,6 +504,8 @@ int jsgpu_batch_begin(jsgpu_ctx* ctx, const jsgpu_image_desc* imgs, uint32_t n, 
     b.blk_y = (int16_t*)ctx->d_blk.p; b.blk_cb = b.blk_y + blk; b.blk_cr = b.blk_cb + blk;
     b.mcu_map = (uint32_t*)ctx->d_mcumap.p;
     b.histo = (uint32_t*)ctx->d_histo.p; b.stats = (int32_t*)ctx->d_stats.p;
+    b.mc_img = (uint32_t*)ctx->d_mc.p; b.mc_total = ctx->mc_total;
+    b.mc_state = (unsigned long long*)((uint8_t*)ctx->d_mc.p + (((size_t)ctx->mc_total * 4 + 63) & ~(size_t)63));
     b.bright_key = (unsigned long long*)ctx->d_misc.p; b.sum_y = b.bright_key + n; b.img_status = (uint32_t*)(b.sum_y + n); b.ovf_count = b.img_status + n;
     b.ph_nchg = b.ovf_count + 1; b.ex_flag = b.ph_nchg + PH_MAX_ROUNDS + 2; b.ex_res = (JsExResult*)ctx->d_ex.p;
     ctx->planned = true;

@@ -81,6 +81,8 @@ struct DevImage {
     uint64_t ph_first;              // ... first entry of this image in the slot arrays
     uint32_t cs_nslots;             // ... 4096-byte chunk slots of k_unstuff_long reserved for this image
     uint64_t cs_first;              // ... first entry of this image in the chunk arrays
+    uint64_t mc_first;              // first 4096-byte chunk of this image in the marker-scan chunk arrays (k_marker_scan2)
+    uint32_t mc_n, mc_pad;          // ... and how many it has
     uint64_t row_off;               // first entry of this image in the per-pixel-row array of the preview pass (jsgpu_preview.cu)
     uint64_t rt_off;                // first entry of this image in the row table (k_unstuff: unstuffed bytes before every 128-byte raw row of a long interval)
 };
@@ -103,6 +105,9 @@ struct DevBatch {
     unsigned long long* seg_uoff;   // where its unstuffed copy starts in ubits
     uint8_t*           ubits;       // unstuffed, 16-byte aligned, 0xFF-padded copies of all intervals
     uint32_t           nseg_total;
+    uint32_t*          mc_img;      // marker scan: image of every 4096-byte chunk (all images back to back)
+    unsigned long long* mc_state;   // ... its look-back word (status | end-of-scan seen | RST markers), zeroed per decode; [mc_total] = ticket counter
+    uint32_t           mc_total;
     uint32_t*          scan_end;    // [nimg] relative offset of the terminating marker
     uint32_t*          nseg_found;  // [nimg]
     // work lists

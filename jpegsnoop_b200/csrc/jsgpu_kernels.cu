@@ -15,6 +15,7 @@
 // colour math uses __fmul_rn/__fadd_rn/__fsub_rn/__fdiv_rn so no FMA contraction can happen.
 #include "jsgpu_internal.h"
 #include <cstdio>
+#include <cstdlib>
 #include <algorithm>
 
 #define FULL 0xffffffffu
@@ -117,10 +118,176 @@ __global__ void __launch_bounds__(MS_THREADS) k_marker_scan(DevBatch b)
     }
 }
 
-int js_launch_marker_scan(const DevBatch& b, uint64_t, cudaStream_t s)
+// ------------------------------------------------------------------------------------------------
+// K0 (chunked form, the default): the same result from ONE parallel pass.  A warp takes the next 4096-byte chunk of the batch (a
+// ticket, so chunks are taken in order), finds its RSTn markers and its first other marker with byte-parallel compares, and gets
+// the number of RST markers in the image's earlier chunks by decoupled look-back: every chunk publishes "my own count" at once and
+// "count of everything up to me" as soon as it knows it, and a chunk that needs its predecessors reads back through those words, 32
+// at a time, until it meets one that already holds a running total.  The combining rule carries the end of scan: markers behind
+// the first terminating marker do not count.  Replaces the CTA-per-image walk with its three barriers per 32 KB.
+// ------------------------------------------------------------------------------------------------
+#define MC_CHUNK 4096u
+#define MC_AGG   (1ull << 62)               // status: own aggregate published
+#define MC_PFX   (2ull << 62)               // status: inclusive prefix published
+#define MC_TERM  (1ull << 61)               // a terminating marker lies in the covered range
+__device__ __forceinline__ unsigned long long mc_combine(unsigned long long left, unsigned long long right)
+{
+    // (count, term) pairs, left range before right range: behind a terminator nothing counts
+    if (left & MC_TERM) return left & (MC_TERM | 0xffffffffull);
+    return ((left + right) & 0xffffffffull) | (right & MC_TERM);
+}
+__device__ __forceinline__ uint32_t mc_nib(uint32_t m) { return (((m & 0x01010101u) * 0x01020408u) >> 24) & 15u; }   // one flag per byte -> 4 bits
+
+__global__ void __launch_bounds__(256) k_marker_scan2(DevBatch b)
+{
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned long long* const ticket = b.mc_state + b.mc_total;
+    __shared__ uint32_t s_base;
+    for (;;) {
+        // one ticket per CTA and round (eight consecutive chunks, one per warp): a ticket per warp is 156 K atomics on one address
+        __syncthreads();
+        if (threadIdx.x == 0) s_base = (uint32_t)atomicAdd(ticket, 8ull);
+        __syncthreads();
+        if (s_base >= b.mc_total) return;
+        const uint32_t c = s_base + wid;
+        if (c >= b.mc_total) continue;
+        const uint32_t ii = b.mc_img[c];
+        const DevImage& im = b.img[ii];
+        const uint32_t ci = c - (uint32_t)im.mc_first;                  // chunk index inside the image
+        const uint8_t* p = b.bits + im.scan_off;
+        const uint32_t n = (uint32_t)im.scan_len, base = ci * MC_CHUNK;
+        // 16-byte pieces r*32 + lane of the chunk (coalesced), zero beyond the scan
+        uint4 v[8];
+        #pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const uint32_t off = base + (uint32_t)(r * 32 + lane) * 16;
+            v[r] = make_uint4(0, 0, 0, 0);
+            if (off + 16 <= n) v[r] = __ldg(reinterpret_cast<const uint4*>(p + off));
+            else if (off < n) { uint32_t w[4] = {0, 0, 0, 0}; for (int i = 0; i < 16; i++) if (off + i < n) w[i >> 2] |= (uint32_t)p[off + i] << (8 * (i & 3)); v[r] = make_uint4(w[0], w[1], w[2], w[3]); }
+        }
+        const uint32_t after = (base + MC_CHUNK < n) ? (uint32_t)p[base + MC_CHUNK] : 0u;      // the byte behind the chunk
+        // per piece: bit i of rst / trm = byte i is an FF followed by D0..D7 / by anything but 00, FF, D0..D7 (and not the last byte of the scan)
+        uint32_t rst[8], trm[8];
+        #pragma unroll
+        for (int r = 0; r < 8; r++) {
+            uint32_t nextw = __shfl_down_sync(FULL, v[r].x, 1);                                  // first word of the next piece
+            const uint32_t wrap = (r < 7) ? __shfl_sync(FULL, v[r < 7 ? r + 1 : 7].x, 0) : after;
+            if (lane == 31) nextw = wrap;
+            const uint32_t ws[5] = { v[r].x, v[r].y, v[r].z, v[r].w, nextw };
+            uint32_t mr = 0, mt = 0;
+            #pragma unroll
+            for (int wi = 0; wi < 4; wi++) {
+                const uint32_t w = ws[wi], nw = __byte_perm(w, ws[wi + 1], 0x4321);             // byte j = the byte after w's byte j
+                const uint32_t isff = __vcmpeq4(w, 0xFFFFFFFFu);
+                const uint32_t isd = __vcmpeq4(nw & 0xF8F8F8F8u, 0xD0D0D0D0u);
+                const uint32_t skip = isd | __vcmpeq4(nw, 0u) | __vcmpeq4(nw, 0xFFFFFFFFu);
+                mr |= mc_nib(isff & isd) << (4 * wi);
+                mt |= mc_nib(isff & ~skip) << (4 * wi);
+            }
+            // an FF that is the last byte of the scan has no marker byte
+            const uint32_t off = base + (uint32_t)(r * 32 + lane) * 16;
+            const uint32_t valid = (off + 16 < n) ? 0xFFFFu : (off + 1 < n) ? ((1u << (n - 1 - off)) - 1u) : 0u;
+            rst[r] = mr & valid; trm[r] = mt & valid;
+        }
+        // first terminating marker of the chunk (position inside the chunk), RST markers before it
+        uint32_t myterm = 0xffffffffu;
+        #pragma unroll
+        for (int r = 7; r >= 0; r--) if (trm[r]) myterm = (uint32_t)(r * 32 + lane) * 16 + (uint32_t)__ffs(trm[r]) - 1;
+        const uint32_t cterm = __reduce_min_sync(FULL, myterm);
+        uint32_t cntp[8], total = 0;                  // exclusive rank of each of my pieces among the chunk's RST markers
+        #pragma unroll
+        for (int r = 0; r < 8; r++) {
+            if (cterm != 0xffffffffu) {                // drop markers at / behind the terminator
+                const uint32_t pos0 = (uint32_t)(r * 32 + lane) * 16;
+                if (pos0 >= cterm) rst[r] = 0; else if (cterm - pos0 < 16) rst[r] &= (1u << (cterm - pos0)) - 1u;
+            }
+            const uint32_t cnt = __popc(rst[r]);
+            uint32_t inc = cnt;
+            #pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(FULL, inc, d); if (lane >= d) inc += y; }
+            cntp[r] = total + inc - cnt;
+            total += __shfl_sync(FULL, inc, 31);
+        }
+        // ---- look-back ----
+        const unsigned long long mine = (unsigned long long)total | ((cterm != 0xffffffffu) ? MC_TERM : 0ull);
+        unsigned long long excl = 0;                   // aggregate of the image's chunks before this one
+        volatile unsigned long long* const st = b.mc_state + im.mc_first;
+        if (ci == 0) { if (lane == 0) { __threadfence(); st[0] = mine | MC_PFX; } }
+        else {
+            if (lane == 0) { __threadfence(); st[ci] = mine | MC_AGG; }
+            int hi = (int)ci - 1;                      // window [hi-31, hi], lane l looks at hi - l
+            bool done = false;
+            while (!done) {
+                const int idx = hi - (int)lane;
+                unsigned long long w = 0;
+                do { w = (idx >= 0) ? st[idx] : MC_PFX; } while (__any_sync(FULL, (w >> 62) == 0));       // all 32 published (or before the image)
+                // nearest predecessor that holds a running total ends the walk; combine everything from there up to hi
+                const uint32_t pf = __ballot_sync(FULL, (w >> 62) == 2);
+                const int stop = pf ? (__ffs(pf) - 1) : 31;             // lane index (distance from hi) of the first prefix word
+                unsigned long long acc = (idx >= 0 && (int)lane <= stop) ? (w & (MC_TERM | 0xffffffffull)) : 0ull;
+                // ordered reduction: lane `stop` is leftmost ... lane 0 rightmost; fold right-to-left so that left ranges come first
+                #pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const unsigned long long o = __shfl_down_sync(FULL, acc, d);       // lanes further right? no: lane+d is further LEFT in the file
+                    if ((int)lane + d <= stop) acc = mc_combine(o, acc);
+                }
+                const unsigned long long win = __shfl_sync(FULL, acc, 0);               // chunks [hi-stop, hi]
+                excl = mc_combine(win, excl);
+                if (pf || hi - 31 <= 0) done = true; else hi -= 32;
+            }
+            if (lane == 0) { __threadfence(); st[ci] = mc_combine(excl, mine) | MC_PFX; }
+        }
+        excl = __shfl_sync(FULL, excl, 0);
+        const bool dead = (excl & MC_TERM) != 0;       // the scan ended in an earlier chunk: nothing here counts
+        const uint32_t found0 = (uint32_t)(excl & 0xffffffffull);
+        uint32_t* const seg_start = b.seg_start + im.seg_first;
+        uint32_t* const seg_end = b.seg_end + im.seg_first;
+        if (!dead) {
+            if (ci == 0 && lane == 0) seg_start[0] = 0;
+            #pragma unroll
+            for (int r = 0; r < 8; r++) {
+                uint32_t m = rst[r], rank = found0 + cntp[r];
+                while (m) {
+                    const uint32_t i = (uint32_t)__ffs(m) - 1; m &= m - 1;
+                    const uint32_t pos = base + (uint32_t)(r * 32 + lane) * 16 + i;
+                    if (rank < im.nseg) seg_end[rank] = pos;
+                    if (rank + 1 < im.nseg) seg_start[rank + 1] = pos + 2;
+                    if (((uint32_t)p[pos + 1] & 7u) != (rank & 7u)) atomicOr(&b.img_status[ii], 32u);    // out of sequence: the reference logs it (ImgDecode.cpp:1414-1424)
+                    rank++;
+                }
+            }
+            // the chunk that holds the end of the scan — the first terminating marker, or the last chunk when there is none — closes the image
+            const bool last = (ci + 1 == im.mc_n);
+            if ((cterm != 0xffffffffu || last) && lane == 0) {
+                const uint32_t found = found0 + total;
+                const uint32_t endpos = (cterm != 0xffffffffu) ? base + cterm : n;
+                const uint32_t nf = found + 1;
+                if (nf <= im.nseg) seg_end[nf - 1] = endpos;
+                for (uint32_t k = nf; k < im.nseg; k++) { seg_start[k] = endpos; seg_end[k] = endpos; }
+                b.scan_end[ii] = endpos;
+                b.nseg_found[ii] = nf;
+                b.stats[(size_t)ii * 16 + 11] = (int32_t)found;    // m_nRestartRead (ImgDecode.cpp:1414)
+                if (nf < im.nseg) atomicOr(&b.img_status[ii], 8u);
+                if (nf > im.nseg) atomicOr(&b.img_status[ii], 32u);
+            }
+        }
+    }
+}
+
+int js_launch_marker_scan(const DevBatch& b, uint64_t max_scan_len, cudaStream_t s)
 {
     if (b.nimg == 0) return 0;
-    k_marker_scan<<<b.nimg, MS_THREADS, 0, s>>>(b);
+    // Which form: the CTA-per-image walk is the faster one when there are many images of similar size (cfg2: 0.44 against 0.59 ms);
+    // the chunked pass wins when a few CTAs would do all the work — a single image (the drop-in class), fewer images than the
+    // device holds CTAs, or sizes so uneven that the largest images set the time (cfg4: 2.4 against 3.1 ms for stage A).
+    static const int mode = [] { const char* e = getenv("JSGPU_MARKER"); return e ? atoi(e) : 2; }();       // 0 = per image, 1 = chunked, 2 = choose
+    const bool uneven = (unsigned long long)max_scan_len * b.nimg > 2ull * b.bits_len;
+    const bool chunked = b.mc_total != 0 && (mode == 1 || (mode == 2 && (b.nimg < 2 * JS_B200_SMS || uneven)));
+    if (!chunked) { k_marker_scan<<<b.nimg, MS_THREADS, 0, s>>>(b); return 1; }
+    cudaMemsetAsync(b.mc_state, 0, ((size_t)b.mc_total + 1) * 8, s);
+    uint32_t grid = (b.mc_total + 7) / 8;
+    if (grid > JS_B200_SMS * 8u) grid = JS_B200_SMS * 8u;
+    k_marker_scan2<<<grid, 256, 0, s>>>(b);
     return 1;
 }
 
