@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1500 python bench.py 2> gpurun_out/bench_full5.err | tail -n 1 > gpurun_out/bench_full5.json
-cut -c1-200 gpurun_out/bench_full5.json; tail -n 3 gpurun_out/bench_full5.err
-(timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/r2h_launches_cfg2_bench.csv python bench.py --configs none --no-e2e --no-cpu --steps 2 --warmup 1 > gpurun_out/ncu_a.log 2>&1)
-awk -F'","' 'NR>2{print $5, $NF}' gpurun_out/r2h_launches_cfg2_bench.csv | sed -n 3,14p
-timeout 300 python bench.py --impl reference --steps 3 --warmup 1 2>/dev/null | tail -n 1 | cut -c1-400
+which compute-sanitizer || ls /usr/local/cuda/bin | grep -i sanit
+(timeout 900 compute-sanitizer --tool memcheck --error-exitcode 77 --print-limit 20 python -m pytest tests/test_gpu_parity.py -q -x -m gpu -k "single_image_dropin and auto and idct_fixed or unusual and auto or damaged_scans and auto_selfsync" > gpurun_out/san_a.log 2>&1; echo "rc_a=$?" >> gpurun_out/san_a.log)
+grep -E "ERROR SUMMARY|rc_a|passed|failed|Invalid|out of bounds" gpurun_out/san_a.log | head -20
+(timeout 600 compute-sanitizer --tool memcheck --error-exitcode 77 --print-limit 20 python -m pytest tests/test_gpu_preview.py tests/test_tiff_export.py -q -x -m gpu > gpurun_out/san_b.log 2>&1; echo "rc_b=$?" >> gpurun_out/san_b.log)
+grep -E "ERROR SUMMARY|rc_b|passed|failed|Invalid|out of bounds" gpurun_out/san_b.log | head -20
