@@ -65,6 +65,12 @@ struct OpCtx {
 	int bright_y,bright_cb,bright_cr; unsigned bright_r,bright_g,bright_b; int bright_mx,bright_my;
 	long avg_y; int avg_valid;
 	int nerr, nwarn;
+	/* channel preview / colour statistics (ID:2740-2741, 631-677; ImgDecode.h:218-280, 656-662) */
+	int cfg_hist_en, cfg_statclip_en; unsigned preview_mode; int shift_y,shift_cb,shift_cr; unsigned shift_mcu_x,shift_mcu_y;
+	unsigned warn_ycc_clip_num;
+	unsigned stat_clip[12];               /* PixelCcClip: Y,Cb,Cr,R,G,B x under,over */
+	int histo_rng[12][3]; unsigned histo_count;   /* PixelCcHisto in its member order: min,max,sum of pre-ranged YCC, ranged YCC, clipped RGB, pre-clip RGB */
+	unsigned cc_histo[3][128], histo_y_full[2048];
 };
 
 static void logerr(OpCtx* c)  { c->nerr++; }
@@ -127,6 +133,7 @@ static void op_reset(OpCtx* c)
 	c->avg_valid=0; c->avg_y=0;
 	free_outputs(c);
 	c->warn_bad_num=0;
+	c->warn_ycc_clip_num=0;                       /* ID:130 */
 }
 
 /* ID:286-306 ResetState (+ID:343-360, 373-406) */
@@ -149,7 +156,7 @@ OpCtx* op_create(void)
 	for (unsigned i=0;i<64;i++) kUnZigZag[kZigZag[i]]=i;
 	OpCtx* c=(OpCtx*)calloc(1,sizeof(OpCtx));
 	c->cfg_fixed=1; c->cfg_decode_ac=1; c->cfg_err_max=20;
-	c->mcu_w=c->mcu_h=1;
+	c->mcu_w=c->mcu_h=1; c->preview_mode=1;       /* PREVIEW_RGB, ID:220 */
 	op_reset(c); precalc_idct(c); gen_huff_mask(c); op_ResetState(c);
 	return c;
 }
@@ -398,11 +405,44 @@ static void ycc2rgb_fast_float(int py,int pcb,int pcr,uint8_t* fy,uint8_t* r,uin
 	*b=(vb<0)?0:(vb>255)?255:(uint8_t)vb;
 }
 
-/* ID:4619-4821 (PREVIEW_RGB, no preview shift, histograms off) */
+/* ID:4229-4601: ConvertYCCtoRGB + CapYccRange + CapRgbRange, the conversion taken when bHistoEn or bStatClipEn is set (ID:4745) */
+static void rng3(int v[3],int x) { if (x<v[0]) v[0]=x; if (x>v[1]) v[1]=x; v[2]=(int)((unsigned)v[2]+(unsigned)x); }
+static void ycc2rgb_full(OpCtx* c,int py,int pcb,int pcr,uint8_t* fy,uint8_t* fcb,uint8_t* fcr,uint8_t* r,uint8_t* g,uint8_t* b)
+{
+	const int he=c->cfg_hist_en;
+	if (he) {
+		rng3(c->histo_rng[0],py); rng3(c->histo_rng[1],pcb); rng3(c->histo_rng[2],pcr);                 /* ID:4238-4249 */
+		int hi=py; if (hi<-1024) hi=-1024; if (hi>1023) hi=1023; c->histo_y_full[hi+1024]++;            /* ID:4251-4260 */
+	}
+	int cur[3]={ (py+1024)/8, (pcb+1024)/8, (pcr+1024)/8 };                                            /* ID:4265-4267 */
+	if (he) { rng3(c->histo_rng[3],cur[0]); rng3(c->histo_rng[4],cur[1]); rng3(c->histo_rng[5],cur[2]); c->histo_count++; }   /* ID:4354-4365 */
+	for (int k=0;k<3;k++) {                                                                            /* ID:4368-4466: over, then under, per channel */
+		if (cur[k]>255) { if (c->warn_ycc_clip_num<10) { c->nwarn++; c->warn_ycc_clip_num++; c->stat_clip[k*2+1]++; if (c->warn_ycc_clip_num==10) c->nwarn++; } cur[k]=255; }
+		if (cur[k]<0)   { if (c->warn_ycc_clip_num<10) { c->nwarn++; c->warn_ycc_clip_num++; c->stat_clip[k*2]++;   if (c->warn_ycc_clip_num==10) c->nwarn++; } cur[k]=0; }
+	}
+	*fy=(uint8_t)cur[0]; *fcb=(uint8_t)cur[1]; *fcr=(uint8_t)cur[2];
+	const int y=cur[0]-128, cb=cur[1]-128, cr=cur[2]-128;
+	float cR=(float)0.299,cG=(float)0.587,cB=(float)0.114;
+	float vr=cr*(2-2*cR)+y;                                                                            /* ID:4289-4296 */
+	float vb=cb*(2-2*cB)+y;
+	float vg=(y-cB*vb-cR*vr)/cG;
+	vr+=128; vb+=128; vg+=128;
+	int lim[3]={ (int)vr,(int)vg,(int)vb };                                                            /* ID:4497-4499 */
+	if (he) { rng3(c->histo_rng[9],lim[0]); rng3(c->histo_rng[10],lim[1]); rng3(c->histo_rng[11],lim[2]); }
+	for (int k=0;k<3;k++) if (lim[k]<0)   { c->stat_clip[6+k*2]++;   lim[k]=0; }                         /* ID:4513-4545: the three underflows first */
+	for (int k=0;k<3;k++) if (lim[k]>255) { c->stat_clip[6+k*2+1]++; lim[k]=255; }
+	if (he) { rng3(c->histo_rng[6],lim[0]); rng3(c->histo_rng[7],lim[1]); rng3(c->histo_rng[8],lim[2]); }
+	*r=(uint8_t)lim[0]; *g=(uint8_t)lim[1]; *b=(uint8_t)lim[2];
+	if (he) { c->cc_histo[0][*r/2]++; c->cc_histo[1][*g/2]++; c->cc_histo[2][*b/2]++; }                /* ID:4313-4321 */
+}
+
+/* ID:4619-4821 with ChannelExtract (ID:4832-4876) and the YCC shift (ID:4733-4739) */
 static void calc_channel_preview_full(OpCtx* c)
 {
+	if (!c->dib) return;
 	unsigned w=c->blk_xmax*8, rowbytes=c->img_x*4; unsigned sum_y=0;
 	unsigned long npix=(unsigned long)(c->img_y+1)*(c->img_x+1);
+	const unsigned shift_ind=c->shift_mcu_y*(c->img_x/c->mcu_w)+c->shift_mcu_x;
 	c->bright_y=c->bright_cb=c->bright_cr=-32768;
 	for (unsigned py=0;py<c->img_y;py++) {
 		unsigned my=py/c->mcu_h, inv=(c->img_y-1)-py;
@@ -411,15 +451,39 @@ static void calc_channel_preview_full(OpCtx* c)
 			int ty=c->pix_y[ind], tcb=0, tcr=0;
 			if (c->nsos==3) { tcb=c->pix_cb[ind]; tcr=c->pix_cr[ind]; }
 			if (ty>c->bright_y) { c->bright_y=ty; c->bright_cb=tcb; c->bright_cr=tcr; c->bright_mx=(int)mx; c->bright_my=(int)my; }
-			uint8_t fy,r,g,b; ycc2rgb_fast_float(ty,tcb,tcr,&fy,&r,&g,&b);
+			if (my*(c->img_x/c->mcu_w)+mx>=shift_ind) { ty+=c->shift_y; tcb+=c->shift_cb; tcr+=c->shift_cr; }
+			uint8_t fy,fcb,fcr,r,g,b;
+			if (c->cfg_hist_en||c->cfg_statclip_en) ycc2rgb_full(c,ty,tcb,tcr,&fy,&fcb,&fcr,&r,&g,&b);
+			else {
+				ycc2rgb_fast_float(ty,tcb,tcr,&fy,&r,&g,&b);
+				int cb=tcb>>3, cr=tcr>>3; cb=(cb<-128)?-128:(cb>127)?127:cb; cr=(cr<-128)?-128:(cr>127)?127:cr;
+				fcb=(uint8_t)(cb+128); fcr=(uint8_t)(cr+128);
+			}
 			sum_y+=fy;
-			c->dib[byte+3]=0; c->dib[byte+2]=r; c->dib[byte+1]=g; c->dib[byte+0]=b;
+			uint8_t dr=r,dg=g,db=b;
+			switch (c->preview_mode) {                                                             /* ChannelExtract */
+			case 2: dr=fcr; dg=fy; db=fcb; break;
+			case 3: dg=db=r; break;  case 4: dr=db=g; break;  case 5: dr=dg=b; break;
+			case 6: dr=dg=db=fy; break; case 7: dr=dg=db=fcb; break; case 8: dr=dg=db=fcr; break;
+			default: break;
+			}
+			c->dib[byte+3]=0; c->dib[byte+2]=dr; c->dib[byte+1]=dg; c->dib[byte+0]=db;
 		}
 	}
 	{ uint8_t fy,r,g,b; ycc2rgb_fast_float(c->bright_y,c->bright_cb,c->bright_cr,&fy,&r,&g,&b); c->bright_r=r; c->bright_g=g; c->bright_b=b; }
 	if (npix==0) npix=1;
 	c->avg_y=(long)(sum_y/npix); c->avg_valid=1;
 }
+
+/* CSnoopConfig::bHistoEn / bStatClipEn; SetPreviewMode / SetPreviewYccOffset (ID:631-659): both recompute the preview */
+void op_config_histo(OpCtx* c,int hist_en,int statclip_en) { c->cfg_hist_en=hist_en; c->cfg_statclip_en=statclip_en; }
+void op_SetPreviewMode(OpCtx* c,unsigned mode) { c->preview_mode=mode; calc_channel_preview_full(c); }
+void op_SetPreviewYccOffset(OpCtx* c,unsigned mx,unsigned my,int y,int cb,int cr)
+{ c->shift_mcu_x=mx; c->shift_mcu_y=my; c->shift_y=y; c->shift_cb=cb; c->shift_cr=cr; calc_channel_preview_full(c); }
+void op_GetStatClip(OpCtx* c,uint32_t* o) { memcpy(o,c->stat_clip,sizeof c->stat_clip); }
+void op_GetHistoRanges(OpCtx* c,int32_t* o,uint32_t* n) { memcpy(o,c->histo_rng,sizeof c->histo_rng); *n=c->histo_count; }
+void op_GetCcHisto(OpCtx* c,unsigned ch,uint32_t* o) { memcpy(o,c->cc_histo[ch<3?ch:0],sizeof c->cc_histo[0]); }
+void op_GetHistoYFull(OpCtx* c,uint32_t* o) { memcpy(o,c->histo_y_full,sizeof c->histo_y_full); }
 
 /* ID:2723-3745 */
 void op_DecodeScanImg(OpCtx* c,unsigned start,int display,int quiet)
@@ -463,6 +527,10 @@ void op_DecodeScanImg(OpCtx* c,unsigned start,int display,int quiet)
 		if (c->dht_size[1][c->dht_sel[1][k]]==0) dht_ready=0;
 	}
 	if (!dht_ready) { logerr(c); return; }
+	if (display) {                                /* ID:3144-3156 */
+		memset(c->stat_clip,0,sizeof c->stat_clip); memset(c->histo_rng,0,sizeof c->histo_rng); c->histo_count=0;
+		memset(c->cc_histo,0,sizeof c->cc_histo); memset(c->histo_y_full,0,sizeof c->histo_y_full);
+	}
 	unsigned dcy=(unsigned)c->dht_sel[0][1], acy=(unsigned)c->dht_sel[1][1];
 	unsigned dccb=(unsigned)c->dht_sel[0][2], accb=(unsigned)c->dht_sel[1][2];
 	unsigned dccr=(unsigned)c->dht_sel[0][3], accr=(unsigned)c->dht_sel[1][3];

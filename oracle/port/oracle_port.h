@@ -58,6 +58,14 @@ int     op_setup_jpeg(OpCtx*, const uint8_t* data, uint64_t n);
 /* CPU baseline pool (OpenMP): returns seconds */
 double  op_bench(const uint8_t* const* datas, const uint64_t* lens, int n, int threads, int reps,
                  int idct_fixed, int* err_lines);
+/* channel preview / colour statistics (ImgDecode.cpp:631-677, 4229-4601, 4619-4876) */
+void op_config_histo(OpCtx*,int hist_en,int statclip_en);
+void op_SetPreviewMode(OpCtx*,unsigned mode);
+void op_SetPreviewYccOffset(OpCtx*,unsigned mcu_x,unsigned mcu_y,int y,int cb,int cr);
+void op_GetStatClip(OpCtx*,uint32_t* out12);
+void op_GetHistoRanges(OpCtx*,int32_t* out36,uint32_t* count);
+void op_GetCcHisto(OpCtx*,unsigned chan,uint32_t* out128);
+void op_GetHistoYFull(OpCtx*,uint32_t* out2048);
 #ifdef __cplusplus
 }
 #endif

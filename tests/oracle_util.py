@@ -100,30 +100,32 @@ class Oracle:
         self.lib.ref_err_line.restype = C.c_char_p; self.lib.ref_err_line.argtypes = [C.c_void_p, C.c_int]
         return [self.lib.ref_err_line(self.ctx, i).decode("latin-1") for i in range(self._f("num_err_lines")(self.ctx))]
 
-    # --- channel preview / colour statistics (compiled reference only) -----------------------------
+    # --- channel preview / colour statistics (both oracles; the histogram bitmaps and log lines: compiled reference only) ------
     def config_histo(self, histo_en=False, statclip_en=False, dump_histo_y=False):
-        assert self.kind != "port"
-        self.lib.ref_config_histo(int(histo_en), int(statclip_en), int(dump_histo_y))
+        if self.kind == "port":
+            self.lib.op_config_histo.argtypes = [C.c_void_p, C.c_int, C.c_int]; self.lib.op_config_histo(self.ctx, int(histo_en), int(statclip_en))
+        else:
+            self.lib.ref_config_histo(int(histo_en), int(statclip_en), int(dump_histo_y))
 
     def set_detail_vlc(self, detail, x=0, y=0, n=1):
+        assert self.kind != "port"
         self.lib.ref_SetDetailVlc.argtypes = [C.c_void_p, C.c_int, C.c_uint, C.c_uint, C.c_uint]; self.lib.ref_SetDetailVlc(self.ctx, int(detail), x, y, n)
 
     def set_preview_mode(self, mode):
-        self.lib.ref_SetPreviewMode.argtypes = [C.c_void_p, C.c_uint]; self.lib.ref_SetPreviewMode(self.ctx, mode)
+        f = self._f("SetPreviewMode"); f.argtypes = [C.c_void_p, C.c_uint]; f(self.ctx, mode)
 
     def set_ycc_offset(self, mx, my, y, cb, cr):
-        self.lib.ref_SetPreviewYccOffset.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_int]
-        self.lib.ref_SetPreviewYccOffset(self.ctx, mx, my, y, cb, cr)
+        f = self._f("SetPreviewYccOffset"); f.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_int]
+        f(self.ctx, mx, my, y, cb, cr)
 
     def colour_stats(self):
-        L = self.lib
-        clip = np.zeros(12, np.uint32); L.ref_GetStatClip.argtypes = [C.c_void_p, C.c_void_p]; L.ref_GetStatClip(self.ctx, clip.ctypes.data)
+        clip = np.zeros(12, np.uint32); f = self._f("GetStatClip"); f.argtypes = [C.c_void_p, C.c_void_p]; f(self.ctx, clip.ctypes.data)
         rng = np.zeros(36, np.int32); n = C.c_uint32()
-        L.ref_GetHistoRanges.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]; L.ref_GetHistoRanges(self.ctx, rng.ctypes.data, C.byref(n))
-        cc = np.zeros((3, 128), np.uint32); L.ref_GetCcHisto.argtypes = [C.c_void_p, C.c_uint, C.c_void_p]
+        f = self._f("GetHistoRanges"); f.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]; f(self.ctx, rng.ctypes.data, C.byref(n))
+        cc = np.zeros((3, 128), np.uint32); f = self._f("GetCcHisto"); f.argtypes = [C.c_void_p, C.c_uint, C.c_void_p]
         for c in range(3):
-            L.ref_GetCcHisto(self.ctx, c, cc[c].ctypes.data)
-        yh = np.zeros(2048, np.uint32); L.ref_GetHistoYFull.argtypes = [C.c_void_p, C.c_void_p]; L.ref_GetHistoYFull(self.ctx, yh.ctypes.data)
+            f(self.ctx, c, cc[c].ctypes.data)
+        yh = np.zeros(2048, np.uint32); f = self._f("GetHistoYFull"); f.argtypes = [C.c_void_p, C.c_void_p]; f(self.ctx, yh.ctypes.data)
         return {"clip": clip, "ranges": rng, "count": int(n.value), "cc_histo": cc, "y_histo": yh}
 
     def histo_dib(self, which):

@@ -67,3 +67,43 @@ def test_synth_generator_is_deterministic_and_decodable(built):
     for i, sp in enumerate(specs):
         one = synth.encode(sp["width"], sp["height"], sp["subsampling"], sp["quality"], sp["restart_interval"], sp["optimize"], sp["seed"])
         assert buf[int(offs[i]):int(offs[i + 1])].tobytes() == one
+
+
+@pytest.mark.skipif(not ref_available("fixed"), reason="compiled reference not present")
+def test_port_preview_and_colour_statistics_match_compiled_reference(built):
+    """The C port's restatement of ConvertYCCtoRGB / CapYccRange / CapRgbRange, ChannelExtract and the YCC shift (ImgDecode.cpp:
+    4229-4601, 4733-4739, 4832-4876) against the compiled reference: DIB, average luminance, m_sHisto, m_sStatClip (with its
+    ten-note cap), m_anCcHisto_*, m_anHistoYFull — on healthy images and on one whose DC drifts out of range."""
+    cases = JC.small_cases()
+
+    def flipped(j, n, seed):
+        r = np.random.default_rng(seed)
+        a = bytearray(j); lo = j.index(b"\xff\xda") + 14
+        for p in r.integers(lo, len(j) - 2, n):
+            a[p] ^= 1 << int(r.integers(0, 8))
+        return bytes(a)
+    todo = [cases[0], cases[1], cases[7], ("flip3_444", flipped(cases[0][1], 3, 3))]
+    for flags in ((True, False), (False, True), (False, False)):
+        ref = Oracle("ref_fixed"); port = Oracle("port", idct_fixed=True)
+        try:
+            ref.config_histo(flags[0], flags[1], False); port.config_histo(flags[0], flags[1])
+            for name, j in todo:
+                want = ref.decode(j); got = port.decode(j)
+                if JC.compare(want, got, what=("pix_y", "pix_cb", "pix_cr")):
+                    continue                       # a damaged stream the port does not follow: nothing to say about the colour pass
+                steps = [None, ("mode", 2), ("mode", 6), ("shift", (1, 1, 200, -90, 40)), ("mode", 8), ("mode", 1), ("shift", (0, 0, 0, 0, 0))]
+                for st in steps:
+                    if st and st[0] == "mode":
+                        ref.set_preview_mode(st[1]); port.set_preview_mode(st[1])
+                    elif st:
+                        ref.set_ycc_offset(*st[1]); port.set_ycc_offset(*st[1])
+                    assert np.array_equal(ref.bitmap(), port.bitmap()), (name, flags, st)
+                    ws = np.zeros(12, np.int32); ref._f("stats")(ref.ctx, ws.ctypes.data)
+                    gs = np.zeros(12, np.int32); port._f("stats")(port.ctx, gs.ctypes.data)
+                    assert np.array_equal(ws[:10], gs[:10]), (name, flags, st, ws, gs)
+                    a, b = ref.colour_stats(), port.colour_stats()
+                    for k in ("clip", "ranges", "cc_histo", "y_histo"):
+                        assert np.array_equal(a[k], b[k]), (name, flags, st, k)
+                    assert a["count"] == b["count"], (name, flags, st)
+        finally:
+            ref.config_histo(False, False, False); ref.close(); port.close()
